@@ -1,0 +1,785 @@
+// api.cu — the C ABI of lcb200 (include/lcb200.h): context, parameter tables, host<->device staging
+// and the composition of the sampler / ring kernels into the reference's scheme operations.
+// No CPU fallback: without an sm_100 device lcb_ctx_create fails with LCB_ERR_NO_DEVICE.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/lcb200.h"
+#include "engine.h"
+
+using namespace lcb;
+
+struct lcb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int secpar = 0, q = 0, d = 0, l = 0, rou = 0;
+    RingCtx ring{};
+    NttTables* d_tab = nullptr;
+    uint32_t* d_a_hat = nullptr;
+    bool has_key_ch = false;
+    std::string last_error;
+    int64_t launches = 0;
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+int fail(lcb_ctx* c, int status, const std::string& what) {
+    if (c) c->last_error = what;
+    return status;
+}
+
+int fail_cuda(lcb_ctx* c, cudaError_t e, const char* what) {
+    return fail(c, e == cudaErrorMemoryAllocation ? LCB_ERR_OOM : LCB_ERR_CUDA,
+                std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CK(c, call)                                              \
+    do {                                                         \
+        cudaError_t e_ = (call);                                 \
+        if (e_ != cudaSuccess) return fail_cuda((c), e_, #call); \
+    } while (0)
+
+uint64_t powmod(uint64_t b, uint64_t e, uint64_t q) {
+    uint64_t r = 1;
+    b %= q;
+    while (e) {
+        if (e & 1) r = r * b % q;
+        b = b * b % q;
+        e >>= 1;
+    }
+    return r;
+}
+
+bool is_prime(int v) {
+    if (v < 2) return false;
+    for (int f = 2; (int64_t)f * f <= v; ++f)
+        if (v % f == 0) return false;
+    return true;
+}
+
+uint32_t bitrev8(uint32_t v) {
+    uint32_t r = 0;
+    for (int i = 0; i < 8; ++i) r |= ((v >> i) & 1u) << (7 - i);
+    return r;
+}
+
+uint32_t shoup(uint32_t w, uint32_t q) { return (uint32_t)(((uint64_t)w << 32) / q); }
+
+int ceil_log2(int v) {
+    int c = 0;
+    while ((1 << c) < v) ++c;
+    return c;
+}
+
+bool on_device(const void* p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// Per-call staging of caller buffers: device pointers pass through, host pointers are mirrored in
+// stream-ordered device scratch (copied in before the kernels, copied back + synchronised after).
+class Staging {
+  public:
+    explicit Staging(lcb_ctx* c) : c_(c) {}
+    ~Staging() {
+        for (void* p : owned_) cudaFreeAsync(p, c_->stream);
+    }
+    cudaError_t alloc(void** out, size_t bytes) {
+        *out = nullptr;
+        if (bytes == 0) bytes = 16;
+        cudaError_t e = cudaMallocAsync(out, bytes, c_->stream);
+        if (e == cudaSuccess) owned_.push_back(*out);
+        return e;
+    }
+    template <typename T>
+    cudaError_t in(const T** dev, const T* p, size_t count) {
+        *dev = p;
+        if (p == nullptr || count == 0 || on_device(p)) return cudaSuccess;
+        void* d = nullptr;
+        cudaError_t e = alloc(&d, count * sizeof(T));
+        if (e != cudaSuccess) return e;
+        host_touched_ = true;
+        *dev = static_cast<const T*>(d);
+        return cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, c_->stream);
+    }
+    template <typename T>
+    cudaError_t out(T** dev, T* p, size_t count) {
+        *dev = p;
+        if (p == nullptr || count == 0 || on_device(p)) return cudaSuccess;
+        void* d = nullptr;
+        cudaError_t e = alloc(&d, count * sizeof(T));
+        if (e != cudaSuccess) return e;
+        host_touched_ = true;
+        *dev = static_cast<T*>(d);
+        back_.push_back({p, d, count * sizeof(T)});
+        return cudaSuccess;
+    }
+    cudaError_t finish() {
+        for (auto& b : back_) {
+            cudaError_t e = cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, c_->stream);
+            if (e != cudaSuccess) return e;
+        }
+        back_.clear();
+        if (host_touched_) return cudaStreamSynchronize(c_->stream);
+        return cudaSuccess;
+    }
+
+  private:
+    struct Back { void* host; void* dev; size_t bytes; };
+    lcb_ctx* c_;
+    std::vector<void*> owned_;
+    std::vector<Back> back_;
+    bool host_touched_ = false;
+};
+
+// read off[n] (total blob length) whether off is host or device memory
+cudaError_t last_offset(lcb_ctx* c, const int64_t* off, int64_t n, int64_t* total) {
+    if (on_device(off)) {
+        cudaError_t e = cudaMemcpyAsync(total, off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream);
+        if (e != cudaSuccess) return e;
+        return cudaStreamSynchronize(c->stream);
+    }
+    *total = off[n];
+    return cudaSuccess;
+}
+
+int fill_sampler(lcb_ctx* c, SamplerArgs& a, const char* salt, const char* suffix, int bd, int wt, int vec_len) {
+    if (bd < 1 || bd > 32767 || wt < 1 || wt > D || vec_len < 1) return LCB_ERR_INVALID;
+    std::string s = std::string(salt ? salt : "") + (suffix ? suffix : "");
+    if ((int)s.size() > SALT_BYTES) return LCB_ERR_INVALID;
+    std::memset(a.salt, 0, sizeof(a.salt));
+    std::memcpy(a.salt, s.data(), s.size());
+    a.salt_len = (int)s.size();
+    a.secpar = c->secpar;
+    a.bd = bd;
+    a.wt = wt;
+    a.vec_len = vec_len;
+    a.idx_bits = LOGD + c->secpar;
+    const int btd = ceil_log2(bd) + 1 + c->secpar;
+    a.mag_bits = btd - 1;
+    const int64_t bits = (int64_t)LOGD + (int64_t)(wt - 1) * a.idx_bits + (int64_t)wt * btd;
+    a.pad_bits = (int)(8 * ((bits + 7) / 8) - bits);
+    a.shared_msg = 0;
+    a.shared_len = 0;
+    a.index_first = 0;
+    a.out_dense = nullptr;
+    a.dense_stride = 0;
+    a.out_pairs = nullptr;
+    return LCB_OK;
+}
+
+std::string salt_of(const char (&s)[LCB_SALT_MAX]) { return std::string(s, strnlen(s, LCB_SALT_MAX)); }
+
+// challenge pairs for n ragged hash inputs (device pointers)
+int run_challenge(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* d_msg, const int64_t* d_off, int64_t n,
+                  int16_t* d_pairs) {
+    SamplerArgs a{};
+    int st = fill_sampler(c, a, salt_of(sch->ch_salt).c_str(), nullptr, sch->ch_bd, sch->ch_wt, 1);
+    if (st != LCB_OK) return fail(c, st, "bad challenge parameters");
+    a.msgs = d_msg;
+    a.off = d_off;
+    a.n = n;
+    a.out_pairs = d_pairs;
+    CK(c, launch_sampler(a, c->stream));
+    c->launches += 1;
+    return LCB_OK;
+}
+
+int run_agg_coefs(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* d_agmsg, int64_t agmsg_len, int64_t first,
+                  int64_t count, int16_t* d_pairs) {
+    if (sch->ag_wt != 1) return fail(c, LCB_ERR_INVALID, "only ag_wt == 1 (monomial aggregation coefficients) is supported");
+    SamplerArgs a{};
+    int st = fill_sampler(c, a, salt_of(sch->ag_salt).c_str(), nullptr, sch->ag_bd, sch->ag_wt, 1);
+    if (st != LCB_OK) return fail(c, st, "bad aggregation parameters");
+    if (a.salt_len + 20 > SALT_BYTES) return fail(c, LCB_ERR_INVALID, "ag_salt too long");
+    a.msgs = d_agmsg;
+    a.off = nullptr;
+    a.n = count;
+    a.shared_msg = 1;
+    a.shared_len = agmsg_len;
+    a.index_first = first;
+    a.out_pairs = d_pairs;
+    CK(c, launch_agg_coefs(a, c->stream));
+    c->launches += 1;
+    return LCB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* lcb_strerror(int status) {
+    switch (status) {
+        case LCB_OK: return "ok";
+        case LCB_ERR_INVALID: return "invalid argument or unsupported parameter set";
+        case LCB_ERR_CUDA: return "CUDA runtime error";
+        case LCB_ERR_NO_DEVICE: return "no sm_100 CUDA device (lcb200 has no CPU fallback)";
+        case LCB_ERR_NO_KEY_CH: return "key_ch not set (call lcb_set_key_ch)";
+        case LCB_ERR_OOM: return "out of device memory";
+        default: return "unknown lcb status";
+    }
+}
+
+const char* lcb_last_error(const lcb_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_create_error.c_str(); }
+
+int lcb_version(void) { return 100; }
+
+int lcb_ctx_create(lcb_ctx** out, int device, int secpar, int q, int d, int l) {
+    if (!out) return LCB_ERR_INVALID;
+    *out = nullptr;
+    g_create_error.clear();
+    if (d != D || l < 1 || l > 64 || secpar < 1 || secpar > 512 || q < 3 || q >= 65536 || !is_prime(q) ||
+        q % (2 * d) != 1) {
+        g_create_error = "supported: d == 256, prime q < 65536 with q % 512 == 1, 1 <= l <= 64, 1 <= secpar <= 512";
+        return LCB_ERR_INVALID;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        g_create_error = "CUDA device not available";
+        return LCB_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+        cudaGetLastError();
+        g_create_error = "device is not sm_100 (B200)";
+        return LCB_ERR_NO_DEVICE;
+    }
+    lcb_ctx* c = new (std::nothrow) lcb_ctx();
+    if (!c) return LCB_ERR_OOM;
+    c->device = device;
+    c->secpar = secpar;
+    c->q = q;
+    c->d = d;
+    c->l = l;
+    auto bail = [&](cudaError_t e, const char* what) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
+        lcb_ctx_destroy(c);
+        return LCB_ERR_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    c->own_stream = true;
+
+    // ---- tables: psi = least element of order exactly 2d (LatticeParameters.rou in lattice_algebra)
+    const uint32_t uq = (uint32_t)q;
+    uint32_t psi = 2;
+    while (!(powmod(psi, 2 * d, uq) == 1 && powmod(psi, d, uq) != 1)) ++psi;
+    c->rou = (int)psi;
+    std::vector<NttTables> host(1);
+    NttTables& t = host[0];
+    for (uint32_t k = 0; k < 256; ++k) {
+        uint32_t w = (uint32_t)powmod(psi, bitrev8(k), uq);
+        uint32_t iw = (uint32_t)powmod(w, uq - 2, uq);
+        t.w[k] = w;
+        t.ws[k] = shoup(w, uq);
+        t.iw[k] = iw;
+        t.iws[k] = shoup(iw, uq);
+        t.oddexp[k] = (uint16_t)(2 * bitrev8(k) + 1);
+    }
+    for (uint32_t e2 = 0; e2 < 512; ++e2) {
+        t.pw[e2] = (uint32_t)powmod(psi, e2, uq);
+        t.pws[e2] = shoup(t.pw[e2], uq);
+    }
+    ModQ& m = c->ring.m;
+    m.q = uq;
+    m.negq = (uint32_t)(0u - uq);
+    m.barrett = 0xFFFFFFFFu / uq;
+    m.cq = ((32768u + uq - 1) / uq) * uq;
+    m.cq2 = ((65536u + 2 * uq + uq - 1) / uq) * uq;
+    m.half = (uq - 1) / 2;
+    m.dinv = (uint32_t)powmod((uint32_t)d, uq - 2, uq);
+    m.dinv_s = shoup(m.dinv, uq);
+    for (int k = 0; k < 16; ++k) {
+        c->ring.sc.w[k] = t.w[k];
+        c->ring.sc.ws[k] = t.ws[k];
+        c->ring.sc.iw[k] = t.iw[k];
+        c->ring.sc.iws[k] = t.iws[k];
+    }
+    if ((e = cudaMalloc(&c->d_tab, sizeof(NttTables))) != cudaSuccess) return bail(e, "cudaMalloc tables");
+    if ((e = cudaMemcpy(c->d_tab, &t, sizeof(NttTables), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy tables");
+    if ((e = cudaMalloc(&c->d_a_hat, (size_t)l * D * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc key_ch");
+    c->ring.tab = c->d_tab;
+    c->ring.a_hat = c->d_a_hat;
+    c->ring.l = l;
+    c->ring.num_sms = prop.multiProcessorCount;
+    *out = c;
+    return LCB_OK;
+}
+
+int lcb_ctx_destroy(lcb_ctx* c) {
+    if (!c) return LCB_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->d_tab) cudaFree(c->d_tab);
+    if (c->d_a_hat) cudaFree(c->d_a_hat);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return LCB_OK;
+}
+
+int lcb_ctx_set_stream(lcb_ctx* c, void* cuda_stream) {
+    if (!c) return LCB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    c->stream = static_cast<cudaStream_t>(cuda_stream);
+    c->own_stream = false;
+    return LCB_OK;
+}
+
+int lcb_synchronize(lcb_ctx* c) {
+    if (!c) return LCB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return LCB_OK;
+}
+
+int lcb_ctx_root_of_unity(const lcb_ctx* c) { return c ? c->rou : LCB_ERR_INVALID; }
+
+int64_t lcb_launch_count(const lcb_ctx* c) { return c ? c->launches : 0; }
+
+int lcb_set_key_ch(lcb_ctx* c, const int16_t* key_ch_coef) {
+    if (!c || !key_ch_coef) return LCB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    Staging sg(c);
+    const int16_t* d_in;
+    CK(c, sg.in(&d_in, key_ch_coef, (size_t)c->l * D));
+    uint16_t* d_ntt;
+    CK(c, sg.alloc((void**)&d_ntt, (size_t)c->l * D * sizeof(uint16_t)));
+    CK(c, launch_ntt_fwd(c->ring, d_in, c->l, d_ntt, c->stream));
+    c->launches += 1;
+    // widen to uint32 on the host side of the stream (tiny: l*256 values, once per parameter set)
+    std::vector<uint16_t> h16((size_t)c->l * D);
+    CK(c, cudaMemcpyAsync(h16.data(), d_ntt, h16.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    std::vector<uint32_t> h32(h16.begin(), h16.end());
+    CK(c, cudaMemcpyAsync(c->d_a_hat, h32.data(), h32.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->has_key_ch = true;
+    CK(c, sg.finish());
+    return LCB_OK;
+}
+
+int lcb_shake256_batch(lcb_ctx* c, const uint8_t* in, const int64_t* in_off, int64_t n, uint8_t* out,
+                       int64_t out_len) {
+    if (!c || !in_off || !out || n < 0 || out_len < 0) return LCB_ERR_INVALID;
+    if (n == 0 || out_len == 0) return LCB_OK;
+    CK(c, cudaSetDevice(c->device));
+    int64_t total = 0;
+    CK(c, last_offset(c, in_off, n, &total));
+    Staging sg(c);
+    const uint8_t* d_in;
+    const int64_t* d_off;
+    uint8_t* d_out;
+    CK(c, sg.in(&d_in, in, (size_t)total));
+    CK(c, sg.in(&d_off, in_off, (size_t)n + 1));
+    CK(c, sg.out(&d_out, out, (size_t)(n * out_len)));
+    CK(c, launch_shake256(d_in, d_off, n, d_out, out_len, c->stream));
+    c->launches += 1;
+    CK(c, sg.finish());
+    return LCB_OK;
+}
+
+int lcb_hash2polyvec_batch(lcb_ctx* c, const char* salt, const uint8_t* msgs, const int64_t* msg_off, int64_t n,
+                           int bd, int wt, int vec_len, int16_t* out_dense, int16_t* out_pairs) {
+    if (!c || !msg_off || n < 0) return LCB_ERR_INVALID;
+    if (n == 0) return LCB_OK;
+    CK(c, cudaSetDevice(c->device));
+    SamplerArgs a{};
+    int st = fill_sampler(c, a, salt, nullptr, bd, wt, vec_len);
+    if (st != LCB_OK) return fail(c, st, "bad sampler parameters");
+    int64_t total = 0;
+    CK(c, last_offset(c, msg_off, n, &total));
+    Staging sg(c);
+    CK(c, sg.in(&a.msgs, msgs, (size_t)total));
+    CK(c, sg.in(&a.off, msg_off, (size_t)n + 1));
+    CK(c, sg.out(&a.out_dense, out_dense, (size_t)n * vec_len * D));
+    CK(c, sg.out(&a.out_pairs, out_pairs, (size_t)n * vec_len * wt * 2));
+    a.n = n;
+    a.dense_stride = (int64_t)vec_len * D;
+    if (a.out_dense && wt < D) CK(c, cudaMemsetAsync(a.out_dense, 0, (size_t)n * vec_len * D * sizeof(int16_t), c->stream));
+    CK(c, launch_sampler(a, c->stream));
+    c->launches += 1;
+    CK(c, sg.finish());
+    return LCB_OK;
+}
+
+int lcb_ntt_fwd_batch(lcb_ctx* c, const int16_t* coef, int64_t npoly, uint16_t* ntt) {
+    if (!c || !coef || !ntt || npoly < 0) return LCB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    Staging sg(c);
+    const int16_t* d_in;
+    uint16_t* d_out;
+    CK(c, sg.in(&d_in, coef, (size_t)npoly * D));
+    CK(c, sg.out(&d_out, ntt, (size_t)npoly * D));
+    CK(c, launch_ntt_fwd(c->ring, d_in, npoly, d_out, c->stream));
+    c->launches += 1;
+    CK(c, sg.finish());
+    return LCB_OK;
+}
+
+int lcb_ntt_inv_batch(lcb_ctx* c, const uint16_t* ntt, int64_t npoly, int16_t* coef) {
+    if (!c || !coef || !ntt || npoly < 0) return LCB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    Staging sg(c);
+    const uint16_t* d_in;
+    int16_t* d_out;
+    CK(c, sg.in(&d_in, ntt, (size_t)npoly * D));
+    CK(c, sg.out(&d_out, coef, (size_t)npoly * D));
+    CK(c, launch_ntt_inv(c->ring, d_in, npoly, d_out, c->stream));
+    c->launches += 1;
+    CK(c, sg.finish());
+    return LCB_OK;
+}
+
+int lcb_poly_mul_batch(lcb_ctx* c, const int16_t* a, const int16_t* b, int64_t npoly, int16_t* out) {
+    if (!c || !a || !b || !out || npoly < 0) return LCB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    Staging sg(c);
+    const int16_t *d_a, *d_b;
+    int16_t* d_out;
+    CK(c, sg.in(&d_a, a, (size_t)npoly * D));
+    CK(c, sg.in(&d_b, b, (size_t)npoly * D));
+    CK(c, sg.out(&d_out, out, (size_t)npoly * D));
+    CK(c, launch_poly_mul(c->ring, d_a, d_b, npoly, d_out, c->stream));
+    c->launches += 1;
+    CK(c, sg.finish());
+    return LCB_OK;
+}
+
+int lcb_lm_keygen_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* seeds, const int64_t* seed_off, int64_t n,
+                        int16_t* sk_coef, uint16_t* sk_ntt, uint16_t* vk_ntt, int16_t* vk_coef) {
+    if (!c || !sch || !seed_off || n < 0) return LCB_ERR_INVALID;
+    if (!c->has_key_ch) return fail(c, LCB_ERR_NO_KEY_CH, "lcb_lm_keygen_batch before lcb_set_key_ch");
+    if (n == 0) return LCB_OK;
+    CK(c, cudaSetDevice(c->device));
+    const int l = c->l;
+    SamplerArgs left{}, right{};
+    int st = fill_sampler(c, left, salt_of(sch->sk_salt).c_str(), "LEFT", sch->sk_bd, sch->sk_wt, l);
+    if (st == LCB_OK) st = fill_sampler(c, right, salt_of(sch->sk_salt).c_str(), "RIGHT", sch->sk_bd, sch->sk_wt, l);
+    if (st != LCB_OK) return fail(c, st, "bad signing-key parameters");
+    int64_t total = 0;
+    CK(c, last_offset(c, seed_off, n, &total));
+    Staging sg(c);
+    const uint8_t* d_seeds;
+    const int64_t* d_off;
+    int16_t *d_sk_coef, *d_vk_coef;
+    uint16_t *d_sk_ntt, *d_vk_ntt;
+    CK(c, sg.in(&d_seeds, seeds, (size_t)total));
+    CK(c, sg.in(&d_off, seed_off, (size_t)n + 1));
+    CK(c, sg.out(&d_sk_coef, sk_coef, (size_t)n * 2 * l * D));
+    CK(c, sg.out(&d_sk_ntt, sk_ntt, (size_t)n * 2 * l * D));
+    CK(c, sg.out(&d_vk_ntt, vk_ntt, (size_t)n * 2 * D));
+    CK(c, sg.out(&d_vk_coef, vk_coef, (size_t)n * 2 * D));
+    // Signing keys pass through HBM in coefficient form between the sampler and the row-vector
+    // product; when the caller does not want them, a bounded scratch chunk is reused.
+    const int64_t chunk = d_sk_coef ? n : (n < 32768 ? n : 32768);
+    int16_t* scratch = nullptr;
+    if (!d_sk_coef) CK(c, sg.alloc((void**)&scratch, (size_t)chunk * 2 * l * D * sizeof(int16_t)));
+    for (int64_t start = 0; start < n; start += chunk) {
+        const int64_t cnt = (n - start < chunk) ? n - start : chunk;
+        int16_t* skc = d_sk_coef ? d_sk_coef + start * 2 * l * D : scratch;
+        if (sch->sk_wt < D) CK(c, cudaMemsetAsync(skc, 0, (size_t)cnt * 2 * l * D * sizeof(int16_t), c->stream));
+        left.msgs = right.msgs = d_seeds;
+        left.off = right.off = d_off + start;
+        left.n = right.n = cnt;
+        left.dense_stride = right.dense_stride = (int64_t)2 * l * D;
+        left.out_dense = skc;
+        right.out_dense = skc + (int64_t)l * D;
+        CK(c, launch_sampler(left, c->stream));
+        CK(c, launch_sampler(right, c->stream));
+        CK(c, launch_matvec(c->ring, skc, cnt * 2, d_sk_ntt ? d_sk_ntt + start * 2 * l * D : nullptr,
+                            d_vk_ntt ? d_vk_ntt + start * 2 * D : nullptr,
+                            d_vk_coef ? d_vk_coef + start * 2 * D : nullptr, c->stream));
+        c->launches += 3;
+    }
+    CK(c, sg.finish());
+    return LCB_OK;
+}
+
+int lcb_challenge_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* chmsg, const int64_t* chmsg_off, int64_t n,
+                        int16_t* out_pairs) {
+    if (!c || !sch || !chmsg_off || !out_pairs || n < 0) return LCB_ERR_INVALID;
+    if (n == 0) return LCB_OK;
+    CK(c, cudaSetDevice(c->device));
+    int64_t total = 0;
+    CK(c, last_offset(c, chmsg_off, n, &total));
+    Staging sg(c);
+    const uint8_t* d_msg;
+    const int64_t* d_off;
+    int16_t* d_pairs;
+    CK(c, sg.in(&d_msg, chmsg, (size_t)total));
+    CK(c, sg.in(&d_off, chmsg_off, (size_t)n + 1));
+    CK(c, sg.out(&d_pairs, out_pairs, (size_t)n * sch->ch_wt * 2));
+    int st = run_challenge(c, sch, d_msg, d_off, n, d_pairs);
+    if (st != LCB_OK) return st;
+    CK(c, sg.finish());
+    return LCB_OK;
+}
+
+int lcb_lm_sign_batch(lcb_ctx* c, const lcb_scheme* sch, const uint16_t* sk_ntt, const uint8_t* chmsg,
+                      const int64_t* chmsg_off, int64_t n, int16_t* sig) {
+    if (!c || !sch || !sk_ntt || !chmsg_off || !sig || n < 0) return LCB_ERR_INVALID;
+    if (n == 0) return LCB_OK;
+    CK(c, cudaSetDevice(c->device));
+    const int l = c->l;
+    int64_t total = 0;
+    CK(c, last_offset(c, chmsg_off, n, &total));
+    Staging sg(c);
+    const uint16_t* d_sk;
+    const uint8_t* d_msg;
+    const int64_t* d_off;
+    int16_t *d_sig, *d_pairs;
+    CK(c, sg.in(&d_sk, sk_ntt, (size_t)n * 2 * l * D));
+    CK(c, sg.in(&d_msg, chmsg, (size_t)total));
+    CK(c, sg.in(&d_off, chmsg_off, (size_t)n + 1));
+    CK(c, sg.out(&d_sig, sig, (size_t)n * l * D));
+    CK(c, sg.alloc((void**)&d_pairs, (size_t)n * sch->ch_wt * 2 * sizeof(int16_t)));
+    int st = run_challenge(c, sch, d_msg, d_off, n, d_pairs);
+    if (st != LCB_OK) return st;
+    CK(c, launch_sign(c->ring, d_sk, d_pairs, sch->ch_wt, n, d_sig, c->stream));
+    c->launches += 1;
+    CK(c, sg.finish());
+    return LCB_OK;
+}
+
+int lcb_lm_verify_batch(lcb_ctx* c, const lcb_scheme* sch, const uint16_t* vk_ntt, const uint8_t* chmsg,
+                        const int64_t* chmsg_off, const int16_t* sig, const uint16_t* st_ntt, int64_t n, int bd,
+                        int wt, uint8_t* verdict) {
+    if (!c || !sch || !vk_ntt || !chmsg_off || !sig || !verdict || n < 0 || bd < 0 || wt < 0) return LCB_ERR_INVALID;
+    if (!c->has_key_ch) return fail(c, LCB_ERR_NO_KEY_CH, "lcb_lm_verify_batch before lcb_set_key_ch");
+    if (n == 0) return LCB_OK;
+    CK(c, cudaSetDevice(c->device));
+    const int l = c->l;
+    int64_t total = 0;
+    CK(c, last_offset(c, chmsg_off, n, &total));
+    Staging sg(c);
+    const uint16_t *d_vk, *d_st;
+    const uint8_t* d_msg;
+    const int64_t* d_off;
+    const int16_t* d_sig;
+    int16_t* d_pairs;
+    uint8_t* d_verdict;
+    CK(c, sg.in(&d_vk, vk_ntt, (size_t)n * 2 * D));
+    CK(c, sg.in(&d_msg, chmsg, (size_t)total));
+    CK(c, sg.in(&d_off, chmsg_off, (size_t)n + 1));
+    CK(c, sg.in(&d_sig, sig, (size_t)n * l * D));
+    CK(c, sg.in(&d_st, st_ntt, (size_t)n * D));
+    CK(c, sg.out(&d_verdict, verdict, (size_t)n));
+    CK(c, sg.alloc((void**)&d_pairs, (size_t)n * sch->ch_wt * 2 * sizeof(int16_t)));
+    int st = run_challenge(c, sch, d_msg, d_off, n, d_pairs);
+    if (st != LCB_OK) return st;
+    CK(c, launch_verify(c->ring, d_sig, d_vk, d_pairs, sch->ch_wt, nullptr, d_st, n, bd > 32767 ? 32767 : bd, wt,
+                        d_verdict, c->stream));
+    c->launches += 1;
+    CK(c, sg.finish());
+    return LCB_OK;
+}
+
+int lcb_bklm_agg_coefs(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* agmsg, int64_t agmsg_len, int64_t first,
+                       int64_t count, int16_t* out_pairs) {
+    if (!c || !sch || !agmsg || !out_pairs || agmsg_len < 0 || first < 0 || count < 0) return LCB_ERR_INVALID;
+    if (count == 0) return LCB_OK;
+    CK(c, cudaSetDevice(c->device));
+    Staging sg(c);
+    const uint8_t* d_msg;
+    int16_t* d_pairs;
+    CK(c, sg.in(&d_msg, agmsg, (size_t)agmsg_len));
+    CK(c, sg.out(&d_pairs, out_pairs, (size_t)count * sch->ag_wt * 2));
+    int st = run_agg_coefs(c, sch, d_msg, agmsg_len, first, count, d_pairs);
+    if (st != LCB_OK) return st;
+    CK(c, sg.finish());
+    return LCB_OK;
+}
+
+int lcb_bklm_aggregate_partial(lcb_ctx* c, const lcb_scheme* sch, const int16_t* sig_sorted, const int16_t* ag_pairs,
+                               const uint8_t* agmsg, int64_t agmsg_len, int64_t first, int64_t count,
+                               int32_t* partial) {
+    if (!c || !sch || !partial || count < 0 || (count > 0 && !sig_sorted) || (!ag_pairs && !agmsg)) return LCB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    const int l = c->l;
+    Staging sg(c);
+    const int16_t *d_sig, *d_pairs_in;
+    const uint8_t* d_msg;
+    int32_t* d_partial;
+    CK(c, sg.in(&d_sig, sig_sorted, (size_t)count * l * D));
+    CK(c, sg.in(&d_pairs_in, ag_pairs, (size_t)count * 2));
+    CK(c, sg.out(&d_partial, partial, (size_t)l * D));
+    CK(c, cudaMemsetAsync(d_partial, 0, (size_t)l * D * sizeof(int32_t), c->stream));
+    if (count > 0) {
+        if (!d_pairs_in) {
+            int16_t* d_pairs;
+            CK(c, sg.in(&d_msg, agmsg, (size_t)agmsg_len));
+            CK(c, sg.alloc((void**)&d_pairs, (size_t)count * 2 * sizeof(int16_t)));
+            int st = run_agg_coefs(c, sch, d_msg, agmsg_len, first, count, d_pairs);
+            if (st != LCB_OK) return st;
+            d_pairs_in = d_pairs;
+        }
+        CK(c, launch_agg_partial(c->ring, d_sig, d_pairs_in, count, d_partial, c->stream));
+        c->launches += 1;
+    }
+    CK(c, sg.finish());
+    return LCB_OK;
+}
+
+int lcb_bklm_aggregate_finish(lcb_ctx* c, const int32_t* partial_sum, int16_t* ag_sig) {
+    if (!c || !partial_sum || !ag_sig) return LCB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    Staging sg(c);
+    const int32_t* d_partial;
+    int16_t* d_out;
+    CK(c, sg.in(&d_partial, partial_sum, (size_t)c->l * D));
+    CK(c, sg.out(&d_out, ag_sig, (size_t)c->l * D));
+    CK(c, launch_agg_finish(c->ring, d_partial, d_out, c->stream));
+    c->launches += 1;
+    CK(c, sg.finish());
+    return LCB_OK;
+}
+
+int lcb_bklm_aggverify_partial(lcb_ctx* c, const lcb_scheme* sch, const uint16_t* vk_ntt_sorted,
+                               const uint8_t* chmsg_sorted, const int64_t* chmsg_off, const int16_t* ag_pairs,
+                               const uint8_t* agmsg, int64_t agmsg_len, int64_t first, int64_t count,
+                               int32_t* partial) {
+    if (!c || !sch || !partial || count < 0 || (count > 0 && (!vk_ntt_sorted || !chmsg_off)) || (!ag_pairs && !agmsg))
+        return LCB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    Staging sg(c);
+    int32_t* d_partial;
+    CK(c, sg.out(&d_partial, partial, (size_t)D));
+    CK(c, cudaMemsetAsync(d_partial, 0, (size_t)D * sizeof(int32_t), c->stream));
+    if (count > 0) {
+        int64_t total = 0;
+        CK(c, last_offset(c, chmsg_off, count, &total));
+        const uint16_t* d_vk;
+        const uint8_t *d_chmsg, *d_agmsg;
+        const int64_t* d_off;
+        const int16_t* d_ag;
+        int16_t* d_ch;
+        CK(c, sg.in(&d_vk, vk_ntt_sorted, (size_t)count * 2 * D));
+        CK(c, sg.in(&d_chmsg, chmsg_sorted, (size_t)total));
+        CK(c, sg.in(&d_off, chmsg_off, (size_t)count + 1));
+        CK(c, sg.in(&d_ag, ag_pairs, (size_t)count * 2));
+        CK(c, sg.alloc((void**)&d_ch, (size_t)count * sch->ch_wt * 2 * sizeof(int16_t)));
+        int st = run_challenge(c, sch, d_chmsg, d_off, count, d_ch);
+        if (st != LCB_OK) return st;
+        if (!d_ag) {
+            int16_t* d_pairs;
+            CK(c, sg.in(&d_agmsg, agmsg, (size_t)agmsg_len));
+            CK(c, sg.alloc((void**)&d_pairs, (size_t)count * 2 * sizeof(int16_t)));
+            st = run_agg_coefs(c, sch, d_agmsg, agmsg_len, first, count, d_pairs);
+            if (st != LCB_OK) return st;
+            d_ag = d_pairs;
+        }
+        CK(c, launch_aggv_partial(c->ring, d_vk, d_ch, sch->ch_wt, d_ag, count, d_partial, c->stream));
+        c->launches += 1;
+    }
+    CK(c, sg.finish());
+    return LCB_OK;
+}
+
+int lcb_bklm_aggverify_finish(lcb_ctx* c, const int32_t* partial_sum, const int16_t* ag_sig, int64_t total, int ag_cap,
+                              int avf_bd, int avf_wt, uint8_t* verdict) {
+    if (!c || !partial_sum || !ag_sig || !verdict) return LCB_ERR_INVALID;
+    if (!c->has_key_ch) return fail(c, LCB_ERR_NO_KEY_CH, "lcb_bklm_aggverify_finish before lcb_set_key_ch");
+    CK(c, cudaSetDevice(c->device));
+    Staging sg(c);
+    const int32_t* d_partial;
+    const int16_t* d_sig;
+    uint8_t* d_verdict;
+    CK(c, sg.in(&d_partial, partial_sum, (size_t)D));
+    CK(c, sg.in(&d_sig, ag_sig, (size_t)c->l * D));
+    CK(c, sg.out(&d_verdict, verdict, 1));
+    CK(c, launch_aggv_finish(c->ring, d_partial, d_sig, total, ag_cap, avf_bd, avf_wt, d_verdict, c->stream));
+    c->launches += 1;
+    CK(c, sg.finish());
+    return LCB_OK;
+}
+
+int lcb_adaptor_witgen_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* seeds, const int64_t* seed_off,
+                             int64_t n, int16_t* wit_coef, uint16_t* st_ntt, int16_t* st_coef) {
+    if (!c || !sch || !seed_off || n < 0) return LCB_ERR_INVALID;
+    if (!c->has_key_ch) return fail(c, LCB_ERR_NO_KEY_CH, "lcb_adaptor_witgen_batch before lcb_set_key_ch");
+    if (n == 0) return LCB_OK;
+    CK(c, cudaSetDevice(c->device));
+    const int l = c->l;
+    SamplerArgs a{};
+    int st = fill_sampler(c, a, salt_of(sch->wit_salt).c_str(), nullptr, sch->wit_bd, sch->wit_wt, l);
+    if (st != LCB_OK) return fail(c, st, "bad witness parameters");
+    int64_t total = 0;
+    CK(c, last_offset(c, seed_off, n, &total));
+    Staging sg(c);
+    int16_t *d_wit, *d_st_coef;
+    uint16_t* d_st_ntt;
+    CK(c, sg.in(&a.msgs, seeds, (size_t)total));
+    CK(c, sg.in(&a.off, seed_off, (size_t)n + 1));
+    CK(c, sg.out(&d_wit, wit_coef, (size_t)n * l * D));
+    CK(c, sg.out(&d_st_ntt, st_ntt, (size_t)n * D));
+    CK(c, sg.out(&d_st_coef, st_coef, (size_t)n * D));
+    if (!d_wit) CK(c, sg.alloc((void**)&d_wit, (size_t)n * l * D * sizeof(int16_t)));
+    if (sch->wit_wt < D) CK(c, cudaMemsetAsync(d_wit, 0, (size_t)n * l * D * sizeof(int16_t), c->stream));
+    a.n = n;
+    a.out_dense = d_wit;
+    a.dense_stride = (int64_t)l * D;
+    CK(c, launch_sampler(a, c->stream));
+    CK(c, launch_matvec(c->ring, d_wit, n, nullptr, d_st_ntt, d_st_coef, c->stream));
+    c->launches += 2;
+    CK(c, sg.finish());
+    return LCB_OK;
+}
+
+static int vec_addsub(lcb_ctx* c, const int16_t* a, const int16_t* b, int64_t npoly, int sub, int16_t* out) {
+    if (!c || !a || !b || !out || npoly < 0) return LCB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    Staging sg(c);
+    const int16_t *d_a, *d_b;
+    int16_t* d_out;
+    CK(c, sg.in(&d_a, a, (size_t)npoly * D));
+    CK(c, sg.in(&d_b, b, (size_t)npoly * D));
+    CK(c, sg.out(&d_out, out, (size_t)npoly * D));
+    CK(c, launch_vec_addsub(c->ring, d_a, d_b, npoly * D, sub, d_out, c->stream));
+    c->launches += 1;
+    CK(c, sg.finish());
+    return LCB_OK;
+}
+
+int lcb_vec_add_batch(lcb_ctx* c, const int16_t* a, const int16_t* b, int64_t npoly, int16_t* out) {
+    return vec_addsub(c, a, b, npoly, 0, out);
+}
+
+int lcb_vec_sub_batch(lcb_ctx* c, const int16_t* a, const int16_t* b, int64_t npoly, int16_t* out) {
+    return vec_addsub(c, a, b, npoly, 1, out);
+}
+
+int lcb_adaptor_witness_verify_batch(lcb_ctx* c, const int16_t* wit_coef, const uint16_t* st_ntt, int64_t n, int bd,
+                                     int wt, uint8_t* verdict) {
+    if (!c || !wit_coef || !st_ntt || !verdict || n < 0 || bd < 0 || wt < 0) return LCB_ERR_INVALID;
+    if (!c->has_key_ch) return fail(c, LCB_ERR_NO_KEY_CH, "lcb_adaptor_witness_verify_batch before lcb_set_key_ch");
+    if (n == 0) return LCB_OK;
+    CK(c, cudaSetDevice(c->device));
+    Staging sg(c);
+    const int16_t* d_wit;
+    const uint16_t* d_st;
+    uint8_t* d_verdict;
+    CK(c, sg.in(&d_wit, wit_coef, (size_t)n * c->l * D));
+    CK(c, sg.in(&d_st, st_ntt, (size_t)n * D));
+    CK(c, sg.out(&d_verdict, verdict, (size_t)n));
+    CK(c, launch_verify(c->ring, d_wit, nullptr, nullptr, 0, d_st, nullptr, n, bd > 32767 ? 32767 : bd, wt, d_verdict,
+                        c->stream));
+    c->launches += 1;
+    CK(c, sg.finish());
+    return LCB_OK;
+}
+
+}  // extern "C"

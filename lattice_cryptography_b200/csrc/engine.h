@@ -1,0 +1,66 @@
+// engine.h — host-side declarations shared by api.cu, sampler.cu and ring.cu.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "lcb_device.cuh"
+
+namespace lcb {
+
+constexpr int SALT_BYTES = 48;
+
+struct SamplerArgs {
+    const uint8_t* msgs;       // ragged items (device)
+    const int64_t* off;        // [n+1] (device); ignored when shared_msg
+    int64_t n;
+    int64_t shared_len;        // shared_msg: every instance hashes msgs[0 .. shared_len)
+    int64_t index_first;       // shared_msg: decimal index appended to the salt = index_first + i
+    int shared_msg;
+    uint8_t salt[SALT_BYTES];
+    int salt_len;
+    int secpar, bd, wt, vec_len;
+    int idx_bits;              // LOGD + secpar
+    int mag_bits;              // btd - 1
+    int pad_bits;              // 8*nb - bti - wt*btd
+    int16_t* out_dense;        // or nullptr; instance stride below (elements)
+    int64_t dense_stride;
+    int16_t* out_pairs;        // or nullptr; [n][vec_len][wt][2]
+};
+
+cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st);
+cudaError_t launch_shake256(const uint8_t* in, const int64_t* off, int64_t n, uint8_t* out, int64_t out_len,
+                            cudaStream_t st);
+cudaError_t launch_agg_coefs(const SamplerArgs& a, cudaStream_t st);   // shared-message fast path, wt == 1
+
+struct RingCtx {
+    ModQ m;
+    StageConst sc;
+    const NttTables* tab;      // device
+    const uint32_t* a_hat;     // device, uint32[l][256]: NTT(key_ch), slot order
+    int l;
+    int num_sms;
+};
+
+cudaError_t launch_ntt_fwd(const RingCtx& c, const int16_t* coef, int64_t npoly, uint16_t* out, cudaStream_t st);
+cudaError_t launch_ntt_inv(const RingCtx& c, const uint16_t* in, int64_t npoly, int16_t* coef, cudaStream_t st);
+cudaError_t launch_poly_mul(const RingCtx& c, const int16_t* a, const int16_t* b, int64_t npoly, int16_t* out,
+                            cudaStream_t st);
+// y = key_ch * v for nvec coefficient-form vectors; optional v_ntt / y_coef outputs
+cudaError_t launch_matvec(const RingCtx& c, const int16_t* vec_coef, int64_t nvec, uint16_t* vec_ntt,
+                          uint16_t* y_ntt, int16_t* y_coef, cudaStream_t st);
+cudaError_t launch_sign(const RingCtx& c, const uint16_t* sk_ntt, const int16_t* ch_pairs, int ch_wt, int64_t n,
+                        int16_t* sig, cudaStream_t st);
+// verdict = bounds(vec) && key_ch*vec == [vk_left*c] + [vk_right | rhs0] + [rhs1]
+cudaError_t launch_verify(const RingCtx& c, const int16_t* vec_coef, const uint16_t* vk_ntt,
+                          const int16_t* ch_pairs, int ch_wt, const uint16_t* rhs_only, const uint16_t* extra_rhs,
+                          int64_t n, int bd, int wt, uint8_t* verdict, cudaStream_t st);
+cudaError_t launch_vec_addsub(const RingCtx& c, const int16_t* a, const int16_t* b, int64_t nelem, int sub,
+                              int16_t* out, cudaStream_t st);
+cudaError_t launch_agg_partial(const RingCtx& c, const int16_t* sigs, const int16_t* ag_pairs, int64_t count,
+                               int32_t* partial, cudaStream_t st);
+cudaError_t launch_agg_finish(const RingCtx& c, const int32_t* partial, int16_t* ag_sig, cudaStream_t st);
+cudaError_t launch_aggv_partial(const RingCtx& c, const uint16_t* vk_ntt, const int16_t* ch_pairs, int ch_wt,
+                                const int16_t* ag_pairs, int64_t count, int32_t* partial, cudaStream_t st);
+cudaError_t launch_aggv_finish(const RingCtx& c, const int32_t* partial, const int16_t* ag_sig, int64_t total,
+                               int ag_cap, int avf_bd, int avf_wt, uint8_t* verdict, cudaStream_t st);
+
+}  // namespace lcb

@@ -1,0 +1,263 @@
+// lcb_device.cuh — device primitives shared by the lcb200 kernels (sm_100a).
+//
+//   * 32-bit modular arithmetic for q < 2^16 on the integer pipes: Shoup multiplication by
+//     precomputed constants (IMAD.HI + 2 IMAD), Barrett reduction, lazy (unreduced) butterflies.
+//   * d = 256 negacyclic NTT: one polynomial per HALF-WARP (16 lanes x 16 coefficients):
+//     stages 1-4 and 5-8 run in registers, with ONE conflict-free transposition through shared
+//     memory in between.  Stage 1-4 twiddles are warp-uniform (kernel-parameter constant bank),
+//     stage 5-8 twiddles are 15 per-lane register pairs.
+//   * Keccak-f[1600] with the state in registers (one SHAKE256 stream per thread).
+//
+// Replaces lattice_algebra's ntt()/cent()/Polynomial arithmetic and binary_digest() (restated in
+// oracle/lattice_algebra/__init__.py).  The reference transform is a 2d-point cyclic NTT of the
+// zero-padded polynomial; this one is the d-point negacyclic NTT, which yields the same
+// coefficient representations (parity level L1) with half the work.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace lcb {
+
+constexpr int D = 256;            // ring degree handled by the fast path
+constexpr int LOGD = 8;
+constexpr int LANES = 16;         // lanes per polynomial
+constexpr int EPT = 16;           // coefficients per lane
+constexpr int XROW = 20;          // padded row pitch (words) of the transposition buffer
+constexpr int XHALF = 336;        // words per half-warp buffer: 16 rows * 20 + 16 (bank offset)
+constexpr int XWARP = 2 * XHALF;  // words per warp
+
+// Modulus constants; passed BY VALUE as a kernel parameter so they live in the constant bank.
+struct ModQ {
+    uint32_t q, negq;
+    uint32_t barrett;     // floor((2^32-1)/q)
+    uint32_t cq;          // least multiple of q >= 32768: makes any int16 input non-negative
+    uint32_t cq2;         // least multiple of q >= 65536 + 2q: bound for u16-derived lazy values
+    uint32_t half;        // (q-1)/2
+    uint32_t dinv, dinv_s;  // d^-1 mod q and its Shoup companion
+};
+
+// Warp-uniform twiddles of stages 1..4 (zeta index k = 1..15), forward and inverse.
+struct StageConst {
+    uint32_t w[16], ws[16], iw[16], iws[16];
+};
+
+// Per-lane twiddles of stages 5..8: [0] stage 5, [1..2] stage 6, [3..6] stage 7, [7..14] stage 8.
+struct LaneTw {
+    uint32_t w[15], ws[15];
+};
+
+// Device-resident tables of one ctx.
+struct NttTables {
+    uint32_t w[256], ws[256];      // zetas[k] = psi^bitrev8(k) and Shoup companions
+    uint32_t iw[256], iws[256];    // zetas[k]^-1
+    uint32_t pw[512], pws[512];    // psi^e, e in [0, 512): NTT image of monomials (BKLM)
+    uint16_t oddexp[256];          // 2*bitrev8(p)+1: exponent of the evaluation point of slot p
+};
+
+__device__ __forceinline__ uint32_t shoup_mul(uint32_t a, uint32_t w, uint32_t ws, const ModQ& m) {
+    // a any 32-bit value, w < q, ws = floor(w * 2^32 / q)  ->  a*w mod q in [0, 2q)
+    uint32_t hi = __umulhi(a, ws);
+    return a * w + hi * m.negq;
+}
+
+__device__ __forceinline__ uint32_t barrett_lazy(uint32_t x, const ModQ& m) {
+    // x any 32-bit value -> x mod q in [0, 2q)
+    uint32_t hi = __umulhi(x, m.barrett);
+    return x + hi * m.negq;
+}
+
+__device__ __forceinline__ uint32_t csub(uint32_t x, uint32_t q) { return x >= q ? x - q : x; }
+
+__device__ __forceinline__ uint32_t barrett_full(uint32_t x, const ModQ& m) {
+    // floor((2^32-1)/q) underestimates the quotient by at most 2
+    return csub(csub(barrett_lazy(x, m), m.q), m.q);
+}
+
+__device__ __forceinline__ uint32_t mulmod_full(uint32_t a, uint32_t b, const ModQ& m) {
+    // a, b < 2^16 -> a*b mod q in [0, q)
+    return barrett_full(a * b, m);
+}
+
+__device__ __forceinline__ uint32_t reduce64(uint64_t acc, const ModQ& m) {
+    // acc < 2^44 -> acc mod q in [0, q)   (q < 2^16)
+    uint32_t r1 = barrett_full((uint32_t)(acc >> 12), m);
+    return barrett_full((r1 << 12) | ((uint32_t)acc & 0xFFFu), m);
+}
+
+__device__ __forceinline__ int32_t center(uint32_t r, const ModQ& m) {
+    // r in [0, q) -> centred residue
+    return r > m.half ? (int32_t)r - (int32_t)m.q : (int32_t)r;
+}
+
+__device__ __forceinline__ void load_lane_tw(LaneTw& t, const uint32_t* __restrict__ w,
+                                             const uint32_t* __restrict__ ws, int lane) {
+    t.w[0] = __ldg(w + 16 + lane);
+    t.ws[0] = __ldg(ws + 16 + lane);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { t.w[1 + i] = __ldg(w + 32 + 2 * lane + i); t.ws[1 + i] = __ldg(ws + 32 + 2 * lane + i); }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { t.w[3 + i] = __ldg(w + 64 + 4 * lane + i); t.ws[3 + i] = __ldg(ws + 64 + 4 * lane + i); }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { t.w[7 + i] = __ldg(w + 128 + 8 * lane + i); t.ws[7 + i] = __ldg(ws + 128 + 8 * lane + i); }
+}
+
+// ---- transposition between the two register layouts -------------------------------------------
+// layout A: r[j] = x[lane + 16 j]      (strides 128..16 are inside a lane)
+// layout B: r[m] = x[16 lane + m]      (strides 8..1 are inside a lane)
+__device__ __forceinline__ void xpose_a_to_b(uint32_t (&r)[EPT], uint32_t* xb, int lane) {
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) xb[XROW * j + lane] = r[j];
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint4 v = *reinterpret_cast<const uint4*>(xb + XROW * lane + 4 * g);
+        r[4 * g] = v.x; r[4 * g + 1] = v.y; r[4 * g + 2] = v.z; r[4 * g + 3] = v.w;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void xpose_b_to_a(uint32_t (&r)[EPT], uint32_t* xb, int lane) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(xb + XROW * lane + 4 * g) = make_uint4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) r[j] = xb[XROW * j + lane];
+    __syncwarp();
+}
+
+// ---- forward negacyclic NTT, Cooley-Tukey, natural order in (layout A) -> bit-reversed out (layout B)
+// input values < 2^17; every stage adds < 2q, so outputs are < 2^17 + 16 q < 2^21 (lazy).
+__device__ __forceinline__ void ntt_fwd_256(uint32_t (&r)[EPT], const ModQ& m, const StageConst& sc,
+                                            const LaneTw& tw, uint32_t* xb, int lane) {
+    const uint32_t q2 = 2 * m.q;
+#pragma unroll
+    for (int s = 1; s <= 4; ++s) {
+        const int len = 8 >> (s - 1);
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            if (j & len) continue;
+            const int k = (1 << (s - 1)) + (j >> (5 - s));
+            uint32_t t = shoup_mul(r[j + len], sc.w[k], sc.ws[k], m);
+            r[j + len] = r[j] + q2 - t;
+            r[j] = r[j] + t;
+        }
+    }
+    xpose_a_to_b(r, xb, lane);
+#pragma unroll
+    for (int s = 5; s <= 8; ++s) {
+        const int len = 256 >> s;
+        const int base = (1 << (s - 5)) - 1;
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            if (j & len) continue;
+            const int k = base + (j >> (9 - s));
+            uint32_t t = shoup_mul(r[j + len], tw.w[k], tw.ws[k], m);
+            r[j + len] = r[j] + q2 - t;
+            r[j] = r[j] + t;
+        }
+    }
+}
+
+// ---- inverse, Gentleman-Sande, bit-reversed in (layout B) -> natural order out (layout A), UNSCALED
+// (multiply by d^-1 afterwards).  Inputs < b0 (a multiple of q); outputs < 256 * b0.
+__device__ __forceinline__ void ntt_inv_256(uint32_t (&r)[EPT], const ModQ& m, const StageConst& sc,
+                                            const LaneTw& itw, uint32_t* xb, int lane, uint32_t b0) {
+    uint32_t b = b0;
+#pragma unroll
+    for (int s = 8; s >= 5; --s) {
+        const int len = 256 >> s;
+        const int base = (1 << (s - 5)) - 1;
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            if (j & len) continue;
+            const int k = base + (j >> (9 - s));
+            uint32_t x = r[j], y = r[j + len];
+            r[j] = x + y;
+            r[j + len] = shoup_mul(x + b - y, itw.w[k], itw.ws[k], m);
+        }
+        b <<= 1;
+    }
+    xpose_b_to_a(r, xb, lane);
+#pragma unroll
+    for (int s = 4; s >= 1; --s) {
+        const int len = 8 >> (s - 1);
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            if (j & len) continue;
+            const int k = (1 << (s - 1)) + (j >> (5 - s));
+            uint32_t x = r[j], y = r[j + len];
+            r[j] = x + y;
+            r[j + len] = shoup_mul(x + b - y, sc.iw[k], sc.iws[k], m);
+        }
+        b <<= 1;
+    }
+}
+
+// final scaling of an unscaled inverse transform value -> centred coefficient
+__device__ __forceinline__ int32_t finish_coef(uint32_t v, const ModQ& m) {
+    return center(csub(shoup_mul(v, m.dinv, m.dinv_s, m), m.q), m);
+}
+
+// ---- 16 consecutive uint16 <-> registers (NTT-form rows, 32 B per lane, 512 B per half-warp)
+__device__ __forceinline__ void load_u16x16(uint32_t (&r)[EPT], const uint16_t* __restrict__ p) {
+    const uint4* v = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(v), b = __ldg(v + 1);
+    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { r[2 * i] = w[i] & 0xFFFFu; r[2 * i + 1] = w[i] >> 16; }
+}
+
+__device__ __forceinline__ void store_u16x16(uint16_t* __restrict__ p, const uint32_t (&r)[EPT]) {
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = (r[2 * i] & 0xFFFFu) | (r[2 * i + 1] << 16);
+    uint4* v = reinterpret_cast<uint4*>(p);
+    v[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    v[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+// ---- Keccak-f[1600] -----------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
+
+#define LCB_KECCAK_RC_INIT                                                                           \
+    {0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,     \
+     0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,     \
+     0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,     \
+     0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL,     \
+     0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,     \
+     0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL}
+
+// rho offsets and pi destinations for lane index i = x + 5y
+__device__ constexpr int KECCAK_RHO[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39,
+                                           41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+__host__ __device__ constexpr int keccak_pi(int i) {
+    // (x, y) -> (y, 2x + 3y)
+    return (i / 5) + 5 * ((2 * (i % 5) + 3 * (i / 5)) % 5);
+}
+
+__device__ __forceinline__ void keccak_f1600(uint64_t (&s)[25], const uint64_t* __restrict__ rc) {
+#pragma unroll 2
+    for (int round = 0; round < 24; ++round) {
+        uint64_t c[5];
+#pragma unroll
+        for (int x = 0; x < 5; ++x) c[x] = s[x] ^ s[x + 5] ^ s[x + 10] ^ s[x + 15] ^ s[x + 20];
+#pragma unroll
+        for (int x = 0; x < 5; ++x) {
+            uint64_t dd = c[(x + 4) % 5] ^ rotl64(c[(x + 1) % 5], 1);
+#pragma unroll
+            for (int y = 0; y < 5; ++y) s[x + 5 * y] ^= dd;
+        }
+        uint64_t b[25];
+#pragma unroll
+        for (int i = 0; i < 25; ++i) b[keccak_pi(i)] = KECCAK_RHO[i] ? rotl64(s[i], KECCAK_RHO[i]) : s[i];
+#pragma unroll
+        for (int y = 0; y < 5; ++y)
+#pragma unroll
+            for (int x = 0; x < 5; ++x)
+                s[x + 5 * y] = b[x + 5 * y] ^ (~b[(x + 1) % 5 + 5 * y] & b[(x + 2) % 5 + 5 * y]);
+        s[0] ^= rc[round];
+    }
+}
+
+}  // namespace lcb

@@ -1,0 +1,592 @@
+// ring.cu — polynomial-ring kernels over Z_q[X]/(X^256+1) (sm_100a).
+//
+// Replaces, batched over independent instances, the reference's arithmetic call sites:
+//   key_ch * sk / key_ch * wit          lm_one_time_sigs.py:95-96, adaptor_sigs.py:100     -> k_matvec
+//   sk_left ** c + sk_right             lm_one_time_sigs.py:168, adaptor_sigs.py:193       -> k_sign
+//   bounds; key_ch*sig == vk0*c+vk1[+st] lm_one_time_sigs.py:173-191, adaptor_sigs.py:198-266 -> k_verify
+//   sum(sig ** ag)                      bklm_one_time_agg_sigs.py:96                       -> k_agg_partial
+//   sum((vk0*c+vk1)*ag); key_ch*ag_sig == . bklm_one_time_agg_sigs.py:99-116               -> k_aggv_*
+//   presig + wit, sig - presig          adaptor_sigs.py:221,225                            -> k_vec_addsub
+//
+// Work mapping: one polynomial vector (one signature / key half / instance) per HALF-WARP; a lane
+// holds 16 coefficients; the public row key_ch stays NTT-resident in shared memory (uint32[l][256])
+// for the life of the kernel; accumulation of the row-vector product is 64-bit (IMAD.WIDE) with a
+// single reduction per output coefficient.  Grids are persistent: (#SM x resident blocks) blocks
+// striding over the batch.
+#include "engine.h"
+
+namespace lcb {
+
+namespace {
+
+constexpr int RBS = 128;                 // threads per block
+constexpr int HWB = RBS / LANES;         // half-warps (work items) per block iteration
+
+struct HalfWarp {
+    int lane;        // 0..15
+    int slot;        // half-warp index within the block
+    uint32_t* xb;    // transposition buffer of this half-warp
+    unsigned mask;   // ballot mask of this half-warp
+};
+
+__device__ __forceinline__ HalfWarp half_warp(uint32_t* xbase) {
+    const int tid = threadIdx.x;
+    HalfWarp h;
+    h.lane = tid & 15;
+    h.slot = tid >> 4;
+    const int upper = (tid >> 4) & 1;
+    h.xb = xbase + (tid >> 5) * XWARP + upper * XHALF;
+    h.mask = upper ? 0xFFFF0000u : 0x0000FFFFu;
+    return h;
+}
+
+// coefficient-form polynomial (int16, natural order) -> layout A registers, made non-negative
+__device__ __forceinline__ void load_coef_a(uint32_t (&r)[EPT], const int16_t* __restrict__ p, int lane, uint32_t cq) {
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) r[j] = (uint32_t)((int)__ldg(p + lane + 16 * j) + (int)cq);
+}
+
+__device__ __forceinline__ void store_coef_a(int16_t* __restrict__ p, const uint32_t (&r)[EPT], int lane, const ModQ& m) {
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) p[lane + 16 * j] = (int16_t)finish_coef(r[j], m);
+}
+
+// sparse (index, coefficient) pairs -> dense polynomial in layout A (via the transposition buffer)
+__device__ __forceinline__ void load_pairs_a(uint32_t (&r)[EPT], const int16_t* __restrict__ pairs, int wt,
+                                             uint32_t* xb, int lane, uint32_t cq) {
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) xb[XROW * j + lane] = 0;
+    __syncwarp();
+    const uint32_t* pp = reinterpret_cast<const uint32_t*>(pairs);
+    for (int e = lane; e < wt; e += LANES) {
+        uint32_t pr = __ldg(pp + e);
+        int idx = (int)(pr & 0xFFu);                 // d = 256
+        int coef = (int)(int16_t)(pr >> 16);
+        xb[XROW * (idx >> 4) + (idx & 15)] = (uint32_t)coef;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) r[j] = xb[XROW * j + lane] + cq;
+    __syncwarp();
+}
+
+__device__ __forceinline__ void copy_a_hat(uint32_t* dst, const uint32_t* __restrict__ src, int l) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (int i = threadIdx.x; i < l * (D / 4); i += blockDim.x) d4[i] = __ldg(s4 + i);
+    __syncthreads();
+}
+
+// acc[m] += r[m] * a_hat_row[16 lane + m]
+__device__ __forceinline__ void mac_row(uint64_t (&acc)[EPT], const uint32_t (&r)[EPT], const uint32_t* row, int lane) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint4 v = *reinterpret_cast<const uint4*>(row + 16 * lane + 4 * g);
+        acc[4 * g] += (uint64_t)r[4 * g] * v.x;
+        acc[4 * g + 1] += (uint64_t)r[4 * g + 1] * v.y;
+        acc[4 * g + 2] += (uint64_t)r[4 * g + 2] * v.z;
+        acc[4 * g + 3] += (uint64_t)r[4 * g + 3] * v.w;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RBS) k_ntt_fwd(ModQ m, StageConst sc, const NttTables* __restrict__ tab,
+                                                 const int16_t* __restrict__ coef, int64_t npoly,
+                                                 uint16_t* __restrict__ out) {
+    __shared__ __align__(16) uint32_t xbuf[(RBS / 32) * XWARP];
+    const HalfWarp h = half_warp(xbuf);
+    LaneTw tw;
+    load_lane_tw(tw, tab->w, tab->ws, h.lane);
+    for (int64_t base = (int64_t)blockIdx.x * HWB; base < npoly; base += (int64_t)gridDim.x * HWB) {
+        const int64_t raw = base + h.slot;
+        const bool live = raw < npoly;
+        const int64_t item = live ? raw : npoly - 1;
+        uint32_t r[EPT];
+        load_coef_a(r, coef + item * D, h.lane, m.cq);
+        ntt_fwd_256(r, m, sc, tw, h.xb, h.lane);
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) r[i] = barrett_full(r[i], m);
+        if (live) store_u16x16(out + item * D + 16 * h.lane, r);
+    }
+}
+
+__global__ void __launch_bounds__(RBS) k_ntt_inv(ModQ m, StageConst sc, const NttTables* __restrict__ tab,
+                                                 const uint16_t* __restrict__ in, int64_t npoly,
+                                                 int16_t* __restrict__ coef) {
+    __shared__ __align__(16) uint32_t xbuf[(RBS / 32) * XWARP];
+    const HalfWarp h = half_warp(xbuf);
+    LaneTw itw;
+    load_lane_tw(itw, tab->iw, tab->iws, h.lane);
+    for (int64_t base = (int64_t)blockIdx.x * HWB; base < npoly; base += (int64_t)gridDim.x * HWB) {
+        const int64_t raw = base + h.slot;
+        const bool live = raw < npoly;
+        const int64_t item = live ? raw : npoly - 1;
+        uint32_t r[EPT];
+        load_u16x16(r, in + item * D + 16 * h.lane);
+        ntt_inv_256(r, m, sc, itw, h.xb, h.lane, m.cq2);
+        if (live) store_coef_a(coef + item * D, r, h.lane, m);
+    }
+}
+
+__global__ void __launch_bounds__(RBS) k_poly_mul(ModQ m, StageConst sc, const NttTables* __restrict__ tab,
+                                                  const int16_t* __restrict__ a, const int16_t* __restrict__ b,
+                                                  int64_t npoly, int16_t* __restrict__ out) {
+    __shared__ __align__(16) uint32_t xbuf[(RBS / 32) * XWARP];
+    const HalfWarp h = half_warp(xbuf);
+    for (int64_t base = (int64_t)blockIdx.x * HWB; base < npoly; base += (int64_t)gridDim.x * HWB) {
+        const int64_t raw = base + h.slot;
+        const bool live = raw < npoly;
+        const int64_t item = live ? raw : npoly - 1;
+        uint32_t ra[EPT], rb[EPT];
+        {
+            LaneTw tw;
+            load_lane_tw(tw, tab->w, tab->ws, h.lane);
+            load_coef_a(ra, a + item * D, h.lane, m.cq);
+            ntt_fwd_256(ra, m, sc, tw, h.xb, h.lane);
+            load_coef_a(rb, b + item * D, h.lane, m.cq);
+            ntt_fwd_256(rb, m, sc, tw, h.xb, h.lane);
+        }
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) ra[i] = mulmod_full(barrett_full(ra[i], m), barrett_full(rb[i], m), m);
+        LaneTw itw;
+        load_lane_tw(itw, tab->iw, tab->iws, h.lane);
+        ntt_inv_256(ra, m, sc, itw, h.xb, h.lane, m.cq2);
+        if (live) store_coef_a(out + item * D, ra, h.lane, m);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// y = key_ch * v  (v: nvec coefficient-form vectors of l polynomials)
+__global__ void __launch_bounds__(RBS) k_matvec(ModQ m, StageConst sc, const NttTables* __restrict__ tab,
+                                                const uint32_t* __restrict__ a_hat_g, int l,
+                                                const int16_t* __restrict__ vec_coef, int64_t nvec,
+                                                uint16_t* __restrict__ vec_ntt, uint16_t* __restrict__ y_ntt,
+                                                int16_t* __restrict__ y_coef) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t* a_hat = smem;
+    uint32_t* xbuf = smem + l * D;
+    copy_a_hat(a_hat, a_hat_g, l);
+    const HalfWarp h = half_warp(xbuf);
+    LaneTw tw;
+    load_lane_tw(tw, tab->w, tab->ws, h.lane);
+    for (int64_t base = (int64_t)blockIdx.x * HWB; base < nvec; base += (int64_t)gridDim.x * HWB) {
+        const int64_t raw = base + h.slot;
+        const bool live = raw < nvec;
+        const int64_t item = live ? raw : nvec - 1;
+        uint64_t acc[EPT];
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) acc[i] = 0;
+        for (int i = 0; i < l; ++i) {
+            uint32_t r[EPT];
+            load_coef_a(r, vec_coef + (item * l + i) * D, h.lane, m.cq);
+            ntt_fwd_256(r, m, sc, tw, h.xb, h.lane);
+            if (vec_ntt) {
+#pragma unroll
+                for (int k = 0; k < EPT; ++k) r[k] = barrett_full(r[k], m);
+                if (live) store_u16x16(vec_ntt + (item * l + i) * D + 16 * h.lane, r);
+            }
+            mac_row(acc, r, a_hat + i * D, h.lane);
+        }
+        uint32_t y[EPT];
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) y[k] = reduce64(acc[k], m);
+        if (y_ntt && live) store_u16x16(y_ntt + item * D + 16 * h.lane, y);
+        if (y_coef) {
+            LaneTw itw;
+            load_lane_tw(itw, tab->iw, tab->iws, h.lane);
+            ntt_inv_256(y, m, sc, itw, h.xb, h.lane, m.cq2);
+            if (live) store_coef_a(y_coef + item * D, y, h.lane, m);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sig = sk_left ** c + sk_right
+__global__ void __launch_bounds__(RBS) k_sign(ModQ m, StageConst sc, const NttTables* __restrict__ tab, int l,
+                                              const uint16_t* __restrict__ sk_ntt, const int16_t* __restrict__ ch_pairs,
+                                              int ch_wt, int64_t n, int16_t* __restrict__ sig) {
+    __shared__ __align__(16) uint32_t xbuf[(RBS / 32) * XWARP];
+    const HalfWarp h = half_warp(xbuf);
+    LaneTw itw;
+    load_lane_tw(itw, tab->iw, tab->iws, h.lane);
+    for (int64_t base = (int64_t)blockIdx.x * HWB; base < n; base += (int64_t)gridDim.x * HWB) {
+        const int64_t raw = base + h.slot;
+        const bool live = raw < n;
+        const int64_t item = live ? raw : n - 1;
+        uint32_t c[EPT];
+        {
+            LaneTw tw;
+            load_lane_tw(tw, tab->w, tab->ws, h.lane);
+            load_pairs_a(c, ch_pairs + item * ch_wt * 2, ch_wt, h.xb, h.lane, m.cq);
+            ntt_fwd_256(c, m, sc, tw, h.xb, h.lane);
+        }
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) c[k] = barrett_full(c[k], m);
+        const uint16_t* skl = sk_ntt + item * 2 * l * D;
+        const uint16_t* skr = skl + (int64_t)l * D;
+        for (int i = 0; i < l; ++i) {
+            uint32_t a[EPT], b[EPT];
+            load_u16x16(a, skl + i * D + 16 * h.lane);
+            load_u16x16(b, skr + i * D + 16 * h.lane);
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) a[k] = barrett_lazy(c[k] * a[k], m) + b[k];   // < 2q + 2^16 <= cq2
+            ntt_inv_256(a, m, sc, itw, h.xb, h.lane, m.cq2);
+            if (live) store_coef_a(sig + (item * l + i) * D, a, h.lane, m);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// verdict = max|v| <= bd && max weight <= wt && key_ch * v == [vk_left * c] + rhs (+ extra)
+//   vk_ntt != null : rhs = vk_ntt[item][1], and the challenge term uses vk_ntt[item][0]
+//   vk_ntt == null : rhs = rhs_only[item]                               (witness_verify)
+__global__ void __launch_bounds__(RBS) k_verify(ModQ m, StageConst sc, const NttTables* __restrict__ tab,
+                                                const uint32_t* __restrict__ a_hat_g, int l,
+                                                const int16_t* __restrict__ vec_coef,
+                                                const uint16_t* __restrict__ vk_ntt,
+                                                const int16_t* __restrict__ ch_pairs, int ch_wt,
+                                                const uint16_t* __restrict__ rhs_only,
+                                                const uint16_t* __restrict__ extra_rhs, int64_t n, int bd, int wt,
+                                                uint8_t* __restrict__ verdict) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t* a_hat = smem;
+    uint32_t* xbuf = smem + l * D;
+    copy_a_hat(a_hat, a_hat_g, l);
+    const HalfWarp h = half_warp(xbuf);
+    LaneTw tw;
+    load_lane_tw(tw, tab->w, tab->ws, h.lane);
+    const bool check_wt = wt < D;
+    for (int64_t base = (int64_t)blockIdx.x * HWB; base < n; base += (int64_t)gridDim.x * HWB) {
+        const int64_t raw = base + h.slot;
+        const bool live = raw < n;
+        const int64_t item = live ? raw : n - 1;
+        uint64_t acc[EPT];
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) acc[i] = 0;
+        bool bad = false;
+        for (int i = 0; i < l; ++i) {
+            const int16_t* p = vec_coef + (item * l + i) * D;
+            uint32_t r[EPT];
+            int nz = 0;
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) {
+                int x = __ldg(p + h.lane + 16 * j);
+                bad |= (unsigned)(x + bd) > (unsigned)(2 * bd);
+                nz += (x != 0);
+                r[j] = (uint32_t)(x + (int)m.cq);
+            }
+            if (check_wt) {
+#pragma unroll
+                for (int o = 8; o >= 1; o >>= 1) nz += __shfl_xor_sync(0xFFFFFFFFu, nz, o);
+                bad |= nz > wt;
+            }
+            ntt_fwd_256(r, m, sc, tw, h.xb, h.lane);
+            mac_row(acc, r, a_hat + i * D, h.lane);
+        }
+        uint32_t rhs[EPT];
+        if (vk_ntt) {
+            uint32_t c[EPT], vl[EPT];
+            load_pairs_a(c, ch_pairs + item * ch_wt * 2, ch_wt, h.xb, h.lane, m.cq);
+            ntt_fwd_256(c, m, sc, tw, h.xb, h.lane);
+            load_u16x16(vl, vk_ntt + item * 2 * D + 16 * h.lane);
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) acc[k] += (uint64_t)c[k] * (m.cq2 - vl[k]);
+            load_u16x16(rhs, vk_ntt + item * 2 * D + D + 16 * h.lane);
+        } else {
+            load_u16x16(rhs, rhs_only + item * D + 16 * h.lane);
+        }
+        if (extra_rhs) {
+            uint32_t ex[EPT];
+            load_u16x16(ex, extra_rhs + item * D + 16 * h.lane);
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) rhs[k] += ex[k];
+        }
+        bool eq = true;
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) eq &= reduce64(acc[k], m) == barrett_full(rhs[k], m);
+        const unsigned votes = __ballot_sync(0xFFFFFFFFu, eq && !bad);
+        if (live && h.lane == 0) verdict[item] = (votes & h.mask) == h.mask ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_vec_addsub(ModQ m, const int16_t* __restrict__ a, const int16_t* __restrict__ b, int64_t nelem,
+                             int sub, int16_t* __restrict__ out) {
+    // 8 coefficients (16 bytes) per thread per step
+    const int64_t nvec = nelem / 8;
+    const uint4* a4 = reinterpret_cast<const uint4*>(a);
+    const uint4* b4 = reinterpret_cast<const uint4*>(b);
+    uint4* o4 = reinterpret_cast<uint4*>(out);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        uint4 va = __ldg(a4 + i), vb = __ldg(b4 + i), vo;
+        const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+        uint32_t wo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int a0 = (int16_t)(wa[k] & 0xFFFF), a1 = (int16_t)(wa[k] >> 16);
+            int b0 = (int16_t)(wb[k] & 0xFFFF), b1 = (int16_t)(wb[k] >> 16);
+            if (sub) { b0 = -b0; b1 = -b1; }
+            int r0 = center(barrett_full((uint32_t)(a0 + b0 + 2 * (int)m.cq + (int)m.q), m), m);
+            int r1 = center(barrett_full((uint32_t)(a1 + b1 + 2 * (int)m.cq + (int)m.q), m), m);
+            wo[k] = ((uint32_t)r0 & 0xFFFFu) | ((uint32_t)r1 << 16);
+        }
+        vo = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+        o4[i] = vo;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BKLM aggregate, monomial coefficients: partial[i][p] += s * sig[t][i][(p - k) mod 256] * (p < k ? -1 : 1)
+// grid = (chunks, l); one warp per signature per step, 8 accumulators per thread.
+__global__ void __launch_bounds__(256) k_agg_partial(ModQ m, int l, const int16_t* __restrict__ sigs,
+                                                     const int16_t* __restrict__ ag_pairs, int64_t count,
+                                                     int32_t* __restrict__ partial) {
+    __shared__ int32_t red[D];
+    const int poly = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    red[threadIdx.x] = 0;
+    __syncthreads();
+    int32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const uint32_t* ap = reinterpret_cast<const uint32_t*>(ag_pairs);
+    for (int64_t t = (int64_t)blockIdx.x * 8 + warp; t < count; t += (int64_t)gridDim.x * 8) {
+        const uint32_t pr = __ldg(ap + t);
+        const int k = (int)(pr & 0xFF);
+        const int s = (int)(int16_t)(pr >> 16);
+        const int16_t* row = sigs + (t * l + poly) * D;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const int p = lane + 32 * jj;
+            int v = __ldg(row + ((p - k) & 255));
+            v = (p < k) ? -v : v;
+            acc[jj] += s * v;
+        }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) atomicAdd(&red[lane + 32 * jj], acc[jj]);
+    __syncthreads();
+    {
+        const int p = threadIdx.x;
+        int v = red[p] % (int)m.q;       // keep cross-block / cross-rank sums far from int32 overflow
+        atomicAdd(&partial[poly * D + p], v);
+    }
+}
+
+__global__ void k_agg_finish(ModQ m, const int32_t* __restrict__ partial, int n, int16_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int v = partial[i] % (int)m.q;
+    if (v < 0) v += (int)m.q;
+    out[i] = (int16_t)center((uint32_t)v, m);
+}
+
+// BKLM aggregate_verify right-hand side: partial[p] += (vk_left*c + vk_right)[p] * (s * X^k)^(p), NTT form
+__global__ void __launch_bounds__(RBS) k_aggv_partial(ModQ m, StageConst sc, const NttTables* __restrict__ tab,
+                                                      const uint16_t* __restrict__ vk_ntt,
+                                                      const int16_t* __restrict__ ch_pairs, int ch_wt,
+                                                      const int16_t* __restrict__ ag_pairs, int64_t count,
+                                                      int32_t* __restrict__ partial) {
+    __shared__ __align__(16) uint32_t xbuf[(RBS / 32) * XWARP];
+    __shared__ uint32_t pw[512];
+    __shared__ uint32_t red[D];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) pw[i] = tab->pw[i];
+    for (int i = threadIdx.x; i < D; i += blockDim.x) red[i] = 0;
+    __syncthreads();
+    const HalfWarp h = half_warp(xbuf);
+    LaneTw tw;
+    load_lane_tw(tw, tab->w, tab->ws, h.lane);
+    uint32_t odd[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) odd[k] = 2 * (__brev((uint32_t)(16 * h.lane + k)) >> 24) + 1;
+    uint32_t lacc[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) lacc[k] = 0;
+    const uint32_t* ap = reinterpret_cast<const uint32_t*>(ag_pairs);
+    for (int64_t base = (int64_t)blockIdx.x * HWB; base < count; base += (int64_t)gridDim.x * HWB) {
+        const int64_t raw = base + h.slot;
+        const bool live = raw < count;
+        const int64_t item = live ? raw : count - 1;
+        uint32_t c[EPT], vl[EPT], vr[EPT];
+        load_pairs_a(c, ch_pairs + item * ch_wt * 2, ch_wt, h.xb, h.lane, m.cq);
+        ntt_fwd_256(c, m, sc, tw, h.xb, h.lane);
+        load_u16x16(vl, vk_ntt + item * 2 * D + 16 * h.lane);
+        load_u16x16(vr, vk_ntt + item * 2 * D + D + 16 * h.lane);
+        const uint32_t pr = __ldg(ap + item);
+        const uint32_t kk = pr & 0xFF;
+        const bool neg = (int16_t)(pr >> 16) < 0;
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            uint32_t t = barrett_full(barrett_lazy(barrett_full(c[k], m) * vl[k], m) + vr[k], m);
+            uint32_t u = mulmod_full(t, pw[(odd[k] * kk) & 511], m);
+            u = neg ? csub(m.q - u, m.q) : u;
+            if (live) lacc[k] = csub(lacc[k] + u, m.q);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) atomicAdd(&red[16 * h.lane + k], lacc[k]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x) atomicAdd(&partial[i], (int32_t)(red[i] % m.q));
+}
+
+// bounds on ag_sig (with lower limits), key_ch * ag_sig == partial sum; one half-warp
+__global__ void __launch_bounds__(32) k_aggv_finish(ModQ m, StageConst sc, const NttTables* __restrict__ tab,
+                                                    const uint32_t* __restrict__ a_hat, int l,
+                                                    const int32_t* __restrict__ partial,
+                                                    const int16_t* __restrict__ ag_sig, int64_t total, int ag_cap,
+                                                    int avf_bd, int avf_wt, uint8_t* __restrict__ verdict) {
+    __shared__ __align__(16) uint32_t xbuf[XWARP];
+    const HalfWarp h = half_warp(xbuf);
+    LaneTw tw;
+    load_lane_tw(tw, tab->w, tab->ws, h.lane);
+    uint64_t acc[EPT];
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) acc[i] = 0;
+    int maxabs = 0, maxw = 0;
+    for (int i = 0; i < l; ++i) {
+        const int16_t* p = ag_sig + i * D;
+        uint32_t r[EPT];
+        int nz = 0;
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            int x = __ldg(p + h.lane + 16 * j);
+            maxabs = max(maxabs, abs(x));
+            nz += (x != 0);
+            r[j] = (uint32_t)(x + (int)m.cq);
+        }
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) nz += __shfl_xor_sync(0xFFFFFFFFu, nz, o);
+        maxw = max(maxw, nz);
+        ntt_fwd_256(r, m, sc, tw, h.xb, h.lane);
+#pragma unroll
+        for (int g = 0; g < EPT; ++g) acc[g] += (uint64_t)r[g] * __ldg(a_hat + i * D + 16 * h.lane + g);
+    }
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) maxabs = max(maxabs, __shfl_xor_sync(0xFFFFFFFFu, maxabs, o));
+    bool ok = maxabs >= 1 && maxabs <= avf_bd && maxw >= 1 && maxw <= avf_wt && total >= 1 && total <= ag_cap;
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        int v = partial[16 * h.lane + k] % (int)m.q;
+        if (v < 0) v += (int)m.q;
+        ok &= reduce64(acc[k], m) == (uint32_t)v;
+    }
+    const unsigned votes = __ballot_sync(0xFFFFFFFFu, ok);
+    if (threadIdx.x == 0) verdict[0] = (votes & 0xFFFFu) == 0xFFFFu ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename K>
+int resident_blocks(K kernel, int threads, size_t smem) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess || nb < 1) nb = 1;
+    return nb;
+}
+
+inline unsigned persistent_grid(int64_t items, int per_block, int num_sms, int resident) {
+    int64_t need = (items + per_block - 1) / per_block;
+    int64_t cap = (int64_t)num_sms * resident;
+    return (unsigned)(need < cap ? need : cap);
+}
+
+inline size_t ring_smem(int l) { return (size_t)l * D * 4 + (size_t)(RBS / 32) * XWARP * 4; }
+
+template <typename K>
+cudaError_t allow_smem(K kernel, size_t smem) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+}  // namespace
+
+cudaError_t launch_ntt_fwd(const RingCtx& c, const int16_t* coef, int64_t npoly, uint16_t* out, cudaStream_t st) {
+    if (npoly <= 0) return cudaSuccess;
+    unsigned grid = persistent_grid(npoly, HWB, c.num_sms, resident_blocks(k_ntt_fwd, RBS, 0));
+    k_ntt_fwd<<<grid, RBS, 0, st>>>(c.m, c.sc, c.tab, coef, npoly, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ntt_inv(const RingCtx& c, const uint16_t* in, int64_t npoly, int16_t* coef, cudaStream_t st) {
+    if (npoly <= 0) return cudaSuccess;
+    unsigned grid = persistent_grid(npoly, HWB, c.num_sms, resident_blocks(k_ntt_inv, RBS, 0));
+    k_ntt_inv<<<grid, RBS, 0, st>>>(c.m, c.sc, c.tab, in, npoly, coef);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_poly_mul(const RingCtx& c, const int16_t* a, const int16_t* b, int64_t npoly, int16_t* out,
+                            cudaStream_t st) {
+    if (npoly <= 0) return cudaSuccess;
+    unsigned grid = persistent_grid(npoly, HWB, c.num_sms, resident_blocks(k_poly_mul, RBS, 0));
+    k_poly_mul<<<grid, RBS, 0, st>>>(c.m, c.sc, c.tab, a, b, npoly, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_matvec(const RingCtx& c, const int16_t* vec_coef, int64_t nvec, uint16_t* vec_ntt,
+                          uint16_t* y_ntt, int16_t* y_coef, cudaStream_t st) {
+    if (nvec <= 0) return cudaSuccess;
+    size_t smem = ring_smem(c.l);
+    cudaError_t e = allow_smem(k_matvec, smem);
+    if (e != cudaSuccess) return e;
+    unsigned grid = persistent_grid(nvec, HWB, c.num_sms, resident_blocks(k_matvec, RBS, smem));
+    k_matvec<<<grid, RBS, smem, st>>>(c.m, c.sc, c.tab, c.a_hat, c.l, vec_coef, nvec, vec_ntt, y_ntt, y_coef);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sign(const RingCtx& c, const uint16_t* sk_ntt, const int16_t* ch_pairs, int ch_wt, int64_t n,
+                        int16_t* sig, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    unsigned grid = persistent_grid(n, HWB, c.num_sms, resident_blocks(k_sign, RBS, 0));
+    k_sign<<<grid, RBS, 0, st>>>(c.m, c.sc, c.tab, c.l, sk_ntt, ch_pairs, ch_wt, n, sig);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_verify(const RingCtx& c, const int16_t* vec_coef, const uint16_t* vk_ntt, const int16_t* ch_pairs,
+                          int ch_wt, const uint16_t* rhs_only, const uint16_t* extra_rhs, int64_t n, int bd, int wt,
+                          uint8_t* verdict, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    size_t smem = ring_smem(c.l);
+    cudaError_t e = allow_smem(k_verify, smem);
+    if (e != cudaSuccess) return e;
+    unsigned grid = persistent_grid(n, HWB, c.num_sms, resident_blocks(k_verify, RBS, smem));
+    k_verify<<<grid, RBS, smem, st>>>(c.m, c.sc, c.tab, c.a_hat, c.l, vec_coef, vk_ntt, ch_pairs, ch_wt, rhs_only,
+                                      extra_rhs, n, bd, wt, verdict);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_vec_addsub(const RingCtx& c, const int16_t* a, const int16_t* b, int64_t nelem, int sub,
+                              int16_t* out, cudaStream_t st) {
+    if (nelem <= 0) return cudaSuccess;
+    int64_t need = (nelem / 8 + 255) / 256;
+    int64_t cap = (int64_t)c.num_sms * 8;
+    k_vec_addsub<<<(unsigned)(need < cap ? need : cap), 256, 0, st>>>(c.m, a, b, nelem, sub, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_agg_partial(const RingCtx& c, const int16_t* sigs, const int16_t* ag_pairs, int64_t count,
+                               int32_t* partial, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    int64_t need = (count + 63) / 64;                 // >= 8 signatures per warp
+    int64_t cap = (int64_t)c.num_sms * 4 / c.l + 1;
+    dim3 grid((unsigned)(need < cap ? need : cap), (unsigned)c.l);
+    k_agg_partial<<<grid, 256, 0, st>>>(c.m, c.l, sigs, ag_pairs, count, partial);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_agg_finish(const RingCtx& c, const int32_t* partial, int16_t* ag_sig, cudaStream_t st) {
+    int n = c.l * D;
+    k_agg_finish<<<(n + 255) / 256, 256, 0, st>>>(c.m, partial, n, ag_sig);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_aggv_partial(const RingCtx& c, const uint16_t* vk_ntt, const int16_t* ch_pairs, int ch_wt,
+                                const int16_t* ag_pairs, int64_t count, int32_t* partial, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    unsigned grid = persistent_grid(count, HWB, c.num_sms, resident_blocks(k_aggv_partial, RBS, 0));
+    k_aggv_partial<<<grid, RBS, 0, st>>>(c.m, c.sc, c.tab, vk_ntt, ch_pairs, ch_wt, ag_pairs, count, partial);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_aggv_finish(const RingCtx& c, const int32_t* partial, const int16_t* ag_sig, int64_t total,
+                               int ag_cap, int avf_bd, int avf_wt, uint8_t* verdict, cudaStream_t st) {
+    k_aggv_finish<<<1, 32, 0, st>>>(c.m, c.sc, c.tab, c.a_hat, c.l, partial, ag_sig, total, ag_cap, avf_bd, avf_wt,
+                                    verdict);
+    return cudaGetLastError();
+}
+
+}  // namespace lcb

@@ -1,0 +1,263 @@
+"""Array-level Python face of the lcb200 C ABI.
+
+Every method takes host (numpy) or device (torch.cuda) arrays; the library detects which.
+Outputs are numpy arrays unless ``device=True`` (then torch CUDA tensors on the engine's
+GPU, left on its stream).  Layouts are the ones documented in include/lcb200.h.
+"""
+from ctypes import byref, c_void_p
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import LcbError, LcbScheme
+
+D = 256
+Bytes = Union[bytes, bytearray, str]
+
+
+def ragged(items: Sequence[Bytes]) -> Tuple[np.ndarray, np.ndarray]:
+    """list of byte strings (str is UTF-8 encoded, as lattice_algebra does) -> (blob, offsets)."""
+    enc = [i.encode() if isinstance(i, str) else bytes(i) for i in items]
+    off = np.zeros(len(enc) + 1, dtype=np.int64)
+    if enc:
+        np.cumsum([len(e) for e in enc], out=off[1:])
+    blob = np.frombuffer(b''.join(enc), dtype=np.uint8) if off[-1] else np.zeros(0, dtype=np.uint8)
+    return np.ascontiguousarray(blob), off
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith('torch')
+
+
+def _addr(x):
+    if x is None:
+        return None
+    if _is_torch(x):
+        if not x.is_contiguous():
+            raise ValueError('device tensors must be contiguous')
+        return c_void_p(x.data_ptr())
+    if not isinstance(x, np.ndarray) or not x.flags['C_CONTIGUOUS']:
+        raise ValueError('host buffers must be C-contiguous numpy arrays')
+    return c_void_p(x.ctypes.data)
+
+
+def make_scheme(sk_bd=1, sk_wt=1, ch_bd=1, ch_wt=1, ag_bd=1, ag_wt=1, wit_bd=1, wit_wt=1, sk_salt='SK_SALT',
+                ch_salt='CH_SALT', ag_salt='AG_SALT', wit_salt='WIT_SALT') -> LcbScheme:
+    s = LcbScheme()
+    s.sk_bd, s.sk_wt, s.ch_bd, s.ch_wt = sk_bd, sk_wt, ch_bd, ch_wt
+    s.ag_bd, s.ag_wt, s.wit_bd, s.wit_wt = ag_bd, ag_wt, wit_bd, wit_wt
+    for name, val in (('sk_salt', sk_salt), ('ch_salt', ch_salt), ('ag_salt', ag_salt), ('wit_salt', wit_salt)):
+        raw = val.encode()
+        if len(raw) >= _ffi.LCB_SALT_MAX:
+            raise ValueError(f'{name} longer than {_ffi.LCB_SALT_MAX - 1} bytes')
+        setattr(s, name, raw)
+    return s
+
+
+class Engine(object):
+    """One GPU context: LatticeParameters (q, d, l) + secpar + the NTT-resident public row key_ch."""
+
+    def __init__(self, secpar: int, modulus: int, degree: int, length: int, device: int = 0):
+        self._lib = _ffi.load()
+        self._ctx = c_void_p()
+        st = self._lib.lcb_ctx_create(byref(self._ctx), device, secpar, modulus, degree, length)
+        if st != _ffi.LCB_OK:
+            detail = self._lib.lcb_last_error(None).decode() or self._lib.lcb_strerror(st).decode()
+            self._ctx = c_void_p()
+            raise LcbError(st, detail)
+        self.secpar, self.q, self.d, self.l, self.device = secpar, modulus, degree, length, device
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, '_ctx', None) is not None and self._ctx.value:
+            self._lib.lcb_ctx_destroy(self._ctx)
+            self._ctx = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st: int):
+        if st != _ffi.LCB_OK:
+            detail = self._lib.lcb_last_error(self._ctx).decode() or self._lib.lcb_strerror(st).decode()
+            raise LcbError(st, f'{self._lib.lcb_strerror(st).decode()} ({detail})')
+
+    def _out(self, shape, dtype, device: bool):
+        if device:
+            import torch
+            tdt = {np.int16: torch.int16, np.uint16: torch.uint16, np.uint8: torch.uint8, np.int32: torch.int32}[dtype]
+            return torch.empty(shape, dtype=tdt, device=f'cuda:{self.device}')
+        return np.empty(shape, dtype=dtype)
+
+    def use_torch_stream(self):
+        """Run on torch's current CUDA stream (so torch.cuda.Event timing sees the kernels)."""
+        import torch
+        self._ck(self._lib.lcb_ctx_set_stream(self._ctx, c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+
+    def synchronize(self):
+        self._ck(self._lib.lcb_synchronize(self._ctx))
+
+    @property
+    def root_of_unity(self) -> int:
+        return self._lib.lcb_ctx_root_of_unity(self._ctx)
+
+    @property
+    def launch_count(self) -> int:
+        return self._lib.lcb_launch_count(self._ctx)
+
+    @staticmethod
+    def _rag(items):
+        if isinstance(items, tuple) and len(items) == 2:
+            return items            # already (blob, offsets); host or device
+        return ragged(items)
+
+    @staticmethod
+    def _count(off) -> int:
+        return int(off.shape[0]) - 1
+
+    # ------------------------------------------------------------------ K1 / K2
+    def set_key_ch(self, key_ch_coef):
+        self._ck(self._lib.lcb_set_key_ch(self._ctx, _addr(key_ch_coef)))
+
+    def shake256(self, items, out_len: int, device: bool = False):
+        blob, off = self._rag(items)
+        n = self._count(off)
+        out = self._out((n, out_len), np.uint8, device)
+        self._ck(self._lib.lcb_shake256_batch(self._ctx, _addr(blob), _addr(off), n, _addr(out), out_len))
+        return out
+
+    def hash2polyvec(self, salt: str, msgs, bd: int, wt: int, vec_len: int, want_dense: bool = True,
+                     want_pairs: bool = False, device: bool = False):
+        blob, off = self._rag(msgs)
+        n = self._count(off)
+        dense = self._out((n, vec_len, D), np.int16, device) if want_dense else None
+        pairs = self._out((n, vec_len, wt, 2), np.int16, device) if want_pairs else None
+        self._ck(self._lib.lcb_hash2polyvec_batch(self._ctx, salt.encode(), _addr(blob), _addr(off), n, bd, wt,
+                                                  vec_len, _addr(dense), _addr(pairs)))
+        return dense, pairs
+
+    # ------------------------------------------------------------------ K3 / K4 / K6
+    def ntt_fwd(self, coef, device: bool = False):
+        npoly = int(np.prod(coef.shape[:-1]))
+        out = self._out(tuple(coef.shape), np.uint16, device)
+        self._ck(self._lib.lcb_ntt_fwd_batch(self._ctx, _addr(coef), npoly, _addr(out)))
+        return out
+
+    def ntt_inv(self, ntt, device: bool = False):
+        npoly = int(np.prod(ntt.shape[:-1]))
+        out = self._out(tuple(ntt.shape), np.int16, device)
+        self._ck(self._lib.lcb_ntt_inv_batch(self._ctx, _addr(ntt), npoly, _addr(out)))
+        return out
+
+    def poly_mul(self, a, b, device: bool = False):
+        npoly = int(np.prod(a.shape[:-1]))
+        out = self._out(tuple(a.shape), np.int16, device)
+        self._ck(self._lib.lcb_poly_mul_batch(self._ctx, _addr(a), _addr(b), npoly, _addr(out)))
+        return out
+
+    # ------------------------------------------------------------------ LM one-time signatures
+    def lm_keygen(self, sch: LcbScheme, seeds, want_sk_coef: bool = True, want_sk_ntt: bool = True,
+                  want_vk_ntt: bool = True, want_vk_coef: bool = True, device: bool = False):
+        blob, off = self._rag(seeds)
+        n = self._count(off)
+        sk_coef = self._out((n, 2, self.l, D), np.int16, device) if want_sk_coef else None
+        sk_ntt = self._out((n, 2, self.l, D), np.uint16, device) if want_sk_ntt else None
+        vk_ntt = self._out((n, 2, D), np.uint16, device) if want_vk_ntt else None
+        vk_coef = self._out((n, 2, D), np.int16, device) if want_vk_coef else None
+        self._ck(self._lib.lcb_lm_keygen_batch(self._ctx, byref(sch), _addr(blob), _addr(off), n, _addr(sk_coef),
+                                               _addr(sk_ntt), _addr(vk_ntt), _addr(vk_coef)))
+        return sk_coef, sk_ntt, vk_ntt, vk_coef
+
+    def challenge(self, sch: LcbScheme, chmsgs, device: bool = False):
+        blob, off = self._rag(chmsgs)
+        n = self._count(off)
+        pairs = self._out((n, sch.ch_wt, 2), np.int16, device)
+        self._ck(self._lib.lcb_challenge_batch(self._ctx, byref(sch), _addr(blob), _addr(off), n, _addr(pairs)))
+        return pairs
+
+    def lm_sign(self, sch: LcbScheme, sk_ntt, chmsgs, device: bool = False):
+        blob, off = self._rag(chmsgs)
+        n = self._count(off)
+        sig = self._out((n, self.l, D), np.int16, device)
+        self._ck(self._lib.lcb_lm_sign_batch(self._ctx, byref(sch), _addr(sk_ntt), _addr(blob), _addr(off), n,
+                                             _addr(sig)))
+        return sig
+
+    def lm_verify(self, sch: LcbScheme, vk_ntt, chmsgs, sig, bd: int, wt: int, st_ntt=None, device: bool = False,
+                  out=None):
+        blob, off = self._rag(chmsgs)
+        n = self._count(off)
+        verdict = out if out is not None else self._out((n,), np.uint8, device)
+        self._ck(self._lib.lcb_lm_verify_batch(self._ctx, byref(sch), _addr(vk_ntt), _addr(blob), _addr(off),
+                                               _addr(sig), _addr(st_ntt), n, bd, wt, _addr(verdict)))
+        return verdict
+
+    # ------------------------------------------------------------------ BKLM aggregation
+    def agg_coefs(self, sch: LcbScheme, agmsg, first: int, count: int, device: bool = False):
+        if isinstance(agmsg, (str, bytes, bytearray)):
+            agmsg = np.frombuffer(agmsg.encode() if isinstance(agmsg, str) else bytes(agmsg), dtype=np.uint8)
+        pairs = self._out((count, sch.ag_wt, 2), np.int16, device)
+        self._ck(self._lib.lcb_bklm_agg_coefs(self._ctx, byref(sch), _addr(agmsg), int(agmsg.shape[0]), first,
+                                              count, _addr(pairs)))
+        return pairs
+
+    def aggregate_partial(self, sch: LcbScheme, sig_sorted, ag_pairs, device: bool = False):
+        count = int(sig_sorted.shape[0])
+        partial = self._out((self.l, D), np.int32, device)
+        self._ck(self._lib.lcb_bklm_aggregate_partial(self._ctx, byref(sch), _addr(sig_sorted), _addr(ag_pairs),
+                                                      None, 0, 0, count, _addr(partial)))
+        return partial
+
+    def aggregate_finish(self, partial_sum, device: bool = False):
+        out = self._out((self.l, D), np.int16, device)
+        self._ck(self._lib.lcb_bklm_aggregate_finish(self._ctx, _addr(partial_sum), _addr(out)))
+        return out
+
+    def aggverify_partial(self, sch: LcbScheme, vk_ntt_sorted, chmsgs_sorted, ag_pairs, device: bool = False):
+        blob, off = self._rag(chmsgs_sorted)
+        count = self._count(off)
+        partial = self._out((D,), np.int32, device)
+        self._ck(self._lib.lcb_bklm_aggverify_partial(self._ctx, byref(sch), _addr(vk_ntt_sorted), _addr(blob),
+                                                      _addr(off), _addr(ag_pairs), None, 0, 0, count,
+                                                      _addr(partial)))
+        return partial
+
+    def aggverify_finish(self, partial_sum, ag_sig, total: int, ag_cap: int, avf_bd: int, avf_wt: int) -> bool:
+        verdict = np.zeros(1, dtype=np.uint8)
+        self._ck(self._lib.lcb_bklm_aggverify_finish(self._ctx, _addr(partial_sum), _addr(ag_sig), total, ag_cap,
+                                                     avf_bd, avf_wt, _addr(verdict)))
+        return bool(verdict[0])
+
+    # ------------------------------------------------------------------ adaptor signatures
+    def witgen(self, sch: LcbScheme, seeds, want_wit: bool = True, want_st_ntt: bool = True,
+               want_st_coef: bool = True, device: bool = False):
+        blob, off = self._rag(seeds)
+        n = self._count(off)
+        wit = self._out((n, self.l, D), np.int16, device) if want_wit else None
+        st_ntt = self._out((n, D), np.uint16, device) if want_st_ntt else None
+        st_coef = self._out((n, D), np.int16, device) if want_st_coef else None
+        self._ck(self._lib.lcb_adaptor_witgen_batch(self._ctx, byref(sch), _addr(blob), _addr(off), n, _addr(wit),
+                                                    _addr(st_ntt), _addr(st_coef)))
+        return wit, st_ntt, st_coef
+
+    def vec_add(self, a, b, device: bool = False):
+        npoly = int(np.prod(a.shape[:-1]))
+        out = self._out(tuple(a.shape), np.int16, device)
+        self._ck(self._lib.lcb_vec_add_batch(self._ctx, _addr(a), _addr(b), npoly, _addr(out)))
+        return out
+
+    def vec_sub(self, a, b, device: bool = False):
+        npoly = int(np.prod(a.shape[:-1]))
+        out = self._out(tuple(a.shape), np.int16, device)
+        self._ck(self._lib.lcb_vec_sub_batch(self._ctx, _addr(a), _addr(b), npoly, _addr(out)))
+        return out
+
+    def witness_verify(self, wit_coef, st_ntt, bd: int, wt: int, device: bool = False):
+        n = int(wit_coef.shape[0])
+        verdict = self._out((n,), np.uint8, device)
+        self._ck(self._lib.lcb_adaptor_witness_verify_batch(self._ctx, _addr(wit_coef), _addr(st_ntt), n, bd, wt,
+                                                            _addr(verdict)))
+        return verdict

@@ -1,0 +1,343 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI with HOST
+buffers, against (a) the golden fixtures produced from the reference's own modules
+(oracle/gen_golden.py) and (b) the restated CPU oracle on seeded inputs.  Bit-exact everywhere."""
+import hashlib
+import json
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SHIPPED = {128: dict(q=11777, l=13, sk_bd=45, ch_wt=20), 256: dict(q=39937, l=23, sk_bd=65, ch_wt=50)}
+D = 256
+
+
+@pytest.fixture(scope='module')
+def engines(golden):
+    from lattice_cryptography_b200 import Engine
+    arrays, _ = golden
+    out = {}
+    for secpar, p in SHIPPED.items():
+        e = Engine(secpar, p['q'], D, p['l'])
+        e.set_key_ch(np.ascontiguousarray(arrays[f's{secpar}_key_ch']))
+        out[secpar] = e
+    yield out
+    for e in out.values():
+        e.close()
+
+
+def scheme(secpar):
+    from lattice_cryptography_b200 import make_scheme
+    p = SHIPPED[secpar]
+    return make_scheme(sk_bd=p['sk_bd'], sk_wt=256, ch_bd=1, ch_wt=p['ch_wt'], ag_bd=1, ag_wt=1, wit_bd=1, wit_wt=20)
+
+
+def negacyclic_mul(a, b, q):
+    full = np.convolve(a.astype(np.int64), b.astype(np.int64))
+    res = full[:D].copy()
+    res[:D - 1] -= full[D:]
+    res %= q
+    res[res > (q - 1) // 2] -= q
+    return res
+
+
+# ------------------------------------------------------------------------------------------- K1
+def test_shake256_matches_hashlib(engines):
+    e = engines[128]
+    rng = np.random.default_rng(1)
+    lens = [0, 1, 7, 8, 9, 134, 135, 136, 137, 271, 272, 273, 1000] + [int(x) for x in rng.integers(0, 700, 300)]
+    items = [bytes(rng.integers(0, 256, n, dtype=np.uint8)) for n in lens]
+    for out_len in (1, 32, 136, 137, 647):
+        got = e.shake256(items, out_len)
+        for it, row in zip(items, got):
+            assert bytes(row) == hashlib.shake_256(it).digest(out_len)
+
+
+def test_shake256_empty_batch_and_long_squeeze(engines):
+    e = engines[256]
+    assert e.shake256([], 10).shape == (0, 10)
+    got = e.shake256([b'abc'], 5000)
+    assert bytes(got[0]) == hashlib.shake_256(b'abc').digest(5000)
+
+
+# ------------------------------------------------------------------------------------------- K2
+@pytest.mark.parametrize('secpar', [128, 256])
+def test_sampler_golden_pairs(engines, golden, secpar):
+    arrays, meta = golden
+    e = engines[secpar]
+    m = meta['cases'][str(secpar)]
+    p = SHIPPED[secpar]
+    # key_ch: bd = q//2 (16-bit limb path), wt = d
+    dense, pairs = e.hash2polyvec('KEY_CH_SEED', [meta['key_ch_seed']], p['q'] // 2, D, p['l'], want_pairs=True)
+    assert np.array_equal(pairs[0], arrays[f's{secpar}_key_ch_pairs'])
+    assert np.array_equal(dense[0], arrays[f's{secpar}_key_ch'])
+    # signing key left half of case 0
+    dense, pairs = e.hash2polyvec('SK_SALTLEFT', [m['lm'][0]['seed']], p['sk_bd'], D, p['l'], want_pairs=True)
+    assert np.array_equal(pairs[0], arrays[f's{secpar}_lm0_skL_pairs'])
+    assert np.array_equal(dense[0], arrays[f's{secpar}_lm0_skL'])
+    # challenges (ragged messages, wt < d, bd = 1)
+    chmsgs = [c['chmsg'] for c in m['lm']]
+    dense, pairs = e.hash2polyvec('CH_SALT', chmsgs, 1, p['ch_wt'], 1, want_pairs=True)
+    for j in range(len(chmsgs)):
+        assert np.array_equal(pairs[j, 0], arrays[f's{secpar}_lm{j}_c_pairs'])
+        assert np.array_equal(dense[j, 0], arrays[f's{secpar}_lm{j}_c'])
+    # adaptor witnesses
+    dense, pairs = e.hash2polyvec('WIT_SALT', [a['wit_seed'] for a in m['adaptor']], 1, 20, p['l'], want_pairs=True)
+    for j in range(len(m['adaptor'])):
+        assert np.array_equal(pairs[j], arrays[f's{secpar}_ad{j}_wit_pairs'])
+        assert np.array_equal(dense[j], arrays[f's{secpar}_ad{j}_wit'])
+
+
+@pytest.mark.parametrize('secpar,bd,wt,vec_len', [(128, 1, 1, 1), (128, 3, 7, 2), (128, 64, 256, 1), (256, 45, 100, 3),
+                                                  (128, 300, 33, 2), (256, 1, 256, 1), (128, 2, 2, 5)])
+def test_sampler_vs_oracle_random(engines, secpar, bd, wt, vec_len):
+    import lattice_algebra as la
+    import schemes
+    e = engines[secpar]
+    p = SHIPPED[secpar]
+    lp = schemes.lattice_parameters(p['q'], D, vec_len)       # vec_len plays `length` for the oracle
+    rng = np.random.default_rng(secpar + bd + wt)
+    msgs = [''.join(chr(int(c)) for c in rng.integers(32, 127, int(n))) for n in rng.integers(0, 300, 40)]
+    dense, pairs = e.hash2polyvec('SALT_X', msgs, bd, wt, vec_len, want_pairs=True)
+    bti, btd = la.bits_to_indices(secpar, D, wt), la.bits_to_decode(secpar, bd)
+    nb = la.get_gen_bytes_per_poly(secpar, lp, la.UNIFORM_INFINITY_WEIGHT, {}, wt, bti, btd)
+    for i, msg in enumerate(msgs):
+        bits = la.binary_digest(msg, nb * vec_len, 'SALT_X')
+        for v in range(vec_len):
+            cd = la.decode2polycoefs(secpar, lp, la.UNIFORM_INFINITY_WEIGHT, {'bd': bd, 'wt': wt},
+                                     bits[v * 8 * nb:(v + 1) * 8 * nb], wt, bti, btd)
+            assert [list(map(int, r)) for r in pairs[i, v]] == [[k, c] for k, c in cd.items()]
+            want = np.zeros(D, dtype=np.int16)
+            for k, c in cd.items():
+                want[k] = c
+            assert np.array_equal(dense[i, v], want)
+
+
+# ------------------------------------------------------------------------------------------- K3/K4/K6
+@pytest.mark.parametrize('secpar', [128, 256])
+def test_ntt_roundtrip_and_product(engines, secpar):
+    e = engines[secpar]
+    q = SHIPPED[secpar]['q']
+    rng = np.random.default_rng(7)
+    h = (q - 1) // 2
+    a = rng.integers(-h, h + 1, (37, D)).astype(np.int16)
+    b = rng.integers(-h, h + 1, (37, D)).astype(np.int16)
+    a[0] = 0
+    a[1] = h
+    b[1] = -h
+    a[2, :] = 0
+    a[2, 255] = 1          # X^255
+    fa = e.ntt_fwd(a)
+    assert fa.dtype == np.uint16 and int(fa.max()) < q
+    assert np.array_equal(e.ntt_inv(fa), a)
+    prod = e.poly_mul(a, b)
+    for i in range(a.shape[0]):
+        assert np.array_equal(prod[i], negacyclic_mul(a[i], b[i], q))
+    # slot p of the NTT form holds a(psi^(2*bitrev8(p)+1)) with psi = least primitive 512th root
+    psi = e.root_of_unity
+    assert pow(psi, 512, q) == 1 and pow(psi, 256, q) != 1
+    x = np.zeros((1, D), dtype=np.int16)
+    x[0, 1] = 1            # the polynomial X
+    fx = e.ntt_fwd(x)[0]
+    for p_ in (0, 1, 2, 77, 255):
+        br = int(format(p_, '08b')[::-1], 2)
+        assert int(fx[p_]) == pow(psi, 2 * br + 1, q)
+
+
+def test_ntt_any_int16_input(engines):
+    e = engines[128]
+    q = 11777
+    x = np.array([[-32768, 32767] * 128], dtype=np.int16)
+    back = e.ntt_inv(e.ntt_fwd(x))[0].astype(np.int64)
+    assert np.array_equal((back - x[0]) % q, np.zeros(D, dtype=np.int64))
+
+
+# ------------------------------------------------------------------------------------------- LM-OTS
+@pytest.mark.parametrize('secpar', [128, 256])
+def test_lm_golden(engines, golden, secpar):
+    arrays, meta = golden
+    e = engines[secpar]
+    m = meta['cases'][str(secpar)]
+    sch = scheme(secpar)
+    cases = m['lm']
+    sk_coef, sk_ntt, vk_ntt, vk_coef = e.lm_keygen(sch, [c['seed'] for c in cases])
+    for j in range(len(cases)):
+        pre = f's{secpar}_lm{j}'
+        assert np.array_equal(sk_coef[j, 0], arrays[pre + '_skL'])
+        assert np.array_equal(sk_coef[j, 1], arrays[pre + '_skR'])
+        assert np.array_equal(vk_coef[j, 0], arrays[pre + '_vkL'])
+        assert np.array_equal(vk_coef[j, 1], arrays[pre + '_vkR'])
+    assert np.array_equal(e.ntt_inv(vk_ntt), vk_coef)
+    assert np.array_equal(e.ntt_inv(sk_ntt), sk_coef)
+    chmsgs = [c['chmsg'] for c in cases]
+    sig = e.lm_sign(sch, sk_ntt, chmsgs)
+    for j in range(len(cases)):
+        assert np.array_equal(sig[j], arrays[f's{secpar}_lm{j}_sig'])
+    vf_bd, vf_wt = m['vf_bd'], m['vf_wt']
+    assert e.lm_verify(sch, vk_ntt, chmsgs, sig, vf_bd, vf_wt).tolist() == [int(c['verdict']) for c in cases]
+    bad = [c['chmsg'] + '!' for c in cases]
+    assert e.lm_verify(sch, vk_ntt, bad, sig, vf_bd, vf_wt).tolist() == [int(c['verdict_bad_msg']) for c in cases]
+    t1 = np.stack([arrays[f's{secpar}_lm{j}_sig_t1'] for j in range(len(cases))])
+    t2 = np.stack([arrays[f's{secpar}_lm{j}_sig_t2'] for j in range(len(cases))])
+    assert e.lm_verify(sch, vk_ntt, chmsgs, t1, vf_bd, vf_wt).tolist() == [int(c['verdict_t1']) for c in cases]
+    assert e.lm_verify(sch, vk_ntt, chmsgs, t2, vf_bd, vf_wt).tolist() == [int(c['verdict_t2']) for c in cases]
+    # boundary of the norm test: a bound equal to the actual max norm passes, one below fails
+    n0 = int(np.abs(sig[0]).max())
+    assert e.lm_verify(sch, vk_ntt[:1], chmsgs[:1], sig[:1], n0, vf_wt).tolist() == [1]
+    assert e.lm_verify(sch, vk_ntt[:1], chmsgs[:1], sig[:1], n0 - 1, vf_wt).tolist() == [0]
+    # weight test: every signature polynomial here is dense, so wt = 255 may reject
+    w0 = int((sig[0] != 0).sum(axis=1).max())
+    assert e.lm_verify(sch, vk_ntt[:1], chmsgs[:1], sig[:1], vf_bd, w0).tolist() == [1]
+    assert e.lm_verify(sch, vk_ntt[:1], chmsgs[:1], sig[:1], vf_bd, w0 - 1).tolist() == [0]
+
+
+@pytest.mark.parametrize('secpar,n', [(128, 300), (256, 131)])
+def test_lm_batch_vs_oracle(engines, golden, secpar, n):
+    """Seeded batch with ragged messages: every sk/vk/sig coefficient against the CPU oracle on a
+    subsample, every verdict against the construction rule (every 5th triple tampered)."""
+    import schemes
+    arrays, meta = golden
+    e = engines[secpar]
+    sch = scheme(secpar)
+    m = meta['cases'][str(secpar)]
+    rng = np.random.default_rng(20260101 + secpar)
+    seeds = [''.join(rng.choice(['0', '1'], secpar)) for _ in range(n)]
+    chmsgs = [f'<lattice_cryptography.one_time_keys.OneTimeVerificationKey object at 0x7f{i:010x}>, ' +
+              ''.join(rng.choice(['0', '1'], int(rng.integers(0, 2 * secpar)))) for i in range(n)]
+    sk_coef, sk_ntt, vk_ntt, vk_coef = e.lm_keygen(sch, seeds)
+    sig = e.lm_sign(sch, sk_ntt, chmsgs)
+    tampered = sig.copy()
+    expect = np.ones(n, dtype=np.uint8)
+    for i in range(0, n, 5):
+        kind = (i // 5) % 3
+        if kind == 0:
+            tampered[i, i % tampered.shape[1], (3 * i) % D] += 1
+        elif kind == 1:
+            tampered[i, (i + 1) % tampered.shape[1], (7 * i) % D] = m['vf_bd'] + 1
+        expect[i] = 0
+    msgs2 = list(chmsgs)
+    for i in range(0, n, 5):
+        if (i // 5) % 3 == 2:
+            msgs2[i] = chmsgs[i] + '0'
+    got = e.lm_verify(sch, vk_ntt, msgs2, tampered, m['vf_bd'], m['vf_wt'])
+    assert np.array_equal(got, expect)
+    assert e.lm_verify(sch, vk_ntt, chmsgs, sig, m['vf_bd'], m['vf_wt']).all()
+    # oracle subsample
+    key_ch = schemes.vec_from_dense(schemes.lattice_parameters(SHIPPED[secpar]['q'], D, SHIPPED[secpar]['l']),
+                                    arrays[f's{secpar}_key_ch'].tolist())
+    pp = schemes.make_lm_parameters(secpar, key_ch)
+    for i in (0, n // 2, n - 1):
+        skl, skr, vkl, vkr = schemes.lm_keygen_one(pp, seeds[i])
+        assert schemes.dense_of_vec(skl) == sk_coef[i, 0].tolist()
+        assert schemes.dense_of_vec(skr) == sk_coef[i, 1].tolist()
+        assert schemes.dense_of_poly(vkl) == vk_coef[i, 0].tolist()
+        assert schemes.dense_of_poly(vkr) == vk_coef[i, 1].tolist()
+        osig = schemes.lm_sign(pp, skl, skr, chmsgs[i])
+        assert schemes.dense_of_vec(osig) == sig[i].tolist()
+        assert schemes.lm_verify(pp, vkl, vkr, msgs2[i], schemes.vec_from_dense(pp['lp'], tampered[i].tolist())) == \
+            bool(expect[i])
+
+
+def test_device_buffers_and_empty_batches(engines, golden):
+    import torch
+    arrays, meta = golden
+    e = engines[128]
+    sch = scheme(128)
+    cases = meta['cases']['128']['lm']
+    seeds = [c['seed'] for c in cases]
+    sk_coef, sk_ntt, vk_ntt, vk_coef = e.lm_keygen(sch, seeds, device=True)
+    assert sk_ntt.is_cuda
+    from lattice_cryptography_b200 import ragged
+    blob, off = ragged([c['chmsg'] for c in cases])
+    dmsg = (torch.from_numpy(blob).cuda(), torch.from_numpy(off).cuda())
+    sig = e.lm_sign(sch, sk_ntt, dmsg, device=True)
+    verdict = e.lm_verify(sch, vk_ntt, dmsg, sig, 945, 256, device=True)
+    e.synchronize()
+    assert verdict.cpu().tolist() == [1] * len(cases)
+    assert np.array_equal(sig.cpu().numpy()[0], arrays['s128_lm0_sig'])
+    # empty batches are accepted everywhere
+    assert e.lm_verify(sch, np.zeros((0, 2, D), np.uint16), [], np.zeros((0, 13, D), np.int16), 945, 256).shape == (0,)
+    assert e.lm_sign(sch, np.zeros((0, 2, 13, D), np.uint16), []).shape == (0, 13, D)
+
+
+# ------------------------------------------------------------------------------------------- BKLM
+@pytest.mark.parametrize('secpar', [128, 256])
+def test_bklm_golden(engines, golden, secpar):
+    arrays, meta = golden
+    e = engines[secpar]
+    sch = scheme(secpar)
+    m = meta['cases'][str(secpar)]
+    seeds = [c['seed'] for c in m['lm']]
+    _, sk_ntt, vk_ntt, _ = e.lm_keygen(sch, seeds)
+    for case in m['bklm']:
+        cap = case['cap']
+        pre = f's{secpar}_bk{cap}'
+        sigs = e.lm_sign(sch, sk_ntt[:cap], case['chmsgs'])
+        assert np.array_equal(sigs, arrays[pre + '_sigs'])
+        order = case['sorted_order']
+        ag = e.agg_coefs(sch, case['agmsg'], 0, cap)
+        want = arrays[pre + '_ag_coefs']
+        for i in range(cap):
+            k, s = int(ag[i, 0, 0]), int(ag[i, 0, 1])
+            dense = np.zeros(D, dtype=np.int16)
+            dense[k] = s
+            assert np.array_equal(dense, want[i])
+        # split the sorted list into two shards, as two ranks would
+        srt_sigs = np.ascontiguousarray(sigs[order])
+        cut = cap // 2
+        ag_hi = e.agg_coefs(sch, case['agmsg'], cut, cap - cut)
+        assert np.array_equal(ag_hi, ag[cut:])
+        part = e.aggregate_partial(sch, srt_sigs[:cut], np.ascontiguousarray(ag[:cut])).astype(np.int64) + \
+            e.aggregate_partial(sch, srt_sigs[cut:], ag_hi)
+        ag_sig = e.aggregate_finish(part.astype(np.int32))
+        assert np.array_equal(ag_sig, arrays[pre + '_ag_sig'])
+        srt_vk = np.ascontiguousarray(vk_ntt[:cap][order])
+        srt_ch = [case['chmsgs'][i] for i in order]
+        vp = e.aggverify_partial(sch, srt_vk[:cut], srt_ch[:cut], np.ascontiguousarray(ag[:cut])).astype(np.int64) + \
+            e.aggverify_partial(sch, srt_vk[cut:], srt_ch[cut:], ag_hi)
+        vp = vp.astype(np.int32)
+        assert e.aggverify_finish(vp, ag_sig, cap, cap, case['avf_bd'], case['avf_wt']) == case['verdict']
+        bad = ag_sig.copy()
+        bad[0, 0] += 1
+        assert e.aggverify_finish(vp, bad, cap, cap, case['avf_bd'], case['avf_wt']) == case['verdict_tampered']
+        # bound / cap failures (bklm_one_time_agg_sigs.py:103-105)
+        assert not e.aggverify_finish(vp, ag_sig, cap, cap - 1, case['avf_bd'], case['avf_wt'])
+        assert not e.aggverify_finish(vp, ag_sig, cap, cap, int(np.abs(ag_sig).max()) - 1, case['avf_wt'])
+        assert not e.aggverify_finish(vp, np.zeros_like(ag_sig), cap, cap, case['avf_bd'], case['avf_wt'])
+
+
+# ------------------------------------------------------------------------------------------- adaptor
+@pytest.mark.parametrize('secpar', [128, 256])
+def test_adaptor_golden(engines, golden, secpar):
+    arrays, meta = golden
+    e = engines[secpar]
+    sch = scheme(secpar)
+    m = meta['cases'][str(secpar)]
+    ap = m['adaptor_params']
+    cases = m['adaptor']
+    seeds = [m['lm'][c['key_index']]['seed'] for c in cases]
+    _, sk_ntt, vk_ntt, _ = e.lm_keygen(sch, seeds)
+    wit, st_ntt, st_coef = e.witgen(sch, [c['wit_seed'] for c in cases])
+    chmsgs = [c['chmsg'] for c in cases]
+    presig = e.lm_sign(sch, sk_ntt, chmsgs)
+    sig = e.vec_add(presig, wit)
+    ext = e.vec_sub(sig, presig)
+    for j in range(len(cases)):
+        pre = f's{secpar}_ad{j}'
+        assert np.array_equal(wit[j], arrays[pre + '_wit'])
+        assert np.array_equal(st_coef[j], arrays[pre + '_st'])
+        assert np.array_equal(presig[j], arrays[pre + '_presig'])
+        assert np.array_equal(sig[j], arrays[pre + '_sig'])
+        assert np.array_equal(ext[j], arrays[pre + '_ext'])
+    assert np.array_equal(e.ntt_inv(st_ntt), st_coef)
+    pv = e.lm_verify(sch, vk_ntt, chmsgs, presig, ap['pvf_bd'], ap['pvf_wt'])
+    assert pv.tolist() == [int(c['preverify']) for c in cases]
+    vv = e.lm_verify(sch, vk_ntt, chmsgs, sig, ap['vf_bd'], ap['vf_wt'], st_ntt=st_ntt)
+    assert vv.tolist() == [int(c['verify']) for c in cases]
+    wv = e.witness_verify(ext, st_ntt, ap['ext_wit_bd'], ap['ext_wit_wt'])
+    assert wv.tolist() == [int(c['witness_verify']) for c in cases]
+    pa = e.lm_verify(sch, vk_ntt, chmsgs, sig, ap['pvf_bd'], ap['pvf_wt'])
+    assert pa.tolist() == [int(c['preverify_of_adapted']) for c in cases]
+    # a wrong witness does not verify
+    assert e.witness_verify(np.ascontiguousarray(ext[::-1]), st_ntt, ap['ext_wit_bd'], ap['ext_wit_wt']).tolist() == [0, 0]
