@@ -150,6 +150,12 @@ int lcb_adaptor_witness_verify_batch(lcb_ctx* ctx, const int16_t* wit_coef, cons
 
 /* Instrumentation: kernels launched by this ctx since creation (bench.py's gpu_launches). */
 int64_t lcb_launch_count(const lcb_ctx* ctx);
+/* Optional per-kernel timing with CUDA events on the ctx stream (what bench.py's roofline reads).
+ * kernel names: sampler shake256 ntt_fwd ntt_inv poly_mul matvec sign verify vec_addsub agg_coefs
+ * agg_partial agg_finish aggv_partial aggv_finish.  lcb_profile_read synchronises the stream. */
+int lcb_profile_enable(lcb_ctx* ctx, int on);
+int lcb_profile_reset(lcb_ctx* ctx);
+int lcb_profile_read(lcb_ctx* ctx, const char* kernel, double* total_ms, int64_t* launches);
 
 #ifdef __cplusplus
 }

@@ -71,6 +71,9 @@ PROTOTYPES = {
     'lcb_vec_sub_batch': (c_int, [c_void_p, _P, _P, c_int64, _P]),
     'lcb_adaptor_witness_verify_batch': (c_int, [c_void_p, _P, _P, c_int64, c_int, c_int, _P]),
     'lcb_launch_count': (c_int64, [c_void_p]),
+    'lcb_profile_enable': (c_int, [c_void_p, c_int]),
+    'lcb_profile_reset': (c_int, [c_void_p]),
+    'lcb_profile_read': (c_int, [c_void_p, c_char_p, POINTER(ctypes.c_double), POINTER(c_int64)]),
 }
 
 _lib = None

@@ -23,6 +23,12 @@ struct lcb_ctx {
     bool has_key_ch = false;
     std::string last_error;
     int64_t launches = 0;
+    // optional per-kernel CUDA-event timing (lcb_profile_*)
+    bool profile = false;
+    struct Pending { int id; cudaEvent_t a, b; };
+    std::vector<Pending> pending;
+    double prof_ms[16] = {0};
+    int64_t prof_n[16] = {0};
 };
 
 namespace {
@@ -44,6 +50,29 @@ int fail_cuda(lcb_ctx* c, cudaError_t e, const char* what) {
         cudaError_t e_ = (call);                                 \
         if (e_ != cudaSuccess) return fail_cuda((c), e_, #call); \
     } while (0)
+
+enum KernelId { K_SAMPLER = 0, K_SHAKE, K_NTT_FWD, K_NTT_INV, K_POLY_MUL, K_MATVEC, K_SIGN, K_VERIFY, K_ADDSUB,
+                K_AGG_COEFS, K_AGG_PARTIAL, K_AGG_FINISH, K_AGGV_PARTIAL, K_AGGV_FINISH, K_COUNT };
+const char* const kKernelNames[K_COUNT] = {"sampler", "shake256", "ntt_fwd", "ntt_inv", "poly_mul", "matvec", "sign",
+                                           "verify", "vec_addsub", "agg_coefs", "agg_partial", "agg_finish",
+                                           "aggv_partial", "aggv_finish"};
+
+// Launch wrapper: counts the launch and, when profiling is on, brackets it with CUDA events on the
+// ctx stream (resolved lazily in lcb_profile_read).
+template <typename F>
+cudaError_t timed(lcb_ctx* c, int id, F&& launch) {
+    c->launches += 1;
+    if (!c->profile) return launch();
+    lcb_ctx::Pending p{id, nullptr, nullptr};
+    cudaError_t e;
+    if ((e = cudaEventCreate(&p.a)) != cudaSuccess) return e;
+    if ((e = cudaEventCreate(&p.b)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(p.a, c->stream)) != cudaSuccess) return e;
+    e = launch();
+    cudaEventRecord(p.b, c->stream);
+    c->pending.push_back(p);
+    return e;
+}
 
 uint64_t powmod(uint64_t b, uint64_t e, uint64_t q) {
     uint64_t r = 1;
@@ -190,8 +219,7 @@ int run_challenge(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* d_msg, const
     a.off = d_off;
     a.n = n;
     a.out_pairs = d_pairs;
-    CK(c, launch_sampler(a, c->stream));
-    c->launches += 1;
+    CK(c, timed(c, K_SAMPLER, [&] { return launch_sampler(a, c->stream); }));
     return LCB_OK;
 }
 
@@ -209,8 +237,7 @@ int run_agg_coefs(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* d_agmsg, int
     a.shared_len = agmsg_len;
     a.index_first = first;
     a.out_pairs = d_pairs;
-    CK(c, launch_agg_coefs(a, c->stream));
-    c->launches += 1;
+    CK(c, timed(c, K_AGG_COEFS, [&] { return launch_agg_coefs(a, c->stream); }));
     return LCB_OK;
 }
 
@@ -350,6 +377,52 @@ int lcb_ctx_root_of_unity(const lcb_ctx* c) { return c ? c->rou : LCB_ERR_INVALI
 
 int64_t lcb_launch_count(const lcb_ctx* c) { return c ? c->launches : 0; }
 
+static int profile_drain(lcb_ctx* c) {
+    if (c->pending.empty()) return LCB_OK;
+    CK(c, cudaStreamSynchronize(c->stream));
+    for (auto& p : c->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            c->prof_ms[p.id] += ms;
+            c->prof_n[p.id] += 1;
+        }
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    c->pending.clear();
+    return LCB_OK;
+}
+
+int lcb_profile_enable(lcb_ctx* c, int on) {
+    if (!c) return LCB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    int st = profile_drain(c);
+    c->profile = on != 0;
+    return st;
+}
+
+int lcb_profile_reset(lcb_ctx* c) {
+    if (!c) return LCB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    int st = profile_drain(c);
+    for (int i = 0; i < K_COUNT; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
+    return st;
+}
+
+int lcb_profile_read(lcb_ctx* c, const char* kernel, double* total_ms, int64_t* launches) {
+    if (!c || !kernel || !total_ms || !launches) return LCB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    int st = profile_drain(c);
+    if (st != LCB_OK) return st;
+    for (int i = 0; i < K_COUNT; ++i)
+        if (std::strcmp(kernel, kKernelNames[i]) == 0) {
+            *total_ms = c->prof_ms[i];
+            *launches = c->prof_n[i];
+            return LCB_OK;
+        }
+    return fail(c, LCB_ERR_INVALID, std::string("unknown kernel name ") + kernel);
+}
+
 int lcb_set_key_ch(lcb_ctx* c, const int16_t* key_ch_coef) {
     if (!c || !key_ch_coef) return LCB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
@@ -358,8 +431,7 @@ int lcb_set_key_ch(lcb_ctx* c, const int16_t* key_ch_coef) {
     CK(c, sg.in(&d_in, key_ch_coef, (size_t)c->l * D));
     uint16_t* d_ntt;
     CK(c, sg.alloc((void**)&d_ntt, (size_t)c->l * D * sizeof(uint16_t)));
-    CK(c, launch_ntt_fwd(c->ring, d_in, c->l, d_ntt, c->stream));
-    c->launches += 1;
+    CK(c, timed(c, K_NTT_FWD, [&] { return launch_ntt_fwd(c->ring, d_in, c->l, d_ntt, c->stream); }));
     // widen to uint32 on the host side of the stream (tiny: l*256 values, once per parameter set)
     std::vector<uint16_t> h16((size_t)c->l * D);
     CK(c, cudaMemcpyAsync(h16.data(), d_ntt, h16.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
@@ -386,8 +458,7 @@ int lcb_shake256_batch(lcb_ctx* c, const uint8_t* in, const int64_t* in_off, int
     CK(c, sg.in(&d_in, in, (size_t)total));
     CK(c, sg.in(&d_off, in_off, (size_t)n + 1));
     CK(c, sg.out(&d_out, out, (size_t)(n * out_len)));
-    CK(c, launch_shake256(d_in, d_off, n, d_out, out_len, c->stream));
-    c->launches += 1;
+    CK(c, timed(c, K_SHAKE, [&] { return launch_shake256(d_in, d_off, n, d_out, out_len, c->stream); }));
     CK(c, sg.finish());
     return LCB_OK;
 }
@@ -410,8 +481,7 @@ int lcb_hash2polyvec_batch(lcb_ctx* c, const char* salt, const uint8_t* msgs, co
     a.n = n;
     a.dense_stride = (int64_t)vec_len * D;
     if (a.out_dense && wt < D) CK(c, cudaMemsetAsync(a.out_dense, 0, (size_t)n * vec_len * D * sizeof(int16_t), c->stream));
-    CK(c, launch_sampler(a, c->stream));
-    c->launches += 1;
+    CK(c, timed(c, K_SAMPLER, [&] { return launch_sampler(a, c->stream); }));
     CK(c, sg.finish());
     return LCB_OK;
 }
@@ -424,8 +494,7 @@ int lcb_ntt_fwd_batch(lcb_ctx* c, const int16_t* coef, int64_t npoly, uint16_t* 
     uint16_t* d_out;
     CK(c, sg.in(&d_in, coef, (size_t)npoly * D));
     CK(c, sg.out(&d_out, ntt, (size_t)npoly * D));
-    CK(c, launch_ntt_fwd(c->ring, d_in, npoly, d_out, c->stream));
-    c->launches += 1;
+    CK(c, timed(c, K_NTT_FWD, [&] { return launch_ntt_fwd(c->ring, d_in, npoly, d_out, c->stream); }));
     CK(c, sg.finish());
     return LCB_OK;
 }
@@ -438,8 +507,7 @@ int lcb_ntt_inv_batch(lcb_ctx* c, const uint16_t* ntt, int64_t npoly, int16_t* c
     int16_t* d_out;
     CK(c, sg.in(&d_in, ntt, (size_t)npoly * D));
     CK(c, sg.out(&d_out, coef, (size_t)npoly * D));
-    CK(c, launch_ntt_inv(c->ring, d_in, npoly, d_out, c->stream));
-    c->launches += 1;
+    CK(c, timed(c, K_NTT_INV, [&] { return launch_ntt_inv(c->ring, d_in, npoly, d_out, c->stream); }));
     CK(c, sg.finish());
     return LCB_OK;
 }
@@ -453,8 +521,7 @@ int lcb_poly_mul_batch(lcb_ctx* c, const int16_t* a, const int16_t* b, int64_t n
     CK(c, sg.in(&d_a, a, (size_t)npoly * D));
     CK(c, sg.in(&d_b, b, (size_t)npoly * D));
     CK(c, sg.out(&d_out, out, (size_t)npoly * D));
-    CK(c, launch_poly_mul(c->ring, d_a, d_b, npoly, d_out, c->stream));
-    c->launches += 1;
+    CK(c, timed(c, K_POLY_MUL, [&] { return launch_poly_mul(c->ring, d_a, d_b, npoly, d_out, c->stream); }));
     CK(c, sg.finish());
     return LCB_OK;
 }
@@ -498,12 +565,13 @@ int lcb_lm_keygen_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* seeds,
         left.dense_stride = right.dense_stride = (int64_t)2 * l * D;
         left.out_dense = skc;
         right.out_dense = skc + (int64_t)l * D;
-        CK(c, launch_sampler(left, c->stream));
-        CK(c, launch_sampler(right, c->stream));
-        CK(c, launch_matvec(c->ring, skc, cnt * 2, d_sk_ntt ? d_sk_ntt + start * 2 * l * D : nullptr,
-                            d_vk_ntt ? d_vk_ntt + start * 2 * D : nullptr,
-                            d_vk_coef ? d_vk_coef + start * 2 * D : nullptr, c->stream));
-        c->launches += 3;
+        CK(c, timed(c, K_SAMPLER, [&] { return launch_sampler(left, c->stream); }));
+        CK(c, timed(c, K_SAMPLER, [&] { return launch_sampler(right, c->stream); }));
+        CK(c, timed(c, K_MATVEC, [&] {
+            return launch_matvec(c->ring, skc, cnt * 2, d_sk_ntt ? d_sk_ntt + start * 2 * l * D : nullptr,
+                                 d_vk_ntt ? d_vk_ntt + start * 2 * D : nullptr,
+                                 d_vk_coef ? d_vk_coef + start * 2 * D : nullptr, c->stream);
+        }));
     }
     CK(c, sg.finish());
     return LCB_OK;
@@ -549,8 +617,7 @@ int lcb_lm_sign_batch(lcb_ctx* c, const lcb_scheme* sch, const uint16_t* sk_ntt,
     CK(c, sg.alloc((void**)&d_pairs, (size_t)n * sch->ch_wt * 2 * sizeof(int16_t)));
     int st = run_challenge(c, sch, d_msg, d_off, n, d_pairs);
     if (st != LCB_OK) return st;
-    CK(c, launch_sign(c->ring, d_sk, d_pairs, sch->ch_wt, n, d_sig, c->stream));
-    c->launches += 1;
+    CK(c, timed(c, K_SIGN, [&] { return launch_sign(c->ring, d_sk, d_pairs, sch->ch_wt, n, d_sig, c->stream); }));
     CK(c, sg.finish());
     return LCB_OK;
 }
@@ -581,9 +648,8 @@ int lcb_lm_verify_batch(lcb_ctx* c, const lcb_scheme* sch, const uint16_t* vk_nt
     CK(c, sg.alloc((void**)&d_pairs, (size_t)n * sch->ch_wt * 2 * sizeof(int16_t)));
     int st = run_challenge(c, sch, d_msg, d_off, n, d_pairs);
     if (st != LCB_OK) return st;
-    CK(c, launch_verify(c->ring, d_sig, d_vk, d_pairs, sch->ch_wt, nullptr, d_st, n, bd > 32767 ? 32767 : bd, wt,
-                        d_verdict, c->stream));
-    c->launches += 1;
+    CK(c, timed(c, K_VERIFY, [&] { return launch_verify(c->ring, d_sig, d_vk, d_pairs, sch->ch_wt, nullptr, d_st, n, bd > 32767 ? 32767 : bd, wt,
+                        d_verdict, c->stream); }));
     CK(c, sg.finish());
     return LCB_OK;
 }
@@ -627,8 +693,7 @@ int lcb_bklm_aggregate_partial(lcb_ctx* c, const lcb_scheme* sch, const int16_t*
             if (st != LCB_OK) return st;
             d_pairs_in = d_pairs;
         }
-        CK(c, launch_agg_partial(c->ring, d_sig, d_pairs_in, count, d_partial, c->stream));
-        c->launches += 1;
+        CK(c, timed(c, K_AGG_PARTIAL, [&] { return launch_agg_partial(c->ring, d_sig, d_pairs_in, count, d_partial, c->stream); }));
     }
     CK(c, sg.finish());
     return LCB_OK;
@@ -642,8 +707,7 @@ int lcb_bklm_aggregate_finish(lcb_ctx* c, const int32_t* partial_sum, int16_t* a
     int16_t* d_out;
     CK(c, sg.in(&d_partial, partial_sum, (size_t)c->l * D));
     CK(c, sg.out(&d_out, ag_sig, (size_t)c->l * D));
-    CK(c, launch_agg_finish(c->ring, d_partial, d_out, c->stream));
-    c->launches += 1;
+    CK(c, timed(c, K_AGG_FINISH, [&] { return launch_agg_finish(c->ring, d_partial, d_out, c->stream); }));
     CK(c, sg.finish());
     return LCB_OK;
 }
@@ -682,8 +746,7 @@ int lcb_bklm_aggverify_partial(lcb_ctx* c, const lcb_scheme* sch, const uint16_t
             if (st != LCB_OK) return st;
             d_ag = d_pairs;
         }
-        CK(c, launch_aggv_partial(c->ring, d_vk, d_ch, sch->ch_wt, d_ag, count, d_partial, c->stream));
-        c->launches += 1;
+        CK(c, timed(c, K_AGGV_PARTIAL, [&] { return launch_aggv_partial(c->ring, d_vk, d_ch, sch->ch_wt, d_ag, count, d_partial, c->stream); }));
     }
     CK(c, sg.finish());
     return LCB_OK;
@@ -701,8 +764,7 @@ int lcb_bklm_aggverify_finish(lcb_ctx* c, const int32_t* partial_sum, const int1
     CK(c, sg.in(&d_partial, partial_sum, (size_t)D));
     CK(c, sg.in(&d_sig, ag_sig, (size_t)c->l * D));
     CK(c, sg.out(&d_verdict, verdict, 1));
-    CK(c, launch_aggv_finish(c->ring, d_partial, d_sig, total, ag_cap, avf_bd, avf_wt, d_verdict, c->stream));
-    c->launches += 1;
+    CK(c, timed(c, K_AGGV_FINISH, [&] { return launch_aggv_finish(c->ring, d_partial, d_sig, total, ag_cap, avf_bd, avf_wt, d_verdict, c->stream); }));
     CK(c, sg.finish());
     return LCB_OK;
 }
@@ -732,9 +794,8 @@ int lcb_adaptor_witgen_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* s
     a.n = n;
     a.out_dense = d_wit;
     a.dense_stride = (int64_t)l * D;
-    CK(c, launch_sampler(a, c->stream));
-    CK(c, launch_matvec(c->ring, d_wit, n, nullptr, d_st_ntt, d_st_coef, c->stream));
-    c->launches += 2;
+    CK(c, timed(c, K_SAMPLER, [&] { return launch_sampler(a, c->stream); }));
+    CK(c, timed(c, K_MATVEC, [&] { return launch_matvec(c->ring, d_wit, n, nullptr, d_st_ntt, d_st_coef, c->stream); }));
     CK(c, sg.finish());
     return LCB_OK;
 }
@@ -748,8 +809,7 @@ static int vec_addsub(lcb_ctx* c, const int16_t* a, const int16_t* b, int64_t np
     CK(c, sg.in(&d_a, a, (size_t)npoly * D));
     CK(c, sg.in(&d_b, b, (size_t)npoly * D));
     CK(c, sg.out(&d_out, out, (size_t)npoly * D));
-    CK(c, launch_vec_addsub(c->ring, d_a, d_b, npoly * D, sub, d_out, c->stream));
-    c->launches += 1;
+    CK(c, timed(c, K_ADDSUB, [&] { return launch_vec_addsub(c->ring, d_a, d_b, npoly * D, sub, d_out, c->stream); }));
     CK(c, sg.finish());
     return LCB_OK;
 }
@@ -775,9 +835,8 @@ int lcb_adaptor_witness_verify_batch(lcb_ctx* c, const int16_t* wit_coef, const 
     CK(c, sg.in(&d_wit, wit_coef, (size_t)n * c->l * D));
     CK(c, sg.in(&d_st, st_ntt, (size_t)n * D));
     CK(c, sg.out(&d_verdict, verdict, (size_t)n));
-    CK(c, launch_verify(c->ring, d_wit, nullptr, nullptr, 0, d_st, nullptr, n, bd > 32767 ? 32767 : bd, wt, d_verdict,
-                        c->stream));
-    c->launches += 1;
+    CK(c, timed(c, K_VERIFY, [&] { return launch_verify(c->ring, d_wit, nullptr, nullptr, 0, d_st, nullptr, n, bd > 32767 ? 32767 : bd, wt, d_verdict,
+                        c->stream); }));
     CK(c, sg.finish());
     return LCB_OK;
 }

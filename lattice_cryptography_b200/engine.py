@@ -108,6 +108,19 @@ class Engine(object):
     def launch_count(self) -> int:
         return self._lib.lcb_launch_count(self._ctx)
 
+    def profile(self, on: bool = True):
+        self._ck(self._lib.lcb_profile_enable(self._ctx, 1 if on else 0))
+
+    def profile_reset(self):
+        self._ck(self._lib.lcb_profile_reset(self._ctx))
+
+    def profile_read(self, kernel: str):
+        """-> (total milliseconds, launches) of one kernel since the last reset (CUDA events)."""
+        import ctypes
+        ms, n = ctypes.c_double(0), ctypes.c_int64(0)
+        self._ck(self._lib.lcb_profile_read(self._ctx, kernel.encode(), byref(ms), byref(n)))
+        return ms.value, n.value
+
     @staticmethod
     def _rag(items):
         if isinstance(items, tuple) and len(items) == 2:
