@@ -171,8 +171,10 @@ class Staging {
     bool host_touched_ = false;
 };
 
-// read off[n] (total blob length) whether off is host or device memory
-cudaError_t last_offset(lcb_ctx* c, const int64_t* off, int64_t n, int64_t* total) {
+// off[n] = total blob length; needed only to stage a HOST blob, so a device blob costs nothing here
+cudaError_t last_offset(lcb_ctx* c, const void* blob, const int64_t* off, int64_t n, int64_t* total) {
+    *total = 0;
+    if (blob == nullptr || on_device(blob)) return cudaSuccess;
     if (on_device(off)) {
         cudaError_t e = cudaMemcpyAsync(total, off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream);
         if (e != cudaSuccess) return e;
@@ -225,11 +227,12 @@ int run_challenge(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* d_msg, const
 
 int run_agg_coefs(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* d_agmsg, int64_t agmsg_len, int64_t first,
                   int64_t count, int16_t* d_pairs) {
-    if (sch->ag_wt != 1) return fail(c, LCB_ERR_INVALID, "only ag_wt == 1 (monomial aggregation coefficients) is supported");
+    if (sch->ag_wt != 1 || sch->ag_bd != 1)
+        return fail(c, LCB_ERR_INVALID, "only ag_wt == ag_bd == 1 (signed monomial aggregation coefficients) is supported");
     SamplerArgs a{};
     int st = fill_sampler(c, a, salt_of(sch->ag_salt).c_str(), nullptr, sch->ag_bd, sch->ag_wt, 1);
     if (st != LCB_OK) return fail(c, st, "bad aggregation parameters");
-    if (a.salt_len + 20 > SALT_BYTES) return fail(c, LCB_ERR_INVALID, "ag_salt too long");
+    if (a.salt_len + 20 > 32) return fail(c, LCB_ERR_INVALID, "ag_salt longer than 12 bytes");
     a.msgs = d_agmsg;
     a.off = nullptr;
     a.n = count;
@@ -298,6 +301,13 @@ int lcb_ctx_create(lcb_ctx** out, int device, int secpar, int q, int d, int l) {
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     c->own_stream = true;
+    {   // stream-ordered scratch: keep freed blocks in the pool instead of returning them at every sync
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
 
     // ---- tables: psi = least element of order exactly 2d (LatticeParameters.rou in lattice_algebra)
     const uint32_t uq = (uint32_t)q;
@@ -450,7 +460,7 @@ int lcb_shake256_batch(lcb_ctx* c, const uint8_t* in, const int64_t* in_off, int
     if (n == 0 || out_len == 0) return LCB_OK;
     CK(c, cudaSetDevice(c->device));
     int64_t total = 0;
-    CK(c, last_offset(c, in_off, n, &total));
+    CK(c, last_offset(c, in, in_off, n, &total));
     Staging sg(c);
     const uint8_t* d_in;
     const int64_t* d_off;
@@ -472,7 +482,7 @@ int lcb_hash2polyvec_batch(lcb_ctx* c, const char* salt, const uint8_t* msgs, co
     int st = fill_sampler(c, a, salt, nullptr, bd, wt, vec_len);
     if (st != LCB_OK) return fail(c, st, "bad sampler parameters");
     int64_t total = 0;
-    CK(c, last_offset(c, msg_off, n, &total));
+    CK(c, last_offset(c, msgs, msg_off, n, &total));
     Staging sg(c);
     CK(c, sg.in(&a.msgs, msgs, (size_t)total));
     CK(c, sg.in(&a.off, msg_off, (size_t)n + 1));
@@ -538,7 +548,7 @@ int lcb_lm_keygen_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* seeds,
     if (st == LCB_OK) st = fill_sampler(c, right, salt_of(sch->sk_salt).c_str(), "RIGHT", sch->sk_bd, sch->sk_wt, l);
     if (st != LCB_OK) return fail(c, st, "bad signing-key parameters");
     int64_t total = 0;
-    CK(c, last_offset(c, seed_off, n, &total));
+    CK(c, last_offset(c, seeds, seed_off, n, &total));
     Staging sg(c);
     const uint8_t* d_seeds;
     const int64_t* d_off;
@@ -583,7 +593,7 @@ int lcb_challenge_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* chmsg,
     if (n == 0) return LCB_OK;
     CK(c, cudaSetDevice(c->device));
     int64_t total = 0;
-    CK(c, last_offset(c, chmsg_off, n, &total));
+    CK(c, last_offset(c, chmsg, chmsg_off, n, &total));
     Staging sg(c);
     const uint8_t* d_msg;
     const int64_t* d_off;
@@ -604,7 +614,7 @@ int lcb_lm_sign_batch(lcb_ctx* c, const lcb_scheme* sch, const uint16_t* sk_ntt,
     CK(c, cudaSetDevice(c->device));
     const int l = c->l;
     int64_t total = 0;
-    CK(c, last_offset(c, chmsg_off, n, &total));
+    CK(c, last_offset(c, chmsg, chmsg_off, n, &total));
     Staging sg(c);
     const uint16_t* d_sk;
     const uint8_t* d_msg;
@@ -631,7 +641,7 @@ int lcb_lm_verify_batch(lcb_ctx* c, const lcb_scheme* sch, const uint16_t* vk_nt
     CK(c, cudaSetDevice(c->device));
     const int l = c->l;
     int64_t total = 0;
-    CK(c, last_offset(c, chmsg_off, n, &total));
+    CK(c, last_offset(c, chmsg, chmsg_off, n, &total));
     Staging sg(c);
     const uint16_t *d_vk, *d_st;
     const uint8_t* d_msg;
@@ -725,7 +735,7 @@ int lcb_bklm_aggverify_partial(lcb_ctx* c, const lcb_scheme* sch, const uint16_t
     CK(c, cudaMemsetAsync(d_partial, 0, (size_t)D * sizeof(int32_t), c->stream));
     if (count > 0) {
         int64_t total = 0;
-        CK(c, last_offset(c, chmsg_off, count, &total));
+        CK(c, last_offset(c, chmsg_sorted, chmsg_off, count, &total));
         const uint16_t* d_vk;
         const uint8_t *d_chmsg, *d_agmsg;
         const int64_t* d_off;
@@ -780,7 +790,7 @@ int lcb_adaptor_witgen_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* s
     int st = fill_sampler(c, a, salt_of(sch->wit_salt).c_str(), nullptr, sch->wit_bd, sch->wit_wt, l);
     if (st != LCB_OK) return fail(c, st, "bad witness parameters");
     int64_t total = 0;
-    CK(c, last_offset(c, seed_off, n, &total));
+    CK(c, last_offset(c, seeds, seed_off, n, &total));
     Staging sg(c);
     int16_t *d_wit, *d_st_coef;
     uint16_t* d_st_ntt;

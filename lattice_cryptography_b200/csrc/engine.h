@@ -15,7 +15,7 @@ struct SamplerArgs {
     int64_t shared_len;        // shared_msg: every instance hashes msgs[0 .. shared_len)
     int64_t index_first;       // shared_msg: decimal index appended to the salt = index_first + i
     int shared_msg;
-    uint8_t salt[SALT_BYTES];
+    alignas(8) uint8_t salt[SALT_BYTES];
     int salt_len;
     int secpar, bd, wt, vec_len;
     int idx_bits;              // LOGD + secpar

@@ -13,6 +13,7 @@
 // for the life of the kernel; accumulation of the row-vector product is 64-bit (IMAD.WIDE) with a
 // single reduction per output coefficient.  Grids are persistent: (#SM x resident blocks) blocks
 // striding over the batch.
+#include <cstdlib>
 #include "engine.h"
 
 namespace lcb {
@@ -70,18 +71,24 @@ __device__ __forceinline__ void load_pairs_a(uint32_t (&r)[EPT], const int16_t* 
     __syncwarp();
 }
 
+// key_ch rows in shared memory: the 16 slots of lane t start at word XROW*t (pitch 20, like the
+// transposition buffer) so that the 128-bit reads of a quarter-warp fall in 8 distinct bank groups.
+constexpr int AROW = LANES * XROW;   // 320 words per row
+
 __device__ __forceinline__ void copy_a_hat(uint32_t* dst, const uint32_t* __restrict__ src, int l) {
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
-    for (int i = threadIdx.x; i < l * (D / 4); i += blockDim.x) d4[i] = __ldg(s4 + i);
+    for (int i = threadIdx.x; i < l * (D / 4); i += blockDim.x) {
+        const int row = i >> 6, q4 = i & 63;            // q4: group of 4 slots within the row
+        *reinterpret_cast<uint4*>(dst + row * AROW + XROW * (q4 >> 2) + 4 * (q4 & 3)) = __ldg(s4 + i);
+    }
     __syncthreads();
 }
 
-// acc[m] += r[m] * a_hat_row[16 lane + m]
+// acc[m] += r[m] * a_hat_row[slot 16 lane + m]
 __device__ __forceinline__ void mac_row(uint64_t (&acc)[EPT], const uint32_t (&r)[EPT], const uint32_t* row, int lane) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-        uint4 v = *reinterpret_cast<const uint4*>(row + 16 * lane + 4 * g);
+        uint4 v = *reinterpret_cast<const uint4*>(row + XROW * lane + 4 * g);
         acc[4 * g] += (uint64_t)r[4 * g] * v.x;
         acc[4 * g + 1] += (uint64_t)r[4 * g + 1] * v.y;
         acc[4 * g + 2] += (uint64_t)r[4 * g + 2] * v.z;
@@ -164,7 +171,7 @@ __global__ void __launch_bounds__(RBS) k_matvec(ModQ m, StageConst sc, const Ntt
                                                 int16_t* __restrict__ y_coef) {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* a_hat = smem;
-    uint32_t* xbuf = smem + l * D;
+    uint32_t* xbuf = smem + l * AROW;
     copy_a_hat(a_hat, a_hat_g, l);
     const HalfWarp h = half_warp(xbuf);
     LaneTw tw;
@@ -185,7 +192,7 @@ __global__ void __launch_bounds__(RBS) k_matvec(ModQ m, StageConst sc, const Ntt
                 for (int k = 0; k < EPT; ++k) r[k] = barrett_full(r[k], m);
                 if (live) store_u16x16(vec_ntt + (item * l + i) * D + 16 * h.lane, r);
             }
-            mac_row(acc, r, a_hat + i * D, h.lane);
+            mac_row(acc, r, a_hat + i * AROW, h.lane);
         }
         uint32_t y[EPT];
 #pragma unroll
@@ -240,7 +247,21 @@ __global__ void __launch_bounds__(RBS) k_sign(ModQ m, StageConst sc, const NttTa
 // verdict = max|v| <= bd && max weight <= wt && key_ch * v == [vk_left * c] + rhs (+ extra)
 //   vk_ntt != null : rhs = vk_ntt[item][1], and the challenge term uses vk_ntt[item][0]
 //   vk_ntt == null : rhs = rhs_only[item]                               (witness_verify)
-__global__ void __launch_bounds__(RBS) k_verify(ModQ m, StageConst sc, const NttTables* __restrict__ tab,
+// Asynchronous global->shared staging of coefficient-form polynomials (LDGSTS, L2-only): each
+// half-warp owns two 512-byte stage buffers and keeps the next two polynomials of its work list
+// in flight while it transforms the current one, so HBM latency never reaches the scoreboard.
+constexpr int STAGE_HALF_BYTES = 2 * D * 2 + 32;   // two polynomials + 32 B so half-warps differ by 8 banks
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int MINB, bool PREFETCH>
+__global__ void __launch_bounds__(RBS, MINB) k_verify(ModQ m, StageConst sc, const NttTables* __restrict__ tab,
                                                 const uint32_t* __restrict__ a_hat_g, int l,
                                                 const int16_t* __restrict__ vec_coef,
                                                 const uint16_t* __restrict__ vk_ntt,
@@ -250,39 +271,76 @@ __global__ void __launch_bounds__(RBS) k_verify(ModQ m, StageConst sc, const Ntt
                                                 uint8_t* __restrict__ verdict) {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* a_hat = smem;
-    uint32_t* xbuf = smem + l * D;
+    uint32_t* xbuf = smem + l * AROW;
+    unsigned char* stage_base = reinterpret_cast<unsigned char*>(xbuf + (RBS / 32) * XWARP);
     copy_a_hat(a_hat, a_hat_g, l);
     const HalfWarp h = half_warp(xbuf);
+    unsigned char* stage = stage_base + h.slot * STAGE_HALF_BYTES;
     LaneTw tw;
     load_lane_tw(tw, tab->w, tab->ws, h.lane);
     const bool check_wt = wt < D;
-    for (int64_t base = (int64_t)blockIdx.x * HWB; base < n; base += (int64_t)gridDim.x * HWB) {
-        const int64_t raw = base + h.slot;
+
+    const int64_t first = (int64_t)blockIdx.x * HWB, stride = (int64_t)gridDim.x * HWB;
+    const int64_t trips = first < n ? (n - first + stride - 1) / stride : 0;   // uniform over the block
+    // work list of this half-warp: polynomial i of item(it), it = 0..trips-1; the prefetch cursor runs 2 ahead
+    int64_t pf_it = 0;
+    int pf_i = 0;
+    unsigned pf_buf = 0;
+    auto issue = [&]() {
+        if (pf_it < trips) {
+            int64_t it_item = first + pf_it * stride + h.slot;
+            it_item = it_item < n ? it_item : n - 1;
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(vec_coef + (it_item * l + pf_i) * D) + 32 * h.lane;
+            unsigned char* dst = stage + pf_buf * (D * 2) + 32 * h.lane;
+            cp_async16(dst, src);
+            cp_async16(dst + 16, src + 16);
+            if (++pf_i == l) { pf_i = 0; ++pf_it; }
+            pf_buf ^= 1u;
+        }
+        cp_async_commit();
+    };
+    issue();
+    issue();
+    unsigned cur = 0;
+    for (int64_t it = 0; it < trips; ++it) {
+        const int64_t raw = first + it * stride + h.slot;
         const bool live = raw < n;
         const int64_t item = live ? raw : n - 1;
         uint64_t acc[EPT];
 #pragma unroll
         for (int i = 0; i < EPT; ++i) acc[i] = 0;
         bool bad = false;
+        int hi = 0, lo = 0;                     // running max / min coefficient of the whole vector
         for (int i = 0; i < l; ++i) {
-            const int16_t* p = vec_coef + (item * l + i) * D;
-            uint32_t r[EPT];
-            int nz = 0;
+            cp_async_wait<1>();
+            __syncwarp();
+            const int16_t* sp = reinterpret_cast<const int16_t*>(stage + cur * (D * 2)) + h.lane;
+            int pre[EPT];
 #pragma unroll
-            for (int j = 0; j < EPT; ++j) {
-                int x = __ldg(p + h.lane + 16 * j);
-                bad |= (unsigned)(x + bd) > (unsigned)(2 * bd);
-                nz += (x != 0);
-                r[j] = (uint32_t)(x + (int)m.cq);
+            for (int j = 0; j < EPT; ++j) pre[j] = sp[16 * j];
+            __syncwarp();
+            issue();                            // refill the buffer just drained with polynomial (+2)
+            cur ^= 1u;
+            uint32_t r[EPT];
+#pragma unroll
+            for (int j = 0; j < EPT; j += 2) {
+                hi = __vimax3_s32(hi, pre[j], pre[j + 1]);
+                lo = __vimin3_s32(lo, pre[j], pre[j + 1]);
             }
             if (check_wt) {
+                int nz = 0;
+#pragma unroll
+                for (int j = 0; j < EPT; ++j) nz += (pre[j] != 0);
 #pragma unroll
                 for (int o = 8; o >= 1; o >>= 1) nz += __shfl_xor_sync(0xFFFFFFFFu, nz, o);
                 bad |= nz > wt;
             }
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) r[j] = (uint32_t)(pre[j] + (int)m.cq);
             ntt_fwd_256(r, m, sc, tw, h.xb, h.lane);
-            mac_row(acc, r, a_hat + i * D, h.lane);
+            mac_row(acc, r, a_hat + i * AROW, h.lane);
         }
+        bad |= hi > bd || lo < -bd;
         uint32_t rhs[EPT];
         if (vk_ntt) {
             uint32_t c[EPT], vl[EPT];
@@ -486,7 +544,8 @@ inline unsigned persistent_grid(int64_t items, int per_block, int num_sms, int r
     return (unsigned)(need < cap ? need : cap);
 }
 
-inline size_t ring_smem(int l) { return (size_t)l * D * 4 + (size_t)(RBS / 32) * XWARP * 4; }
+inline size_t ring_smem(int l) { return (size_t)l * AROW * 4 + (size_t)(RBS / 32) * XWARP * 4; }
+inline size_t verify_smem(int l) { return ring_smem(l) + (size_t)HWB * STAGE_HALF_BYTES; }
 
 template <typename K>
 cudaError_t allow_smem(K kernel, size_t smem) {
@@ -540,12 +599,27 @@ cudaError_t launch_verify(const RingCtx& c, const int16_t* vec_coef, const uint1
                           int ch_wt, const uint16_t* rhs_only, const uint16_t* extra_rhs, int64_t n, int bd, int wt,
                           uint8_t* verdict, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
-    size_t smem = ring_smem(c.l);
-    cudaError_t e = allow_smem(k_verify, smem);
-    if (e != cudaSuccess) return e;
-    unsigned grid = persistent_grid(n, HWB, c.num_sms, resident_blocks(k_verify, RBS, smem));
-    k_verify<<<grid, RBS, smem, st>>>(c.m, c.sc, c.tab, c.a_hat, c.l, vec_coef, vk_ntt, ch_pairs, ch_wt, rhs_only,
-                                      extra_rhs, n, bd, wt, verdict);
+    size_t smem = verify_smem(c.l);
+    // TEMPORARY tuning switch (env LCB_VERIFY_VARIANT): resident blocks per SM x prefetch
+    static int variant = -1;
+    if (variant < 0) { const char* v = getenv("LCB_VERIFY_VARIANT"); variant = v ? atoi(v) : 0; }
+#define LCB_LAUNCH_VERIFY(K)                                                                                     \
+    do {                                                                                                         \
+        cudaError_t e = allow_smem(K, smem);                                                                     \
+        if (e != cudaSuccess) return e;                                                                          \
+        unsigned grid = persistent_grid(n, HWB, c.num_sms, resident_blocks(K, RBS, smem));                       \
+        K<<<grid, RBS, smem, st>>>(c.m, c.sc, c.tab, c.a_hat, c.l, vec_coef, vk_ntt, ch_pairs, ch_wt, rhs_only,  \
+                                   extra_rhs, n, bd, wt, verdict);                                               \
+    } while (0)
+    switch (variant) {
+        case 1: LCB_LAUNCH_VERIFY((k_verify<5, true>)); break;
+        case 2: LCB_LAUNCH_VERIFY((k_verify<6, true>)); break;
+        case 3: LCB_LAUNCH_VERIFY((k_verify<4, false>)); break;
+        case 4: LCB_LAUNCH_VERIFY((k_verify<5, false>)); break;
+        case 5: LCB_LAUNCH_VERIFY((k_verify<6, false>)); break;
+        default: LCB_LAUNCH_VERIFY((k_verify<4, true>)); break;
+    }
+#undef LCB_LAUNCH_VERIFY
     return cudaGetLastError();
 }
 

@@ -307,6 +307,22 @@ def test_bklm_golden(engines, golden, secpar):
         assert not e.aggverify_finish(vp, np.zeros_like(ag_sig), cap, cap, case['avf_bd'], case['avf_wt'])
 
 
+@pytest.mark.parametrize('n,first,msg_len', [(1, 0, 0), (130, 0, 5), (257, 95, 1000), (1500, 9990, 33000), (64, 99999990, 271)])
+def test_agg_coefs_vs_hashlib(engines, n, first, msg_len):
+    """make_agg_coefs (bklm_one_time_agg_sigs.py:78-81) for many indices over one shared message:
+    ag_i = +-X^k with k = first digest byte, sign = next bit of SHAKE256('AG_SALT' + str(i) + msg).
+    Covers every salt-length class (1..8 digits), unaligned messages and sharded index ranges."""
+    e = engines[128]
+    sch = scheme(128)
+    rng = np.random.default_rng(n + msg_len)
+    msg = bytes(rng.integers(32, 127, msg_len, dtype=np.uint8))
+    blob = np.frombuffer(b'xyz' + msg, dtype=np.uint8)[3:]          # deliberately misaligned host view
+    got = e.agg_coefs(sch, np.ascontiguousarray(blob) if msg_len == 0 else blob, first, n)
+    for i in range(n):
+        dg = hashlib.shake_256(b'AG_SALT' + str(first + i).encode() + msg).digest(2)
+        assert (int(got[i, 0, 0]), int(got[i, 0, 1])) == (dg[0], 1 if dg[1] & 0x80 else -1), (i, first + i)
+
+
 # ------------------------------------------------------------------------------------------- adaptor
 @pytest.mark.parametrize('secpar', [128, 256])
 def test_adaptor_golden(engines, golden, secpar):
