@@ -1,0 +1,135 @@
+"""Boneh-Kim style aggregation of LM one-time signatures: the reference's entry points
+(lattice_cryptography/bklm_one_time_agg_sigs.py:27-116) on the CUDA engine, plus sharded variants.
+
+Drop-in: make_setup_parameters, prepare_make_agg_coefs, prepare_hash2polyinput, make_agg_coefs,
+         prepare_aggregate, aggregate, aggregate_verify
+Sharded: aggregate_shard / aggregate_finish, aggregate_verify_shard / aggregate_verify_finish -
+         each rank (GPU) handles a contiguous range of the SORTED list and the int32 partial sums
+         are added across ranks (one NCCL reduce; see lattice_cryptography_b200.distributed).
+
+Sorting by str(otvk) and building the hash-input strings stay on the host: they depend on CPython
+object identity.  The shipped parameters have ag_wt = ag_bd = 1, i.e. every
+aggregation coefficient is a signed monomial; that is the only case the engine supports.
+"""
+from typing import Dict, List, Tuple
+
+import numpy as np
+
+from .lattice_algebra import Polynomial, PolynomialVector, is_bitstring
+from .lm_one_time_sigs import (BDs, Message, PublicParameters, SALTs, SecurityParameter, Signature, WTs, _ctx,
+                               challenge_messages, make_setup_parameters as setup_pars, make_signature_challenge)
+from .one_time_keys import ALLOWABLE_SECPARS, OneTimeVerificationKey, bits_to_decode, bits_to_indices
+
+AggCoef = Polynomial
+
+for _s in ALLOWABLE_SECPARS:
+    BDs[_s]['ag_bd'] = 1
+    WTs[_s]['ag_wt'] = 1
+    SALTs[_s]['ag_salt'] = 'AG_SALT'
+CAPs: Dict[int, int] = {i: 2 for i in ALLOWABLE_SECPARS}
+
+
+def make_setup_parameters(secpar: SecurityParameter) -> PublicParameters:
+    pp = setup_pars(secpar=secpar)
+    lp = pp['scheme_parameters'].lp
+    pp['ag_cap'], pp['ag_salt'] = CAPs[secpar], SALTs[secpar]['ag_salt']
+    pp['ag_bd'], pp['ag_wt'] = BDs[secpar]['ag_bd'], WTs[secpar]['ag_wt']
+    pp['avf_wt'] = max(1, min(lp.degree, pp['ag_cap'] * pp['ag_wt'] * pp['vf_wt']))
+    pp['avf_bd'] = max(1, min(lp.modulus // 2, pp['ag_cap'] * min(pp['ag_wt'], pp['vf_wt']) * pp['ag_bd'] * pp['vf_bd']))
+    return pp
+
+
+def set_aggregation_capacity(pp: PublicParameters, ag_cap: int) -> PublicParameters:
+    """Raise/lower pp['ag_cap'] and recompute avf_bd / avf_wt by the reference's formulas
+    (bklm_one_time_agg_sigs.py:36-43).  Not a reference function: the reference hard-codes cap = 2."""
+    lp = pp['scheme_parameters'].lp
+    pp['ag_cap'] = ag_cap
+    pp['avf_wt'] = max(1, min(lp.degree, ag_cap * pp['ag_wt'] * pp['vf_wt']))
+    pp['avf_bd'] = max(1, min(lp.modulus // 2, ag_cap * min(pp['ag_wt'], pp['vf_wt']) * pp['ag_bd'] * pp['vf_bd']))
+    return pp
+
+
+# ------------------------------------------------------------------------------- host-side preparation
+def prepare_make_agg_coefs(otvks: List[OneTimeVerificationKey], msgs: List[Message]) -> Tuple[
+        List[OneTimeVerificationKey], List[Message]]:
+    if len(otvks) != len(msgs):
+        raise ValueError("Cannot prepare_make_agg_coefs without two input vectors of equal length.")
+    elif not all(is_bitstring(msg) for msg in msgs):
+        raise ValueError("Input messages must be bitstrings.")
+    order = sorted(range(len(otvks)), key=lambda i: str(otvks[i]))      # stable, like sorted() on the zip
+    return [otvks[i] for i in order], [msgs[i] for i in order]
+
+
+def prepare_hash2polyinput(pp: PublicParameters, otvks: List[OneTimeVerificationKey], msgs: List[Message]) -> dict:
+    srt_keys, srt_msgs = prepare_make_agg_coefs(otvks=otvks, msgs=msgs)
+    sp = pp['scheme_parameters']
+    return {'secpar': sp.secpar, 'lp': sp.lp, 'distribution': sp.distribution,
+            'dist_pars': {'bd': pp['ag_bd'], 'wt': pp['ag_wt']}, 'num_coefs': pp['ag_wt'],
+            'bti': bits_to_indices(secpar=sp.secpar, degree=sp.lp.degree, wt=pp['ag_wt']),
+            'btd': bits_to_decode(secpar=sp.secpar, bd=pp['ag_bd']),
+            'msg': str(list(zip(srt_keys, srt_msgs))), 'const_time_flag': False}
+
+
+def _monomials(lp, pairs: np.ndarray) -> List[AggCoef]:
+    return [Polynomial(lp, {int(k): int(s)}, const_time_flag=False) for k, s in pairs[:, 0, :]]
+
+
+def make_agg_coefs(pp: PublicParameters, otvks: List[OneTimeVerificationKey], msgs: List[Message]) -> List[AggCoef]:
+    h2p = prepare_hash2polyinput(pp=pp, otvks=otvks, msgs=msgs)
+    eng, sch = _ctx(pp)
+    return _monomials(h2p['lp'], eng.agg_coefs(sch, h2p['msg'], 0, len(otvks)))
+
+
+def prepare_aggregate(otvks: List[OneTimeVerificationKey], msgs: List[Message], sigs: List[Signature]) -> Tuple[
+        List[OneTimeVerificationKey], List[Message], List[Signature]]:
+    order = sorted(range(len(otvks)), key=lambda i: str(otvks[i]))
+    return [otvks[i] for i in order], [msgs[i] for i in order], [sigs[i] for i in order]
+
+
+# ------------------------------------------------------------------------------- sharded engine API
+def aggregate_shard(pp: PublicParameters, sig_sorted, agmsg, first: int, device: bool = False):
+    """int32[l,d] partial sum over the shard of the SORTED signature list that starts at global
+    position `first` (sig_sorted int16[count,l,d]); aggregation coefficients are derived here."""
+    eng, sch = _ctx(pp)
+    count = int(sig_sorted.shape[0])
+    ag = eng.agg_coefs(sch, agmsg, first, count, device=device)
+    return eng.aggregate_partial(sch, sig_sorted, ag, device=device)
+
+
+def aggregate_finish(pp: PublicParameters, partial_sum, device: bool = False):
+    eng, _ = _ctx(pp)
+    return eng.aggregate_finish(partial_sum, device=device)
+
+
+def aggregate_verify_shard(pp: PublicParameters, vk_ntt_sorted, chmsgs_sorted, agmsg, first: int, device: bool = False):
+    """int32[d] partial sum (NTT form) of (vk_left*c + vk_right) * ag over one shard of the sorted list."""
+    eng, sch = _ctx(pp)
+    count = int(vk_ntt_sorted.shape[0])
+    ag = eng.agg_coefs(sch, agmsg, first, count, device=device)
+    return eng.aggverify_partial(sch, vk_ntt_sorted, chmsgs_sorted, ag, device=device)
+
+
+def aggregate_verify_finish(pp: PublicParameters, partial_sum, ag_sig, total: int) -> bool:
+    eng, _ = _ctx(pp)
+    return eng.aggverify_finish(partial_sum, ag_sig, total, pp['ag_cap'], pp['avf_bd'], pp['avf_wt'])
+
+
+# ------------------------------------------------------------------------------- drop-in API
+def aggregate(pp: PublicParameters, otvks: List[OneTimeVerificationKey], msgs: List[Message],
+              sigs: List[Signature]) -> Signature:
+    srt_keys, srt_msgs, srt_sigs = prepare_aggregate(otvks=otvks, msgs=msgs, sigs=sigs)
+    agmsg = prepare_hash2polyinput(pp=pp, otvks=otvks, msgs=msgs)['msg']
+    sig_sorted = np.ascontiguousarray(np.stack([s.coef for s in srt_sigs]))
+    partial = aggregate_shard(pp, sig_sorted, agmsg, 0)
+    return PolynomialVector(pp['scheme_parameters'].lp, const_time_flag=False, _coef=aggregate_finish(pp, partial))
+
+
+def aggregate_verify(pp: PublicParameters, otvks: List[OneTimeVerificationKey], msgs: List[Message],
+                     ag_sig: Signature) -> bool:
+    if len(otvks) < 1 or len(otvks) > pp['ag_cap'] or len(otvks) != len(msgs):
+        return False
+    srt_keys, srt_msgs = prepare_make_agg_coefs(otvks=otvks, msgs=msgs)
+    agmsg = str(list(zip(srt_keys, srt_msgs)))
+    vk_sorted = np.ascontiguousarray(np.stack([np.stack([k[0].ntt, k[1].ntt]) for k in srt_keys]))
+    partial = aggregate_verify_shard(pp, vk_sorted, challenge_messages(srt_keys, srt_msgs), agmsg, 0)
+    return aggregate_verify_finish(pp, partial, np.ascontiguousarray(ag_sig.coef), len(otvks))

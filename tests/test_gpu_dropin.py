@@ -1,0 +1,175 @@
+"""GPU tests of the drop-in Python layer: the reference's own integration tests and the algebraic
+identities its unit tests assert, run against lattice_cryptography_b200's modules.
+  * tests/test_bklm_one_time_agg_sigs.py:406-415 (test_all), tests/test_adaptor_sigs.py:196-217
+    (test_general), benchmarks/demo_signing.py
+  * tests/test_lm_one_time_sigs.py:164-176,284-292 identities; no-forgery checks the reference lacks.
+Objects and verdicts are also compared with the CPU oracle on the same key_ch / seeds / hash inputs."""
+from secrets import randbits
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('secpar', [128, 256])
+def test_lm_dropin_identities(secpar):
+    from lattice_cryptography_b200 import lm_one_time_sigs as lm
+    from lattice_cryptography_b200.one_time_keys import SecretSeed
+    pp = lm.make_setup_parameters(secpar)
+    sp = pp['scheme_parameters']
+    assert pp['vf_bd'] == {128: 945, 256: 3315}[secpar] and pp['vf_wt'] == 256
+    seeds = [SecretSeed(secpar=secpar, lp=sp.lp, seed=bin(j)[2:].zfill(secpar)) for j in (0, 1, 12345)]
+    keys = lm.keygen(pp=pp, num_keys_to_gen=3, seeds=seeds, multiprocessing=True)
+    assert [k[0] for k in keys] == seeds
+    for seed, sk, vk in keys:
+        assert sk.left_key.const_time_flag and sk.right_key.const_time_flag
+        assert not vk.left_key.const_time_flag and not vk.right_key.const_time_flag
+        assert sp.key_ch * sk[0] == vk[0] == vk.left_key
+        assert sp.key_ch * sk[1] == vk[1] == vk.right_key
+        for entry in sk[0].get_coef_rep() + sk[1].get_coef_rep():
+            assert 1 <= entry[1] <= pp['sk_bd'] and 1 <= entry[2] <= pp['sk_wt']
+        msg = 'QRL is awesome!'
+        c = lm.make_signature_challenge(pp=pp, otvk=vk, msg=msg)
+        coefs, norm, weight = c.get_coef_rep()
+        assert norm == 1 and weight == pp['ch_wt'] and set(coefs.values()) <= {-1, 1}
+        sig = lm.sign(pp=pp, otk=(seed, sk, vk), msg=msg)
+        assert sig == sk[0] ** c + sk[1]
+        assert sp.key_ch * sig == vk[0] * c + vk[1]
+        cnw = sig.get_coef_rep()
+        assert 1 <= max(i[1] for i in cnw) <= pp['vf_bd'] and 1 <= max(i[2] for i in cnw) <= pp['vf_wt']
+        assert lm.verify(pp=pp, otvk=vk, msg=msg, sig=sig) is True
+        assert lm.verify(pp=pp, otvk=vk, msg=msg + ' ', sig=sig) is False
+        assert lm.verify(pp=pp, otvk=keys[0][2] if vk is not keys[0][2] else keys[1][2], msg=msg, sig=sig) is False
+    # unseeded path, single key and the error contract of keygen_core (lm_one_time_sigs.py:128-131)
+    one = lm.keygen(pp=pp, num_keys_to_gen=1)[0]
+    assert len(one[0].seed) == secpar and lm.verify(pp, one[2], '0101', lm.sign(pp, one, '0101'))
+    with pytest.raises(ValueError, match='natural number'):
+        lm.keygen_core(pp=pp, num_keys_to_gen=0)
+    with pytest.raises(ValueError, match='seed for each key'):
+        lm.keygen_core(pp=pp, num_keys_to_gen=2, seeds=seeds)
+
+
+def test_lm_dropin_matches_oracle():
+    """Same key_ch, seed and full hash input -> same keys, challenge and signature as the CPU oracle."""
+    import schemes
+    from lattice_cryptography_b200 import lm_one_time_sigs as lm
+    from lattice_cryptography_b200.lattice_algebra import PolynomialVector
+    from lattice_cryptography_b200.one_time_keys import SchemeParameters, SecretSeed
+    secpar = 128
+    okc = schemes.key_ch_from_seed(secpar, 'drop-in parity key_ch')
+    opp = schemes.make_lm_parameters(secpar, okc)
+    pp = lm.make_setup_parameters(secpar)
+    lp = pp['scheme_parameters'].lp
+    pp['scheme_parameters'] = SchemeParameters(secpar=secpar, lp=lp, distribution=lm.DISTRIBUTION, key_ch=PolynomialVector(
+        lp, _coef=np.array(schemes.dense_of_vec(okc), dtype=np.int16)))
+    seed = bin(987654321)[2:].zfill(secpar)
+    key = lm.keygen(pp, 1, [SecretSeed(seed=seed, secpar=secpar, lp=lp)])[0]
+    skl, skr, vkl, vkr = schemes.lm_keygen_one(opp, seed)
+    assert key[1][0].coef.tolist() == schemes.dense_of_vec(skl) and key[1][1].coef.tolist() == schemes.dense_of_vec(skr)
+    assert key[2][0].coef.tolist() == schemes.dense_of_poly(vkl) and key[2][1].coef.tolist() == schemes.dense_of_poly(vkr)
+    msg = 'Blessed are the cheesemakers.'
+    chmsg = str(key[2]) + ', ' + msg
+    sig = lm.sign(pp, key, msg)
+    assert sig.coef.tolist() == schemes.dense_of_vec(schemes.lm_sign(opp, skl, skr, chmsg))
+    assert lm.make_signature_challenge(pp, key[2], msg).coef.tolist() == schemes.dense_of_poly(schemes.challenge(opp, chmsg))
+
+
+@pytest.mark.parametrize('secpar', [128, 256])
+def test_bklm_all(secpar):
+    from lattice_cryptography_b200 import bklm_one_time_agg_sigs as bk
+    from lattice_cryptography_b200.lm_one_time_sigs import keygen, sign, verify
+    pp = bk.make_setup_parameters(secpar)
+    assert pp['ag_cap'] == 2 and pp['avf_bd'] == {128: 1890, 256: 6630}[secpar] and pp['avf_wt'] == 256
+    for _ in range(4):
+        keys = keygen(pp=pp, num_keys_to_gen=pp['ag_cap'])
+        msgs = [bin(randbits(32))[2:].zfill(32) for _ in keys]
+        sigs = [sign(pp=pp, otk=k, msg=m) for k, m in zip(keys, msgs)]
+        assert all(verify(pp=pp, otvk=k[2], msg=m, sig=s) for k, m, s in zip(keys, msgs, sigs))
+        vks = [k[2] for k in keys]
+        ag_sig = bk.aggregate(pp=pp, otvks=vks, msgs=msgs, sigs=sigs)
+        # the engine's aggregate equals the object-level formula of the reference (bklm_one_time_agg_sigs.py:92-96)
+        srt_keys, srt_msgs, srt_sigs = bk.prepare_aggregate(otvks=vks, msgs=msgs, sigs=sigs)
+        coefs = bk.make_agg_coefs(pp=pp, otvks=vks, msgs=msgs)
+        assert all(c.get_coef_rep()[1:] == (1, 1) for c in coefs)
+        assert ag_sig == sum([s ** c for s, c in zip(srt_sigs, coefs)])
+        assert bk.aggregate_verify(pp=pp, otvks=vks, msgs=msgs, ag_sig=ag_sig)
+        assert bk.aggregate_verify(pp=pp, otvks=vks[::-1], msgs=msgs[::-1], ag_sig=ag_sig)      # order-independent
+        assert not bk.aggregate_verify(pp=pp, otvks=vks, msgs=msgs[::-1], ag_sig=ag_sig)
+        assert not bk.aggregate_verify(pp=pp, otvks=vks[:1], msgs=msgs, ag_sig=ag_sig)          # length mismatch
+        assert not bk.aggregate_verify(pp=pp, otvks=vks + vks[:1], msgs=msgs + msgs[:1], ag_sig=ag_sig)   # over cap
+    with pytest.raises(ValueError, match='bitstrings'):
+        bk.prepare_make_agg_coefs(vks, ['01', 'xy'])
+    with pytest.raises(ValueError, match='equal length'):
+        bk.prepare_make_agg_coefs(vks, ['01'])
+
+
+def test_bklm_larger_aggregate_sharded():
+    """ag_cap raised to 24 and the sorted list split into 3 shards, as 3 ranks would."""
+    from lattice_cryptography_b200 import bklm_one_time_agg_sigs as bk
+    from lattice_cryptography_b200.lm_one_time_sigs import challenge_messages, keygen, sign
+    pp = bk.set_aggregation_capacity(bk.make_setup_parameters(128), 24)
+    assert pp['avf_bd'] == 5888 and pp['avf_wt'] == 256
+    keys = keygen(pp=pp, num_keys_to_gen=24)
+    msgs = [bin(randbits(32))[2:].zfill(32) for _ in keys]
+    sigs = [sign(pp=pp, otk=k, msg=m) for k, m in zip(keys, msgs)]
+    vks = [k[2] for k in keys]
+    whole = bk.aggregate(pp=pp, otvks=vks, msgs=msgs, sigs=sigs)
+    srt_keys, srt_msgs, srt_sigs = bk.prepare_aggregate(vks, msgs, sigs)
+    agmsg = str(list(zip(srt_keys, srt_msgs)))
+    sig_arr = np.stack([s.coef for s in srt_sigs])
+    vk_arr = np.stack([np.stack([k[0].ntt, k[1].ntt]) for k in srt_keys])
+    chm = challenge_messages(srt_keys, srt_msgs)
+    part = np.zeros((13, 256), dtype=np.int64)
+    vpart = np.zeros(256, dtype=np.int64)
+    for a, b in ((0, 7), (7, 16), (16, 24)):
+        part += bk.aggregate_shard(pp, np.ascontiguousarray(sig_arr[a:b]), agmsg, a)
+        vpart += bk.aggregate_verify_shard(pp, np.ascontiguousarray(vk_arr[a:b]), chm[a:b], agmsg, a)
+    ag = bk.aggregate_finish(pp, part.astype(np.int32))
+    assert np.array_equal(ag, whole.coef)
+    assert bk.aggregate_verify_finish(pp, vpart.astype(np.int32), ag, 24)
+    assert bk.aggregate_verify(pp=pp, otvks=vks, msgs=msgs, ag_sig=whole)
+
+
+def test_adaptor_general():
+    from lattice_cryptography_b200 import adaptor_sigs as ad
+    for secpar in (128, 256):
+        pp = ad.make_setup_parameters(secpar=secpar)
+        assert (pp['pvf_bd'], pp['vf_bd'], pp['ext_wit_bd']) == {128: (945, 946, 1891), 256: (3315, 3316, 6631)}[secpar]
+        key = ad.keygen(pp=pp, num_keys_to_gen=1)[0]
+        otvk = key[2]
+        seed, wit, st = ad.witgen(pp=pp, num_wits_to_gen=1)[0]
+        assert pp['scheme_parameters'].key_ch * wit.key == st.key
+        message = 'Blessed are the cheesemakers.'
+        presig = ad.presign(pp=pp, otk=key, msg=message, st=st)
+        assert ad.preverify(pp=pp, otvk=otvk, msg=message, st=st, presig=presig)
+        sig = ad.adapt(presig=presig, wit=wit)
+        assert ad.verify(pp=pp, otvk=otvk, msg=message, st=st, sig=sig)
+        assert not ad.verify(pp=pp, otvk=otvk, msg=message, st=st, sig=presig)        # un-adapted
+        ext = ad.extract(pp=pp, sig=sig, presig=presig)
+        assert ext.key == wit.key
+        assert ad.witness_verify(pp=pp, wit=ext, st=st)
+        signed = ad.sign(pp=pp, otk=key, msg=message, wit_st_pair=(seed, wit, st))
+        assert signed == sig and ad.verify(pp=pp, otvk=otvk, msg=message, st=st, sig=signed)
+        other = ad.witgen(pp=pp, num_wits_to_gen=1)[0]
+        assert not ad.witness_verify(pp=pp, wit=other[1], st=st)
+        with pytest.raises(ValueError, match='witnesses'):
+            ad.witgen(pp=pp, num_wits_to_gen=0)
+
+
+def test_container_validation_messages():
+    """Error strings of the key containers (one_time_keys.py:26-38 etc.) - host logic, but the module
+    imports the engine, so it lives with the GPU tests."""
+    from lattice_cryptography_b200 import one_time_keys as otk
+    from lattice_cryptography_b200.lm_one_time_sigs import LPs
+    lp = LPs[128]
+    with pytest.raises(ValueError, match=r'must be an integer in \[128, 256\] but had 127'):
+        otk.SecretSeed(seed='0' * 128, secpar=127, lp=lp)
+    with pytest.raises(ValueError, match='Input must be a binary string'):
+        otk.SecretSeed(seed='012', secpar=128, lp=lp)
+    with pytest.raises(ValueError, match='enough bits'):
+        otk.SecretSeed(seed='01', secpar=128, lp=lp)
+    assert otk.SecretSeed(seed='0' * 128, secpar=128, lp=lp) == otk.SecretSeed(seed='0' * 128, secpar=128, lp=lp)
+    assert otk.bits_to_indices(128, 256, 20) == 2592 and otk.bits_to_decode(128, 1) == 129
+    with pytest.raises(ValueError, match='non-positive'):
+        otk.bits_per_coefficient(128, 0)
