@@ -357,3 +357,48 @@ def test_adaptor_golden(engines, golden, secpar):
     assert pa.tolist() == [int(c['preverify_of_adapted']) for c in cases]
     # a wrong witness does not verify
     assert e.witness_verify(np.ascontiguousarray(ext[::-1]), st_ntt, ap['ext_wit_bd'], ap['ext_wit_wt']).tolist() == [0, 0]
+
+
+# ------------------------------------------------------------------------------------------- big batches vs the C oracle
+@pytest.mark.parametrize('secpar,n', [(128, 2048), (256, 600)])
+def test_lm_big_batch_vs_c_oracle(engines, golden, secpar, n):
+    """Every verdict of a few thousand triples (a third tampered in assorted ways, ragged messages)
+    and every key / signature coefficient of a subsample against oracle/lcb_oracle.c, whose products
+    are schoolbook convolutions and whose decoder walks the digest bit by bit."""
+    import c_oracle
+    arrays, meta = golden
+    e = engines[secpar]
+    sch = scheme(secpar)
+    s = SHIPPED[secpar]
+    m = meta['cases'][str(secpar)]
+    p = c_oracle.params(secpar, s['q'], s['l'], s['sk_bd'], s['ch_wt'])
+    key_ch = np.ascontiguousarray(arrays[f's{secpar}_key_ch'])
+    rng = np.random.default_rng(99 + secpar)
+    seeds = [''.join(rng.choice(['0', '1'], secpar + int(rng.integers(0, 9)))) for _ in range(n)]
+    chmsgs = [bytes(rng.integers(1, 256, int(rng.integers(0, 400)), dtype=np.uint8)) for _ in range(n)]
+    sk_coef, sk_ntt, vk_ntt, vk_coef = e.lm_keygen(sch, seeds)
+    sig = e.lm_sign(sch, sk_ntt, chmsgs)
+    bad = sig.copy()
+    msgs2 = list(chmsgs)
+    for i in range(n):
+        kind = int(rng.integers(0, 9))
+        a, b = int(rng.integers(0, s['l'])), int(rng.integers(0, 256))
+        if kind == 0:
+            bad[i, a, b] += int(rng.choice([-1, 1]))
+        elif kind == 1:
+            bad[i, a, b] = int(rng.choice([-1, 1])) * (m['vf_bd'] + int(rng.integers(0, 3)))   # at / over the bound
+        elif kind == 2:
+            msgs2[i] = chmsgs[i] + b'\x01'
+        elif kind == 3:
+            bad[i] = sig[(i + 1) % n]
+    from lattice_cryptography_b200 import ragged
+    blob, off = ragged(msgs2)
+    got = e.lm_verify(sch, vk_ntt, (blob, off), bad, m['vf_bd'], m['vf_wt'])
+    want = c_oracle.lm_verify_batch(p, key_ch, vk_coef, blob, off, bad, m['vf_bd'], m['vf_wt'])
+    assert np.array_equal(got, want)
+    assert 0.5 < want.mean() < 0.8          # both verdicts are well represented
+    for i in range(0, n, max(1, n // 24)):
+        skl, skr, vkl, vkr = c_oracle.lm_keygen(p, key_ch, seeds[i].encode())
+        assert np.array_equal(skl, sk_coef[i, 0]) and np.array_equal(skr, sk_coef[i, 1])
+        assert np.array_equal(vkl, vk_coef[i, 0]) and np.array_equal(vkr, vk_coef[i, 1])
+        assert np.array_equal(c_oracle.lm_sign(p, skl, skr, chmsgs[i]), sig[i])
