@@ -12,9 +12,7 @@ every rank verifies its own 2^20 triples (independent units, no data-path collec
 import argparse
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -39,6 +37,8 @@ def parse():
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--cpu-per-core', type=int, default=16, help='CPU baseline: verifies per host core')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the keygen+sign / BKLM / adaptor measurements')
+    ap.add_argument('--bklm-log2n', type=int, default=16, help='log2 of signatures per aggregate (whole job)')
     return ap.parse_args()
 
 
@@ -66,7 +66,7 @@ def reference_arm(a):
     vals, t0 = [], time.perf_counter()
     leg = None
     for step in range(a.warmup + a.steps):
-        leg = cpu_leg(a.secpar, max(1, a.cpu_per_core // 4))
+        leg = cpu_leg(a.secpar, max(1, a.cpu_per_core // 2))
         if step >= a.warmup:
             vals.append(leg['value'])
     v = sum(vals) / len(vals)
@@ -83,43 +83,55 @@ def reference_arm(a):
 
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler(object):
-    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
-        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    """SM clock / power / throttle reasons sampled every 5 ms by NVML in a thread DURING the timed region."""
+    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
 
     def __init__(self, device):
-        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        import threading
+        self.rows, self.stop_flag, self.h = [], False, None
         try:
-            self.p = subprocess.Popen(['nvidia-smi', f'--id={device}', f'--query-gpu={self.Q}',
-                                       '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.f,
-                                      stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            return
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0, reasons))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def stop(self):
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
-        if self.p is None:
+        if self.h is None:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        rows = [r.split(',') for r in self.f.read().strip().splitlines() if r.count(',') >= 6]
-        self.f.close()
-        os.unlink(self.f.name)
-        if not rows:
+        self.stop_flag = True
+        self.t.join(timeout=2)
+        if not self.rows:
             return out
-        sm = sorted(float(r[0]) for r in rows)
-        # under load = the upper half of the samples (the sampler also sees idle edges)
-        load = sm[len(sm) // 2:]
-        out['sm_mhz'] = load[len(load) // 2]
-        out['sm_max_mhz'] = float(rows[0][1])
-        out['power_w_max'] = max(float(r[2]) for r in rows)
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        out['reasons'] = [n for i, n in enumerate(names) if any(r[3 + i].strip() == 'Active' for r in rows)]
-        out['samples'] = len(rows)
+        sm = sorted(r[0] for r in self.rows)
+        out['sm_mhz'] = float(sm[len(sm) // 2])
+        out['sm_min_mhz'] = float(sm[0])
+        out['sm_max_mhz'] = float(self.max_sm)
+        out['power_w_max'] = max(r[1] for r in self.rows)
+        seen = 0
+        for r in self.rows:
+            seen |= r[2]
+        out['reasons'] = [name for bit, name in self.REASONS.items() if seen & bit]
+        out['samples'] = len(self.rows)
         return out
 
 
@@ -139,6 +151,147 @@ def build_inputs(a, rank, torch, np):
     seed_off = np.arange(n + 1, dtype=np.int64) * a.secpar
     ch_off = np.arange(n + 1, dtype=np.int64) * ch.shape[1]
     return seeds.reshape(-1), seed_off, ch, ch_off
+
+
+
+# ---------------------------------------------------------------------------------------------------
+# Secondary measurements (BASELINE.json configs[2..4] at sizes that keep the default run short).  Timed
+# with CUDA events on the engine's stream, max over ranks; none of them is the headline metric.
+def _timed(torch, dist, world, dev, fn, reps=3):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def _engine(secpar, local, np):
+    from lattice_cryptography_b200 import Engine, make_scheme
+    p = SHIPPED[secpar]
+    eng = Engine(secpar, p['q'], D, p['l'], device=local)
+    eng.use_torch_stream()
+    key_ch, _ = eng.hash2polyvec('KEY_CH_SEED', [KEY_CH_SEED], p['q'] // 2, D, p['l'])
+    eng.set_key_ch(np.ascontiguousarray(key_ch[0]))
+    sch = make_scheme(sk_bd=p['sk_bd'], sk_wt=256, ch_bd=1, ch_wt=p['ch_wt'], wit_bd=1, wit_wt=20)
+    return eng, sch, p
+
+
+def secondary_keygen_sign(a, rank, local, world, torch, np, dist):
+    """configs[2]: keygen + sign from synthetic seeds at secpar 256 (2^16 seeds per GPU here)."""
+    class A: secpar, log2n = 256, 16
+    eng, sch, p = _engine(256, local, np)
+    dev = f'cuda:{local}'
+    n = 1 << A.log2n
+    seeds, seed_off, ch, ch_off = build_inputs(A, rank, torch, np)
+    d_seeds = (torch.from_numpy(seeds).to(dev), torch.from_numpy(seed_off).to(dev))
+    d_ch = (torch.from_numpy(ch).to(dev).view(-1), torch.from_numpy(ch_off).to(dev))
+    out = {}
+
+    def run():
+        _, sk_ntt, vk_ntt, _ = eng.lm_keygen(sch, d_seeds, want_sk_coef=False, want_vk_coef=False, device=True)
+        out['sig'] = eng.lm_sign(sch, sk_ntt, d_ch, device=True)
+        out['vk'] = vk_ntt
+    ms = _timed(torch, dist, world, dev, run, reps=2)
+    ok = bool(eng.lm_verify(sch, out['vk'], d_ch, out['sig'], p['vf_bd'], p['vf_wt'], device=True).all().item())
+    eng.close()
+    perms = 2 * 2853 + 26
+    return {'keys_per_s': world * n / (ms * 1e-3), 'ms': ms, 'n_per_gpu': n, 'all_verify': ok,
+            'keccak_gperm_s_per_gpu': n * perms / (ms * 1e-3) / 1e9, 'keccak_roofline_gperm_s': 4.05}
+
+
+def secondary_bklm(a, rank, local, world, torch, np, dist):
+    """configs[3]: aggregate + aggregate-verify of 2^k signatures per aggregate (secpar 128), the sorted list
+    sharded over the ranks, ONE reduce of int32 partial sums each."""
+    from lattice_cryptography_b200.distributed import reduce_partial, shard_range
+    class A: secpar, log2n = 128, a.bklm_log2n
+    eng, sch, p = _engine(128, local, np)
+    dev = f'cuda:{local}'
+    total = 1 << A.log2n
+    start, count = shard_range(total, rank, world)
+    # synthetic keys / 32-bit messages; object addresses ascend, so sorted order == index order
+    rng = np.random.default_rng(777)
+    bits = rng.integers(0, 2, (total, 32), dtype=np.uint8) + ord('0')
+    msgs = [bytes(r).decode() for r in bits]
+    ident = [f'<lattice_cryptography.one_time_keys.OneTimeVerificationKey object at 0x7f{16 * i:010x}>' for i in range(total)]
+    agmsg = np.frombuffer(('[' + ', '.join(f"({k}, '{m}')" for k, m in zip(ident, msgs)) + ']').encode(), dtype=np.uint8)
+    d_agmsg = torch.from_numpy(agmsg.copy()).to(dev)
+    seeds = [bin((0x9E3779B97F4A7C15 * (i + 1)) % (1 << 128))[2:].zfill(128) for i in range(start, start + count)]
+    chm = [k + ', ' + m for k, m in zip(ident[start:start + count], msgs[start:start + count])]
+    from lattice_cryptography_b200 import ragged
+    cb, co = ragged(chm)
+    d_chm = (torch.from_numpy(cb).to(dev), torch.from_numpy(co).to(dev))
+    _, sk_ntt, vk_ntt, _ = eng.lm_keygen(sch, seeds, want_sk_coef=False, want_vk_coef=False, device=True)
+    sigs = eng.lm_sign(sch, sk_ntt, d_chm, device=True)
+    res = {}
+
+    def agg():
+        ag = eng.agg_coefs(sch, d_agmsg, start, count, device=True)
+        part = eng.aggregate_partial(sch, sigs, ag, device=True)
+        part = reduce_partial(part)
+        if rank == 0:
+            res['ag_sig'] = eng.aggregate_finish(part, device=True)
+    ms_agg = _timed(torch, dist, world, dev, agg, reps=1)
+    ag_sig = res.get('ag_sig')
+    if world > 1:
+        if rank != 0:
+            ag_sig = torch.empty((p['l'], D), dtype=torch.int16, device=dev)
+        dist.broadcast(ag_sig, src=0)
+    avf_bd = min(p['q'] // 2, total * p['vf_bd'])
+
+    def aggv():
+        ag = eng.agg_coefs(sch, d_agmsg, start, count, device=True)
+        part = eng.aggverify_partial(sch, vk_ntt, d_chm, ag, device=True)
+        part = reduce_partial(part)
+        if rank == 0:
+            res['ok'] = eng.aggverify_finish(part, ag_sig, total, total, avf_bd, 256)
+    ms_aggv = _timed(torch, dist, world, dev, aggv, reps=1)
+    eng.profile(True)
+    eng.profile_reset()
+    eng.agg_coefs(sch, d_agmsg, start, count, device=True)
+    coef_ms, _ = eng.profile_read('agg_coefs')
+    eng.profile(False)
+    eng.close()
+    perms = count * ((len(agmsg) + 12) // 136 + 1)
+    return {'sigs_per_aggregate': total, 'aggregate_sigs_per_s': total / (ms_agg * 1e-3),
+            'aggregate_verify_sigs_per_s': total / (ms_aggv * 1e-3), 'aggregate_ms': ms_agg,
+            'aggregate_verify_ms': ms_aggv, 'verdict': res.get('ok') if rank == 0 else None,
+            'agmsg_bytes': int(len(agmsg)), 'agg_coefs_ms_rank0': coef_ms,
+            'agg_coefs_gperm_s_per_gpu': perms / (coef_ms * 1e-3) / 1e9, 'keccak_roofline_gperm_s': 4.05}
+
+
+def secondary_adaptor(a, rank, local, world, torch, np, dist):
+    """configs[4]: adaptor pre-sign / pre-verify / adapt / verify / extract / witness-verify, 2^15 instances per GPU."""
+    class A: secpar, log2n = 128, 15
+    eng, sch, p = _engine(128, local, np)
+    dev = f'cuda:{local}'
+    n = 1 << A.log2n
+    seeds, seed_off, ch, ch_off = build_inputs(A, rank, torch, np)
+    d_seeds = (torch.from_numpy(seeds).to(dev), torch.from_numpy(seed_off).to(dev))
+    d_ch = (torch.from_numpy(ch).to(dev).view(-1), torch.from_numpy(ch_off).to(dev))
+    _, sk_ntt, vk_ntt, _ = eng.lm_keygen(sch, d_seeds, want_sk_coef=False, want_vk_coef=False, device=True)
+    pvf_bd, vf_bd, ext_bd = p['vf_bd'], p['vf_bd'] + 1, 2 * p['vf_bd'] + 1
+    st = {}
+    t = {}
+    t['witgen'] = _timed(torch, dist, world, dev, lambda: st.update(zip(('wit', 'st_ntt', 'st_coef'), eng.witgen(sch, d_seeds, device=True))))
+    t['presign'] = _timed(torch, dist, world, dev, lambda: st.__setitem__('presig', eng.lm_sign(sch, sk_ntt, d_ch, device=True)))
+    t['preverify'] = _timed(torch, dist, world, dev, lambda: st.__setitem__('pv', eng.lm_verify(sch, vk_ntt, d_ch, st['presig'], pvf_bd, 256, device=True)))
+    t['adapt'] = _timed(torch, dist, world, dev, lambda: st.__setitem__('sig', eng.vec_add(st['presig'], st['wit'], device=True)))
+    t['verify'] = _timed(torch, dist, world, dev, lambda: st.__setitem__('vv', eng.lm_verify(sch, vk_ntt, d_ch, st['sig'], vf_bd, 256, st_ntt=st['st_ntt'], device=True)))
+    t['extract'] = _timed(torch, dist, world, dev, lambda: st.__setitem__('ext', eng.vec_sub(st['sig'], st['presig'], device=True)))
+    t['witness_verify'] = _timed(torch, dist, world, dev, lambda: st.__setitem__('wv', eng.witness_verify(st['ext'], st['st_ntt'], ext_bd, 256, device=True)))
+    ok = bool(st['pv'].all().item() and st['vv'].all().item() and st['wv'].all().item())
+    eng.close()
+    return {'n_per_gpu': n, 'all_verdicts_true': ok,
+            'ops_per_s': {k: world * n / (v * 1e-3) for k, v in t.items()}, 'ms': t}
 
 
 def engine_arm(a):
@@ -299,8 +452,30 @@ def engine_arm(a):
             'setup': {'keygen_s': t_keygen, 'sign_s': t_sign, 'keygen_keys_per_s': n / t_keygen,
                       'sign_sigs_per_s': n / t_sign},
         }
+        # integer-pipe view of the same kernel: thread-instructions per verify from the ncu instruction
+        # count of this build (profiles/README.md), against 148 SM x 64 lanes x max clock per pipe
+        instr_per_unit = 32 * 3718            # smsp__inst_executed.sum / verifies, k_verify, secpar 128
+        pipe_peak = 148 * 64 * (clk['sm_max_mhz'] or 1965.0) * 1e6 if clk else 148 * 64 * 1965e6
+        line['roofline']['int_pipe'] = {
+            'thread_instr_per_unit': instr_per_unit, 'fma_pipe_share': 0.54,
+            'achieved_tinstr_s': instr_per_unit * n / (k_ms * 1e-3) / 1e12,
+            'issue_peak_tinstr_s': 2 * pipe_peak / 1e12,
+            'fma_pipe_frac': 0.54 * instr_per_unit * n / (k_ms * 1e-3) / pipe_peak,
+            'note': 'fraction of the FMA-heavy (IMAD) pipe issue limit, the binding unit of k_verify'}
         if cpu is not None:
             line['cpu_baseline'] = cpu
+    del sig, sig_v, vk_ntt, d_ch, h_sig, h_vk, h_ch, np_sig, np_vk, np_ch
+    torch.cuda.empty_cache()
+    secondary = {}
+    if not a.no_secondary:
+        for name, fn in (('keygen_sign_secpar256', secondary_keygen_sign), ('bklm', secondary_bklm),
+                         ('adaptor', secondary_adaptor)):
+            try:
+                secondary[name] = fn(a, rank, local, world, torch, np, dist)
+            except Exception as exc:          # the headline line must survive a secondary failure
+                secondary[name] = {'error': repr(exc)[:300]}
+    if rank == 0:
+        line['secondary'] = secondary
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
