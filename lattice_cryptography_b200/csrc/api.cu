@@ -330,6 +330,7 @@ int lcb_ctx_create(lcb_ctx** out, int device, int secpar, int q, int d, int l) {
         t.pws[e2] = shoup(t.pw[e2], uq);
     }
     ModQ& m = c->ring.m;
+    m.zero = 0;
     m.q = uq;
     m.negq = (uint32_t)(0u - uq);
     m.barrett = 0xFFFFFFFFu / uq;
@@ -562,7 +563,10 @@ int lcb_lm_keygen_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* seeds,
     CK(c, sg.out(&d_vk_coef, vk_coef, (size_t)n * 2 * D));
     // Signing keys pass through HBM in coefficient form between the sampler and the row-vector
     // product; when the caller does not want them, a bounded scratch chunk is reused.
-    const int64_t chunk = d_sk_coef ? n : (n < 32768 ? n : 32768);
+    // The chunk is two full waves of sampler blocks (4 resident blocks of 128 streams per SM), so that
+    // every launch fills the machine: 151,552 keys = 2.0 GB (secpar 128) / 3.6 GB (secpar 256) of scratch.
+    const int64_t wave = (int64_t)c->ring.num_sms * 4 * 128;
+    const int64_t chunk = d_sk_coef ? n : (n < 2 * wave ? n : 2 * wave);
     int16_t* scratch = nullptr;
     if (!d_sk_coef) CK(c, sg.alloc((void**)&scratch, (size_t)chunk * 2 * l * D * sizeof(int16_t)));
     for (int64_t start = 0; start < n; start += chunk) {

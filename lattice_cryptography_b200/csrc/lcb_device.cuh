@@ -28,6 +28,8 @@ constexpr int XWARP = 2 * XHALF;  // words per warp
 
 // Modulus constants; passed BY VALUE as a kernel parameter so they live in the constant bank.
 struct ModQ {
+    uint32_t zero;        // always 0, but opaque to the compiler: turns `a + b` into a 3-input IADD3 (ALU pipe)
+                          // where ptxas would otherwise pick IMAD.IADD and load the FMA-heavy pipe further
     uint32_t q, negq;
     uint32_t barrett;     // floor((2^32-1)/q)
     uint32_t cq;          // least multiple of q >= 32768: makes any int16 input non-negative
@@ -140,7 +142,7 @@ __device__ __forceinline__ void ntt_fwd_256(uint32_t (&r)[EPT], const ModQ& m, c
             const int k = (1 << (s - 1)) + (j >> (5 - s));
             uint32_t t = shoup_mul(r[j + len], sc.w[k], sc.ws[k], m);
             r[j + len] = r[j] + q2 - t;
-            r[j] = r[j] + t;
+            r[j] = r[j] + t + m.zero;
         }
     }
     xpose_a_to_b(r, xb, lane);
@@ -154,7 +156,7 @@ __device__ __forceinline__ void ntt_fwd_256(uint32_t (&r)[EPT], const ModQ& m, c
             const int k = base + (j >> (9 - s));
             uint32_t t = shoup_mul(r[j + len], tw.w[k], tw.ws[k], m);
             r[j + len] = r[j] + q2 - t;
-            r[j] = r[j] + t;
+            r[j] = r[j] + t + m.zero;
         }
     }
 }

@@ -13,7 +13,6 @@
 // for the life of the kernel; accumulation of the row-vector product is 64-bit (IMAD.WIDE) with a
 // single reduction per output coefficient.  Grids are persistent: (#SM x resident blocks) blocks
 // striding over the batch.
-#include <cstdlib>
 #include "engine.h"
 
 namespace lcb {
@@ -260,8 +259,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int MINB, bool PREFETCH>
-__global__ void __launch_bounds__(RBS, MINB) k_verify(ModQ m, StageConst sc, const NttTables* __restrict__ tab,
+__global__ void __launch_bounds__(RBS, 4) k_verify(ModQ m, StageConst sc, const NttTables* __restrict__ tab,
                                                 const uint32_t* __restrict__ a_hat_g, int l,
                                                 const int16_t* __restrict__ vec_coef,
                                                 const uint16_t* __restrict__ vk_ntt,
@@ -600,26 +598,11 @@ cudaError_t launch_verify(const RingCtx& c, const int16_t* vec_coef, const uint1
                           uint8_t* verdict, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     size_t smem = verify_smem(c.l);
-    // TEMPORARY tuning switch (env LCB_VERIFY_VARIANT): resident blocks per SM x prefetch
-    static int variant = -1;
-    if (variant < 0) { const char* v = getenv("LCB_VERIFY_VARIANT"); variant = v ? atoi(v) : 0; }
-#define LCB_LAUNCH_VERIFY(K)                                                                                     \
-    do {                                                                                                         \
-        cudaError_t e = allow_smem(K, smem);                                                                     \
-        if (e != cudaSuccess) return e;                                                                          \
-        unsigned grid = persistent_grid(n, HWB, c.num_sms, resident_blocks(K, RBS, smem));                       \
-        K<<<grid, RBS, smem, st>>>(c.m, c.sc, c.tab, c.a_hat, c.l, vec_coef, vk_ntt, ch_pairs, ch_wt, rhs_only,  \
-                                   extra_rhs, n, bd, wt, verdict);                                               \
-    } while (0)
-    switch (variant) {
-        case 1: LCB_LAUNCH_VERIFY((k_verify<5, true>)); break;
-        case 2: LCB_LAUNCH_VERIFY((k_verify<6, true>)); break;
-        case 3: LCB_LAUNCH_VERIFY((k_verify<4, false>)); break;
-        case 4: LCB_LAUNCH_VERIFY((k_verify<5, false>)); break;
-        case 5: LCB_LAUNCH_VERIFY((k_verify<6, false>)); break;
-        default: LCB_LAUNCH_VERIFY((k_verify<4, true>)); break;
-    }
-#undef LCB_LAUNCH_VERIFY
+    cudaError_t e = allow_smem(k_verify, smem);
+    if (e != cudaSuccess) return e;
+    unsigned grid = persistent_grid(n, HWB, c.num_sms, resident_blocks(k_verify, RBS, smem));
+    k_verify<<<grid, RBS, smem, st>>>(c.m, c.sc, c.tab, c.a_hat, c.l, vec_coef, vk_ntt, ch_pairs, ch_wt, rhs_only,
+                                      extra_rhs, n, bd, wt, verdict);
     return cudaGetLastError();
 }
 

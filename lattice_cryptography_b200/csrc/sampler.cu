@@ -10,57 +10,13 @@
 // conflict-free because all threads of a warp consume the stream in lock-step) and read back by a
 // big-endian bit cursor that feeds the index / coefficient decoder directly.
 #include "engine.h"
+#include "sampler_device.cuh"
 
 namespace lcb {
 
 namespace {
 
 constexpr int SBS = 128;          // threads per block = SHAKE streams per block
-constexpr int RATE_WORDS = 34;    // 136 bytes
-
-__constant__ uint64_t c_rc[24] = LCB_KECCAK_RC_INIT;
-
-// ---- message access ------------------------------------------------------------------------------
-// 32-bit little-endian word of a byte string at an arbitrary byte offset, from aligned loads only.
-// The word must lie inside the string except for its alignment slack (never crosses the aligned
-// word that holds the last valid byte).
-__device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t* p) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-    const unsigned sh = (unsigned)(a & 3) * 8;
-    const uint32_t w0 = __ldg(w);
-    const uint32_t w1 = sh ? __ldg(w + 1) : 0u;
-    return __funnelshift_r(w0, w1, sh);
-}
-
-// The hash input of one stream: salt (warp-uniform, from the kernel parameter) || msg (ragged).
-struct InputView {
-    const uint32_t* salt_w;     // salt bytes, zero padded, as words
-    int salt_len;
-    const uint8_t* msg;
-    int64_t msg_len;
-    __device__ __forceinline__ int64_t total() const { return (int64_t)salt_len + msg_len; }
-    __device__ __forceinline__ uint32_t byte_at(int64_t p) const {
-        if (p < salt_len) return (salt_w[p >> 2] >> (8 * (p & 3))) & 0xFFu;
-        return __ldg(msg + (p - salt_len));
-    }
-    // stream word k (bytes 4k .. 4k+3) with SHAKE padding applied: pad_pos = total(), last = index of
-    // the final byte of the final block
-    __device__ __forceinline__ uint32_t word_at(int64_t k, int64_t tot, int64_t last) const {
-        const int64_t p = 4 * k;
-        if (p + 4 <= salt_len) return salt_w[k];
-        if (p >= salt_len && p + 4 <= tot) return load_u32_unaligned(msg + (p - salt_len));
-        uint32_t v = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int64_t q = p + b;
-            uint32_t byte = q < tot ? byte_at(q) : (q == tot ? 0x1Fu : 0u);
-            if (q == last) byte ^= 0x80u;
-            v |= byte << (8 * b);
-        }
-        return v;
-    }
-};
 
 // Absorb an input into a fresh state; leaves the state PERMUTED, i.e. its first 136 bytes are the
 // first squeeze block.  `rate` is this block's [34][SBS] staging area in shared memory.
@@ -77,7 +33,7 @@ __device__ __forceinline__ void absorb(KeccakState& s, uint32_t* rate, int tid, 
             s.lo[i] ^= rate[(2 * i) * SBS + tid];
             s.hi[i] ^= rate[(2 * i + 1) * SBS + tid];
         }
-        keccak_f1600(s, c_rc);
+        keccak_f1600(s, c_keccak_rc);
     }
 }
 
@@ -102,167 +58,40 @@ __global__ void __launch_bounds__(SBS) k_shake256(const uint8_t* __restrict__ in
         }
         for (int k = 0; k < 136 && produced < out_len; ++k, ++produced)
             o[produced] = rb[((k >> 2) * SBS + tid) * 4 + (k & 3)];
-        if (produced < out_len) keccak_f1600(s, c_rc);
+        if (produced < out_len) keccak_f1600(s, c_keccak_rc);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Fused SHAKE256 squeeze + decode2polycoefs.  Shared memory per block:
-//   rate  [34][SBS] u32   big-endian stream words of the current rate block
-//   bmap  [8][SBS]  u32   bitmap of still-unused positions (d = 256)
-//   idxb  [wt][SBS] u8    indices in draw order (coefficients are drawn after ALL indices)
-//
-// A field of L bits is reduced modulo m (the number of unused positions, or bd) without big
-// integers: for m <= 256 the field is cut into 16-bit pieces h_j and sum_j h_j * (2^(16j) mod m)
-// < 2^28 is reduced once; for larger m a 16-bit Horner recurrence with one Barrett step per piece.
+// Fused SHAKE256 squeeze + decode2polycoefs (sampler_device.cuh), one stream per thread.
+// Shared memory per block: rate [34][SBS] u32, bmap [8][SBS] u32, two modulus tables, idxb [wt][SBS] u8.
 __global__ void __launch_bounds__(SBS) k_sampler(SamplerArgs a) {
     extern __shared__ uint32_t smem[];
     uint32_t* rate = smem;
     uint32_t* bmap = rate + RATE_WORDS * SBS;
-    uint32_t* mutab = bmap + 8 * SBS;                  // [257] floor((2^32-1)/m)
-    uint32_t* r16tab = mutab + 260;                    // [257] 2^16 mod m
+    uint32_t* mutab = bmap + 8 * SBS;
+    uint32_t* r16tab = mutab + 260;
     uint8_t* idxb = reinterpret_cast<uint8_t*>(r16tab + 260);
 
     const int tid = threadIdx.x;
     const int64_t inst_raw = (int64_t)blockIdx.x * SBS + tid;
     const bool live = inst_raw < a.n;
     const int64_t inst = live ? inst_raw : a.n - 1;
-    for (int mth = 1 + tid; mth <= 256; mth += SBS) {
-        mutab[mth] = 0xFFFFFFFFu / (uint32_t)mth;
-        r16tab[mth] = 65536u % (uint32_t)mth;
-    }
+    fill_mod_tables(mutab, r16tab);
     __syncthreads();
 
     const InputView iv{reinterpret_cast<const uint32_t*>(a.salt), a.salt_len, a.msgs + a.off[inst],
                        a.off[inst + 1] - a.off[inst]};
-    const int64_t in_total = iv.total();
-    const int64_t in_blocks = in_total / 136 + 1;      // the pad byte always needs room
-    const int64_t in_last = in_blocks * 136 - 1;
-    int64_t in_blk = 0;
-    KeccakState s;
-#pragma unroll
-    for (int i = 0; i < 25; ++i) { s.lo[i] = 0; s.hi[i] = 0; }
-
-    // Big-endian bit cursor over the squeeze stream.  The ONLY call site of the permutation is the
-    // refill below: the first refill absorbs every input block (xor + permute), later ones squeeze.
-    uint64_t buf = 0;
-    int nbits = 0;
-    int wpos = RATE_WORDS;
-    auto get = [&](int n) -> uint32_t {       // next n bits (1 <= n <= 32), most significant first
-        if (nbits < n) {
-            if (wpos == RATE_WORDS) {
-                do {
-                    if (in_blk < in_blocks) {
-                        for (int w = 0; w < RATE_WORDS; ++w)
-                            rate[w * SBS + tid] = iv.word_at(in_blk * RATE_WORDS + w, in_total, in_last);
-#pragma unroll
-                        for (int i = 0; i < 17; ++i) {
-                            s.lo[i] ^= rate[(2 * i) * SBS + tid];
-                            s.hi[i] ^= rate[(2 * i + 1) * SBS + tid];
-                        }
-                        ++in_blk;
-                    }
-                    keccak_f1600(s, c_rc);
-                } while (in_blk < in_blocks);
-#pragma unroll
-                for (int i = 0; i < 17; ++i) {
-                    rate[(2 * i) * SBS + tid] = __byte_perm(s.lo[i], 0, 0x0123);
-                    rate[(2 * i + 1) * SBS + tid] = __byte_perm(s.hi[i], 0, 0x0123);
-                }
-                wpos = 0;
-            }
-            buf = (buf << 32) | rate[wpos * SBS + tid];
-            ++wpos;
-            nbits += 32;
-        }
-        nbits -= n;
-        return (uint32_t)((buf >> nbits) & ((1ull << n) - 1ull));
-    };
-    const uint32_t bd_mu = 0xFFFFFFFFu / (uint32_t)a.bd, bd_r16 = 65536u % (uint32_t)a.bd;
-
+    const DecodeParams dp{a.bd, a.wt, a.vec_len, a.idx_bits, a.mag_bits, a.pad_bits};
+    const StreamCols sc{rate + tid, bmap + tid, idxb + tid, SBS, mutab, r16tab};
+    int16_t* dense = a.out_dense ? a.out_dense + inst * a.dense_stride : nullptr;
+    uint32_t* pairs = a.out_pairs ? reinterpret_cast<uint32_t*>(a.out_pairs) + inst * a.vec_len * (int64_t)a.wt : nullptr;
     const int wt = a.wt;
-    for (int poly = 0; poly < a.vec_len; ++poly) {
-#pragma unroll
-        for (int w = 0; w < 8; ++w) bmap[w * SBS + tid] = 0xFFFFFFFFu;
-        int16_t* dense = a.out_dense ? a.out_dense + inst * a.dense_stride + (int64_t)poly * D : nullptr;
-        uint32_t* pairs = a.out_pairs
-                              ? reinterpret_cast<uint32_t*>(a.out_pairs) + (inst * a.vec_len + poly) * (int64_t)wt
-                              : nullptr;
-        for (int f = 0; f <= 2 * wt; ++f) {
-            // ---- field description (warp-uniform)
-            int width;                 // value bits after the optional sign bit
-            uint32_t mod;              // 0: raw value (<= 32 bits);  1: value not needed (skip)
-            const bool is_coef = f >= wt && f < 2 * wt;
-            if (f == 0) { width = LOGD; mod = 0; }
-            else if (f < wt) { width = a.idx_bits; mod = (uint32_t)(D - f); }
-            else if (is_coef) { width = a.mag_bits; mod = (uint32_t)a.bd; }
-            else { width = a.pad_bits; mod = 1; }
-            const bool small = mod >= 2 && mod <= 256, big = mod > 256;
-            const uint32_t mu = is_coef ? bd_mu : (small ? mutab[mod] : 0u);
-            const uint32_t r16 = is_coef ? bd_r16 : (small ? r16tab[mod] : 0u);   // 2^16 mod m
-            // ---- consume it, most significant bits first, through ONE call site of the bit cursor.
-            // small m: 32-bit pieces c, acc <- ((acc*r16 + c>>16)*r16 + (c&0xFFFF)) mod m  (< 2^25 before
-            // the reduction); large m: 16-bit Horner pieces; the leading piece absorbs the odd bits.
-            uint32_t sign = 0, r = 0;
-            bool want_sign = is_coef;
-            int rem = width + (is_coef ? 1 : 0);
-            while (rem > 0) {
-                const int mask = big ? 15 : 31;
-                const int take = want_sign ? 1 : ((rem & mask) ? (rem & mask) : mask + 1);
-                const uint32_t c = get(take);
-                rem -= take;
-                if (want_sign) { sign = c; want_sign = false; }
-                else if (mod == 0) r = c;
-                else if (mod != 1) {
-                    const uint32_t x = small ? (r * r16 + (c >> 16)) * r16 + (c & 0xFFFFu) : ((r << take) | c);
-                    uint32_t t = x - __umulhi(x, mu) * mod;
-                    t = t >= mod ? t - mod : t;
-                    r = t >= mod ? t - mod : t;
-                }
-            }
-            // ---- act on it
-            if (f < wt) {
-                uint32_t selw, word, pos;
-                if (f == 0) {
-                    selw = r >> 5;
-                    pos = r & 31;
-                    word = bmap[selw * SBS + tid];
-                } else {
-                    // r-th (0-based) still-unused position in ascending order
-                    uint32_t k = r;
-                    bool found = false;
-                    selw = 0; word = 0;
-#pragma unroll
-                    for (uint32_t w = 0; w < 8; ++w) {
-                        uint32_t cand = bmap[w * SBS + tid];
-                        uint32_t c = __popc(cand);
-                        if (!found) {
-                            if (k < c) { found = true; selw = w; word = cand; }
-                            else k -= c;
-                        }
-                    }
-                    uint32_t wd = word, c;
-                    pos = 0;
-                    c = __popc(wd & 0xFFFFu); if (k >= c) { k -= c; pos += 16; wd >>= 16; }
-                    c = __popc(wd & 0xFFu);   if (k >= c) { k -= c; pos += 8;  wd >>= 8; }
-                    c = __popc(wd & 0xFu);    if (k >= c) { k -= c; pos += 4;  wd >>= 4; }
-                    c = __popc(wd & 0x3u);    if (k >= c) { k -= c; pos += 2;  wd >>= 2; }
-                    c = wd & 1u;              if (k >= c) { pos += 1; }
-                }
-                bmap[selw * SBS + tid] = word & ~(1u << pos);
-                idxb[f * SBS + tid] = (uint8_t)(selw * 32 + pos);
-            } else if (is_coef) {
-                const int e = f - wt;
-                const int idx = idxb[e * SBS + tid];
-                const int mag = 1 + (int)r;
-                const int coef = sign ? mag : -mag;
-                if (live) {
-                    if (dense) dense[idx] = (int16_t)coef;
-                    if (pairs) pairs[e] = (uint32_t)idx | ((uint32_t)(uint16_t)(int16_t)coef << 16);
-                }
-            }
-        }
-    }
+    sample_stream(dp, iv, sc, [&](int poly, int e, int idx, int coef) {
+        if (!live) return;
+        if (dense) dense[(int64_t)poly * D + idx] = (int16_t)coef;
+        if (pairs) pairs[(int64_t)poly * wt + e] = (uint32_t)idx | ((uint32_t)(uint16_t)(int16_t)coef << 16);
+    });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -350,7 +179,7 @@ __global__ void __launch_bounds__(ABS) k_agg_coefs(SamplerArgs a) {
                 s.hi[i] ^= edge[(2 * i + 1) * ABS + threadIdx.x];
             }
         }
-        keccak_f1600(s, c_rc);
+        keccak_f1600(s, c_keccak_rc);
     }
     const uint32_t k = s.lo[0] & 0xFFu;                 // first digest byte: the 8 index bits
     const int sgn = (s.lo[0] >> 15) & 1u ? 1 : -1;      // top bit of the second byte: the sign bit
