@@ -339,6 +339,8 @@ int lcb_ctx_create(lcb_ctx** out, int device, int secpar, int q, int d, int l) {
     m.half = (uq - 1) / 2;
     m.dinv = (uint32_t)powmod((uint32_t)d, uq - 2, uq);
     m.dinv_s = shoup(m.dinv, uq);
+    m.z1c = (int32_t)t.w[1] > (int32_t)m.half ? (int32_t)t.w[1] - (int32_t)uq : (int32_t)t.w[1];
+    m.k1 = (uint32_t)((((1ull << 30) + (1ull << 15) + uq - 1) / uq) * uq);
     for (int k = 0; k < 16; ++k) {
         c->ring.sc.w[k] = t.w[k];
         c->ring.sc.ws[k] = t.ws[k];

@@ -36,6 +36,8 @@ struct ModQ {
     uint32_t cq2;         // least multiple of q >= 65536 + 2q: bound for u16-derived lazy values
     uint32_t half;        // (q-1)/2
     uint32_t dinv, dinv_s;  // d^-1 mod q and its Shoup companion
+    int32_t z1c;          // zetas[1] (the stage-1 twiddle) as a centred residue, |z1c| < 2^15
+    uint32_t k1;          // least multiple of q >= 2^30 + 2^15: offset of the reduction-free first stage
 };
 
 // Warp-uniform twiddles of stages 1..4 (zeta index k = 1..15), forward and inverse.
@@ -81,9 +83,10 @@ __device__ __forceinline__ uint32_t mulmod_full(uint32_t a, uint32_t b, const Mo
 }
 
 __device__ __forceinline__ uint32_t reduce64(uint64_t acc, const ModQ& m) {
-    // acc < 2^44 -> acc mod q in [0, q)   (q < 2^16)
-    uint32_t r1 = barrett_full((uint32_t)(acc >> 12), m);
-    return barrett_full((r1 << 12) | ((uint32_t)acc & 0xFFFu), m);
+    // acc < 2^54 -> acc mod q in [0, q)   (q < 2^16): three 12-bit-shifted Barrett steps
+    uint32_t r = barrett_full((uint32_t)(acc >> 24), m);
+    r = barrett_full((r << 12) | ((uint32_t)(acc >> 12) & 0xFFFu), m);
+    return barrett_full((r << 12) | ((uint32_t)acc & 0xFFFu), m);
 }
 
 __device__ __forceinline__ int32_t center(uint32_t r, const ModQ& m) {
@@ -135,6 +138,47 @@ __device__ __forceinline__ void ntt_fwd_256(uint32_t (&r)[EPT], const ModQ& m, c
     const uint32_t q2 = 2 * m.q;
 #pragma unroll
     for (int s = 1; s <= 4; ++s) {
+        const int len = 8 >> (s - 1);
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            if (j & len) continue;
+            const int k = (1 << (s - 1)) + (j >> (5 - s));
+            uint32_t t = shoup_mul(r[j + len], sc.w[k], sc.ws[k], m);
+            r[j + len] = r[j] + q2 - t;
+            r[j] = r[j] + t + m.zero;
+        }
+    }
+    xpose_a_to_b(r, xb, lane);
+#pragma unroll
+    for (int s = 5; s <= 8; ++s) {
+        const int len = 256 >> s;
+        const int base = (1 << (s - 5)) - 1;
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            if (j & len) continue;
+            const int k = base + (j >> (9 - s));
+            uint32_t t = shoup_mul(r[j + len], tw.w[k], tw.ws[k], m);
+            r[j + len] = r[j] + q2 - t;
+            r[j] = r[j] + t + m.zero;
+        }
+    }
+}
+
+// Same transform for RAW centred int16 coefficients (any value in [-2^15, 2^15)): the first stage needs
+// no modular reduction at all, because |x * z1c| < 2^30 fits a word: X' = X + z1c*Y + k1, Y' = X - z1c*Y + k1
+// with k1 = 0 mod q.  One IMAD instead of IMAD.HI + 2 IMAD per first-stage butterfly, and no input
+// offset.  Outputs are < 2^31 + 2^16 + 14 q < 2^32 (lazy); 64-bit row-vector accumulators stay < 2^54.
+__device__ __forceinline__ void ntt_fwd_256_raw(const int (&x)[EPT], uint32_t (&r)[EPT], const ModQ& m,
+                                                const StageConst& sc, const LaneTw& tw, uint32_t* xb, int lane) {
+    const uint32_t q2 = 2 * m.q;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int t = x[j + 8] * m.z1c;
+        r[j] = (uint32_t)(x[j] + t) + m.k1;
+        r[j + 8] = (uint32_t)(x[j] - t) + m.k1;
+    }
+#pragma unroll
+    for (int s = 2; s <= 4; ++s) {
         const int len = 8 >> (s - 1);
 #pragma unroll
         for (int j = 0; j < EPT; ++j) {

@@ -46,6 +46,11 @@ __device__ __forceinline__ void load_coef_a(uint32_t (&r)[EPT], const int16_t* _
     for (int j = 0; j < EPT; ++j) r[j] = (uint32_t)((int)__ldg(p + lane + 16 * j) + (int)cq);
 }
 
+__device__ __forceinline__ void load_coef_raw(int (&x)[EPT], const int16_t* __restrict__ p, int lane) {
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) x[j] = (int)__ldg(p + lane + 16 * j);
+}
+
 __device__ __forceinline__ void store_coef_a(int16_t* __restrict__ p, const uint32_t (&r)[EPT], int lane, const ModQ& m) {
 #pragma unroll
     for (int j = 0; j < EPT; ++j) p[lane + 16 * j] = (int16_t)finish_coef(r[j], m);
@@ -108,8 +113,9 @@ __global__ void __launch_bounds__(RBS) k_ntt_fwd(ModQ m, StageConst sc, const Nt
         const bool live = raw < npoly;
         const int64_t item = live ? raw : npoly - 1;
         uint32_t r[EPT];
-        load_coef_a(r, coef + item * D, h.lane, m.cq);
-        ntt_fwd_256(r, m, sc, tw, h.xb, h.lane);
+        int x[EPT];
+        load_coef_raw(x, coef + item * D, h.lane);
+        ntt_fwd_256_raw(x, r, m, sc, tw, h.xb, h.lane);
 #pragma unroll
         for (int i = 0; i < EPT; ++i) r[i] = barrett_full(r[i], m);
         if (live) store_u16x16(out + item * D + 16 * h.lane, r);
@@ -184,8 +190,9 @@ __global__ void __launch_bounds__(RBS) k_matvec(ModQ m, StageConst sc, const Ntt
         for (int i = 0; i < EPT; ++i) acc[i] = 0;
         for (int i = 0; i < l; ++i) {
             uint32_t r[EPT];
-            load_coef_a(r, vec_coef + (item * l + i) * D, h.lane, m.cq);
-            ntt_fwd_256(r, m, sc, tw, h.xb, h.lane);
+            int x[EPT];
+            load_coef_raw(x, vec_coef + (item * l + i) * D, h.lane);
+            ntt_fwd_256_raw(x, r, m, sc, tw, h.xb, h.lane);
             if (vec_ntt) {
 #pragma unroll
                 for (int k = 0; k < EPT; ++k) r[k] = barrett_full(r[k], m);
@@ -333,9 +340,7 @@ __global__ void __launch_bounds__(RBS, 4) k_verify(ModQ m, StageConst sc, const 
                 for (int o = 8; o >= 1; o >>= 1) nz += __shfl_xor_sync(0xFFFFFFFFu, nz, o);
                 bad |= nz > wt;
             }
-#pragma unroll
-            for (int j = 0; j < EPT; ++j) r[j] = (uint32_t)(pre[j] + (int)m.cq);
-            ntt_fwd_256(r, m, sc, tw, h.xb, h.lane);
+            ntt_fwd_256_raw(pre, r, m, sc, tw, h.xb, h.lane);
             mac_row(acc, r, a_hat + i * AROW, h.lane);
         }
         bad |= hi > bd || lo < -bd;

@@ -65,16 +65,17 @@ __global__ void __launch_bounds__(SBS) k_shake256(const uint8_t* __restrict__ in
 // ------------------------------------------------------------------------------------------------
 // Fused SHAKE256 squeeze + decode2polycoefs (sampler_device.cuh), one stream per thread.
 // Shared memory per block: rate [34][SBS] u32, bmap [8][SBS] u32, two modulus tables, idxb [wt][SBS] u8.
-__global__ void __launch_bounds__(SBS) k_sampler(SamplerArgs a) {
+template <int P>   // streams (threads) per block; compile-time so that column addressing is shifts, not multiplies
+__global__ void __launch_bounds__(P) k_sampler(SamplerArgs a) {
     extern __shared__ uint32_t smem[];
     uint32_t* rate = smem;
-    uint32_t* bmap = rate + RATE_WORDS * SBS;
-    uint32_t* mutab = bmap + 8 * SBS;
+    uint32_t* bmap = rate + RATE_WORDS * P;
+    uint32_t* mutab = bmap + 8 * P;
     uint32_t* r16tab = mutab + 260;
     uint8_t* idxb = reinterpret_cast<uint8_t*>(r16tab + 260);
 
     const int tid = threadIdx.x;
-    const int64_t inst_raw = (int64_t)blockIdx.x * SBS + tid;
+    const int64_t inst_raw = (int64_t)blockIdx.x * P + tid;
     const bool live = inst_raw < a.n;
     const int64_t inst = live ? inst_raw : a.n - 1;
     fill_mod_tables(mutab, r16tab);
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(SBS) k_sampler(SamplerArgs a) {
     const InputView iv{reinterpret_cast<const uint32_t*>(a.salt), a.salt_len, a.msgs + a.off[inst],
                        a.off[inst + 1] - a.off[inst]};
     const DecodeParams dp{a.bd, a.wt, a.vec_len, a.idx_bits, a.mag_bits, a.pad_bits};
-    const StreamCols sc{rate + tid, bmap + tid, idxb + tid, SBS, mutab, r16tab};
+    const StreamCols sc{rate + tid, bmap + tid, idxb + tid, P, mutab, r16tab};
     int16_t* dense = a.out_dense ? a.out_dense + inst * a.dense_stride : nullptr;
     uint32_t* pairs = a.out_pairs ? reinterpret_cast<uint32_t*>(a.out_pairs) + inst * a.vec_len * (int64_t)a.wt : nullptr;
     const int wt = a.wt;
@@ -198,11 +199,22 @@ cudaError_t launch_shake256(const uint8_t* in, const int64_t* off, int64_t n, ui
 
 cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st) {
     if (a.n <= 0) return cudaSuccess;
-    size_t smem = (size_t)(RATE_WORDS + 8) * SBS * 4 + 2 * 260 * 4 + (size_t)a.wt * SBS;
-    cudaError_t e = cudaFuncSetAttribute(k_sampler, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    // Grids of at most two 128-stream blocks per SM (small batches of long streams) run as 64-stream
+    // blocks instead, which spreads them over twice as many scheduler slots.
+    const bool narrow = (a.n + SBS - 1) / SBS <= (int64_t)num_sms * 2;
+    const int threads = narrow ? SBS / 2 : SBS;
+    size_t smem = (size_t)(RATE_WORDS + 8) * threads * 4 + 2 * 260 * 4 + (size_t)a.wt * threads;
+    auto kern = narrow ? k_sampler<SBS / 2> : k_sampler<SBS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int64_t blocks = (a.n + SBS - 1) / SBS;
-    k_sampler<<<(unsigned)blocks, SBS, smem, st>>>(a);
+    int64_t blocks = (a.n + threads - 1) / threads;
+    kern<<<(unsigned)blocks, threads, smem, st>>>(a);
     return cudaGetLastError();
 }
 
