@@ -93,38 +93,47 @@ __device__ __forceinline__ void sample_stream(const DecodeParams& dp, const Inpu
     KeccakState s;
 #pragma unroll
     for (int i = 0; i < 25; ++i) { s.lo[i] = 0; s.hi[i] = 0; }
-    uint64_t buf = 0;
-    int nbits = 0;
+    // Big-endian bit cursor: `cur` is the stream word being consumed (`off` bits of it already used),
+    // `nxt` the word after it; a field of n <= 32 bits is one funnel shift.  fetch() is the only place
+    // that touches the sponge: the first call absorbs every input block, later ones squeeze.
     int wpos = RATE_WORDS;
-    auto get = [&](int n) -> uint32_t {       // next n bits (1 <= n <= 32), most significant first
-        if (nbits < n) {
-            if (wpos == RATE_WORDS) {
-                do {
-                    if (in_blk < in_blocks) {
-                        for (int w = 0; w < RATE_WORDS; ++w)
-                            sc.rate[w * P] = iv.word_at(in_blk * RATE_WORDS + w, in_total, in_last);
+    auto fetch = [&]() -> uint32_t {
+        if (wpos == RATE_WORDS) {
+            do {
+                if (in_blk < in_blocks) {
+                    for (int w = 0; w < RATE_WORDS; ++w)
+                        sc.rate[w * P] = iv.word_at(in_blk * RATE_WORDS + w, in_total, in_last);
 #pragma unroll
-                        for (int i = 0; i < 17; ++i) {
-                            s.lo[i] ^= sc.rate[(2 * i) * P];
-                            s.hi[i] ^= sc.rate[(2 * i + 1) * P];
-                        }
-                        ++in_blk;
+                    for (int i = 0; i < 17; ++i) {
+                        s.lo[i] ^= sc.rate[(2 * i) * P];
+                        s.hi[i] ^= sc.rate[(2 * i + 1) * P];
                     }
-                    keccak_f1600(s, c_keccak_rc);
-                } while (in_blk < in_blocks);
-#pragma unroll
-                for (int i = 0; i < 17; ++i) {
-                    sc.rate[(2 * i) * P] = __byte_perm(s.lo[i], 0, 0x0123);
-                    sc.rate[(2 * i + 1) * P] = __byte_perm(s.hi[i], 0, 0x0123);
+                    ++in_blk;
                 }
-                wpos = 0;
+                keccak_f1600(s, c_keccak_rc);
+            } while (in_blk < in_blocks);
+#pragma unroll
+            for (int i = 0; i < 17; ++i) {
+                sc.rate[(2 * i) * P] = __byte_perm(s.lo[i], 0, 0x0123);
+                sc.rate[(2 * i + 1) * P] = __byte_perm(s.hi[i], 0, 0x0123);
             }
-            buf = (buf << 32) | sc.rate[wpos * P];
-            ++wpos;
-            nbits += 32;
+            wpos = 0;
         }
-        nbits -= n;
-        return (uint32_t)((buf >> nbits) & ((1ull << n) - 1ull));
+        return sc.rate[(wpos++) * P];
+    };
+    // `nxt` runs one word ahead of `cur`; the refill loop is the single call site of fetch() (it also
+    // performs the two initial fetches: off starts at 64).
+    uint32_t cur = 0, nxt = 0;
+    unsigned off = 64;
+    auto get = [&](int n) -> uint32_t {       // next n bits (1 <= n <= 32), most significant first
+        while (off >= 32) {
+            off -= 32;
+            cur = nxt;
+            nxt = fetch();
+        }
+        const uint32_t v = __funnelshift_l(nxt, cur, off) >> (32 - n);
+        off += n;
+        return v;
     };
     const uint32_t bd_mu = 0xFFFFFFFFu / (uint32_t)dp.bd, bd_r16 = 65536u % (uint32_t)dp.bd;
     const int wt = dp.wt;
