@@ -244,7 +244,7 @@ def secondary_bklm(a, rank, local, world, torch, np, dist):
     if world > 1:
         if rank != 0:
             ag_sig = torch.empty((p['l'], D), dtype=torch.int16, device=dev)
-        dist.broadcast(ag_sig, src=0)
+        dist.broadcast(ag_sig.view(torch.uint8), src=0)      # NCCL has no int16
     avf_bd = min(p['q'] // 2, total * p['vf_bd'])
 
     def aggv():

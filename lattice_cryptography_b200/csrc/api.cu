@@ -23,6 +23,8 @@ struct lcb_ctx {
     bool has_key_ch = false;
     std::string last_error;
     int64_t launches = 0;
+    uint8_t* idx_scratch = nullptr;      // sampler index parking (grow-only, stream-ordered reuse)
+    size_t idx_scratch_bytes = 0;
     // optional per-kernel CUDA-event timing (lcb_profile_*)
     bool profile = false;
     struct Pending { int id; cudaEvent_t a, b; };
@@ -72,6 +74,23 @@ cudaError_t timed(lcb_ctx* c, int id, F&& launch) {
     cudaEventRecord(p.b, c->stream);
     c->pending.push_back(p);
     return e;
+}
+
+// Point a sampler launch at the ctx's index scratch, growing it when the batch needs more.
+cudaError_t sampler_scratch(lcb_ctx* c, SamplerArgs& a) {
+    const size_t need = sampler_scratch_bytes(a.n, a.wt);
+    if (need > c->idx_scratch_bytes) {
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) return e;
+        if (c->idx_scratch) cudaFree(c->idx_scratch);
+        c->idx_scratch = nullptr;
+        c->idx_scratch_bytes = 0;
+        if ((e = cudaMalloc(&c->idx_scratch, need)) != cudaSuccess) return e;
+        c->idx_scratch_bytes = need;
+    }
+    a.idx_scratch = c->idx_scratch;
+    a.idx_stride = sampler_stride(a.n);
+    return cudaSuccess;
 }
 
 uint64_t powmod(uint64_t b, uint64_t e, uint64_t q) {
@@ -221,6 +240,7 @@ int run_challenge(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* d_msg, const
     a.off = d_off;
     a.n = n;
     a.out_pairs = d_pairs;
+    CK(c, sampler_scratch(c, a));
     CK(c, timed(c, K_SAMPLER, [&] { return launch_sampler(a, c->stream); }));
     return LCB_OK;
 }
@@ -268,7 +288,7 @@ int lcb_ctx_create(lcb_ctx** out, int device, int secpar, int q, int d, int l) {
     if (!out) return LCB_ERR_INVALID;
     *out = nullptr;
     g_create_error.clear();
-    if (d != D || l < 1 || l > 64 || secpar < 1 || secpar > 512 || q < 3 || q >= 65536 || !is_prime(q) ||
+    if (d != D || l < 1 || l > 64 || secpar < 1 || secpar > 512 ||   /* fields of 8+secpar / 16+secpar bits must fit the sampler window */ q < 3 || q >= 65536 || !is_prime(q) ||
         q % (2 * d) != 1) {
         g_create_error = "supported: d == 256, prime q < 65536 with q % 512 == 1, 1 <= l <= 64, 1 <= secpar <= 512";
         return LCB_ERR_INVALID;
@@ -364,6 +384,7 @@ int lcb_ctx_destroy(lcb_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->d_tab) cudaFree(c->d_tab);
     if (c->d_a_hat) cudaFree(c->d_a_hat);
+    if (c->idx_scratch) cudaFree(c->idx_scratch);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return LCB_OK;
@@ -494,6 +515,7 @@ int lcb_hash2polyvec_batch(lcb_ctx* c, const char* salt, const uint8_t* msgs, co
     a.n = n;
     a.dense_stride = (int64_t)vec_len * D;
     if (a.out_dense && wt < D) CK(c, cudaMemsetAsync(a.out_dense, 0, (size_t)n * vec_len * D * sizeof(int16_t), c->stream));
+    CK(c, sampler_scratch(c, a));
     CK(c, timed(c, K_SAMPLER, [&] { return launch_sampler(a, c->stream); }));
     CK(c, sg.finish());
     return LCB_OK;
@@ -581,7 +603,9 @@ int lcb_lm_keygen_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* seeds,
         left.dense_stride = right.dense_stride = (int64_t)2 * l * D;
         left.out_dense = skc;
         right.out_dense = skc + (int64_t)l * D;
+        CK(c, sampler_scratch(c, left));
         CK(c, timed(c, K_SAMPLER, [&] { return launch_sampler(left, c->stream); }));
+        CK(c, sampler_scratch(c, right));
         CK(c, timed(c, K_SAMPLER, [&] { return launch_sampler(right, c->stream); }));
         CK(c, timed(c, K_MATVEC, [&] {
             return launch_matvec(c->ring, skc, cnt * 2, d_sk_ntt ? d_sk_ntt + start * 2 * l * D : nullptr,
@@ -810,6 +834,7 @@ int lcb_adaptor_witgen_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* s
     a.n = n;
     a.out_dense = d_wit;
     a.dense_stride = (int64_t)l * D;
+    CK(c, sampler_scratch(c, a));
     CK(c, timed(c, K_SAMPLER, [&] { return launch_sampler(a, c->stream); }));
     CK(c, timed(c, K_MATVEC, [&] { return launch_matvec(c->ring, d_wit, n, nullptr, d_st_ntt, d_st_coef, c->stream); }));
     CK(c, sg.finish());

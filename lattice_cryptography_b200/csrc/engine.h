@@ -24,9 +24,13 @@ struct SamplerArgs {
     int16_t* out_dense;        // or nullptr; instance stride below (elements)
     int64_t dense_stride;
     int16_t* out_pairs;        // or nullptr; [n][vec_len][wt][2]
+    uint8_t* idx_scratch;      // device scratch, sampler_scratch_bytes(n, wt) bytes
+    int64_t idx_stride;        // streams rounded up to whole blocks
 };
 
 cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st);
+inline int64_t sampler_stride(int64_t n) { return (n + 127) / 128 * 128; }
+inline size_t sampler_scratch_bytes(int64_t n, int wt) { return (size_t)sampler_stride(n) * (size_t)wt; }
 cudaError_t launch_shake256(const uint8_t* in, const int64_t* off, int64_t n, uint8_t* out, int64_t out_len,
                             cudaStream_t st);
 cudaError_t launch_agg_coefs(const SamplerArgs& a, cudaStream_t st);   // shared-message fast path, wt == 1

@@ -319,7 +319,7 @@ struct KeccakRhoPi<25> {
 };
 
 __device__ __forceinline__ void keccak_f1600(KeccakState& s, const uint64_t* __restrict__ rc) {
-#pragma unroll 4
+#pragma unroll 2
     for (int round = 0; round < 24; ++round) {
         uint32_t clo[5], chi[5], dlo[5], dhi[5];
 #pragma unroll

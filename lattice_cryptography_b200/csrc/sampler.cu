@@ -68,11 +68,10 @@ __global__ void __launch_bounds__(SBS) k_shake256(const uint8_t* __restrict__ in
 template <int P>   // streams (threads) per block; compile-time so that column addressing is shifts, not multiplies
 __global__ void __launch_bounds__(P) k_sampler(SamplerArgs a) {
     extern __shared__ uint32_t smem[];
-    uint32_t* rate = smem;
-    uint32_t* bmap = rate + RATE_WORDS * P;
+    uint32_t* ring = smem;                       // [RING_WORDS][P]
+    uint32_t* bmap = ring + RING_WORDS * P;      // [8][P]   (directly after the ring, see StreamCols)
     uint32_t* mutab = bmap + 8 * P;
     uint32_t* r16tab = mutab + 260;
-    uint8_t* idxb = reinterpret_cast<uint8_t*>(r16tab + 260);
 
     const int tid = threadIdx.x;
     const int64_t inst_raw = (int64_t)blockIdx.x * P + tid;
@@ -84,7 +83,7 @@ __global__ void __launch_bounds__(P) k_sampler(SamplerArgs a) {
     const InputView iv{reinterpret_cast<const uint32_t*>(a.salt), a.salt_len, a.msgs + a.off[inst],
                        a.off[inst + 1] - a.off[inst]};
     const DecodeParams dp{a.bd, a.wt, a.vec_len, a.idx_bits, a.mag_bits, a.pad_bits};
-    const StreamCols sc{rate + tid, bmap + tid, idxb + tid, P, mutab, r16tab};
+    const StreamCols sc{ring + tid, bmap + tid, P, mutab, r16tab, a.idx_scratch + inst_raw, a.idx_stride};
     int16_t* dense = a.out_dense ? a.out_dense + inst * a.dense_stride : nullptr;
     uint32_t* pairs = a.out_pairs ? reinterpret_cast<uint32_t*>(a.out_pairs) + inst * a.vec_len * (int64_t)a.wt : nullptr;
     const int wt = a.wt;
@@ -209,7 +208,8 @@ cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st) {
     // blocks instead, which spreads them over twice as many scheduler slots.
     const bool narrow = (a.n + SBS - 1) / SBS <= (int64_t)num_sms * 2;
     const int threads = narrow ? SBS / 2 : SBS;
-    size_t smem = (size_t)(RATE_WORDS + 8) * threads * 4 + 2 * 260 * 4 + (size_t)a.wt * threads;
+    if (!a.idx_scratch || a.idx_stride < (a.n + threads - 1) / threads * threads) return cudaErrorInvalidValue;
+    size_t smem = (size_t)(RING_WORDS + 8) * threads * 4 + 2 * 260 * 4;
     auto kern = narrow ? k_sampler<SBS / 2> : k_sampler<SBS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

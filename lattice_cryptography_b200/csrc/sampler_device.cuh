@@ -59,13 +59,18 @@ struct DecodeParams {
     int pad_bits;              // 8*nb - bti - wt*btd
 };
 
+constexpr int RING_EXTRA = 20;                       // words a field may need beyond the current block
+constexpr int RING_WORDS = RATE_WORDS + RING_EXTRA;  // per-stream window over the squeeze stream
+constexpr int MAX_FIELD_BITS = 32 * (RING_EXTRA - 1);
+
 struct StreamCols {
-    uint32_t* rate;            // [34] column: big-endian stream words of the current rate block
-    uint32_t* bmap;            // [8]  column: bitmap of still-unused positions (d = 256)
-    uint8_t* idxb;             // [wt] byte column: indices in draw order (coefficients come after ALL indices)
+    uint32_t* ring;            // [RING_WORDS] column: big-endian stream words, window over the digest
+    uint32_t* bmap;            // [8] column: bitmap of still-unused positions (d = 256); MUST follow `ring`
     int pitch;
     const uint32_t* mutab;     // [257] floor((2^32-1)/m)   (block-shared)
     const uint32_t* r16tab;    // [257] 2^16 mod m
+    uint8_t* idxs;             // global scratch, byte e of this stream at idxs[e * idx_stride]
+    int64_t idx_stride;
 };
 
 __device__ __forceinline__ void fill_mod_tables(uint32_t* mutab, uint32_t* r16tab) {
@@ -75,13 +80,27 @@ __device__ __forceinline__ void fill_mod_tables(uint32_t* mutab, uint32_t* r16ta
     }
 }
 
+__device__ __forceinline__ uint32_t barrett_small(uint32_t x, uint32_t mu, uint32_t mod) {
+    uint32_t t = x - __umulhi(x, mu) * mod;          // in [0, 3 mod)
+    t = min(t, t - mod);                             // unsigned wrap-around: subtracts only when t >= mod
+    return min(t, t - mod);
+}
+
 // SHAKE256(salt || msg) -> vec_len polynomials; emit(poly, e, index, coefficient) in draw order.
 //
-// A field of L bits is reduced modulo m (the number of unused positions, or bd) without big integers:
-// for m <= 256 as 32-bit pieces c, acc <- ((acc*r16 + c>>16)*r16 + (c&0xFFFF)) mod m with r16 = 2^16 mod m
-// (one Barrett step per 32 bits); for larger m a 16-bit Horner recurrence.  Fields whose value is not
-// needed (magnitudes when bd = 1, pad bits) are skipped 32 bits at a time.  The permutation has ONE
-// call site: the first refill absorbs every input block (xor + permute), later refills squeeze.
+// The digest is consumed through a per-stream WINDOW of RING_WORDS stream words in shared memory.
+// ensure(bits) - called once at the start of every field and the ONLY call site of the permutation -
+// tops the window up by one 136-byte block whenever the field would not fit (the first call absorbs
+// every input block).  Inside a field the cursor is a pure funnel shift over two window words, so the
+// per-field code is straight-line and specialised:
+//   index field   : (8 + secpar) bits reduced mod (#unused positions) as one head piece + 32-bit pieces,
+//                   acc <- ((acc*r16 + c>>16)*r16 + (c&0xFFFF)) mod m with r16 = 2^16 mod m, then the
+//                   acc-th unused position is taken from a 256-bit bitmap (popcount search);
+//   coefficient   : sign bit, then magnitude 1 + (field mod bd) the same way (bd <= 256), or a 16-bit
+//                   Horner recurrence (larger bd, only key_ch), or nothing at all when bd == 1;
+//   pad bits      : skipped.
+// Indices are parked in a global scratch column until their coefficients arrive (the coefficients of a
+// polynomial are drawn after ALL its indices).
 template <typename Emit>
 __device__ __forceinline__ void sample_stream(const DecodeParams& dp, const InputView& iv, const StreamCols& sc,
                                               Emit&& emit) {
@@ -93,20 +112,22 @@ __device__ __forceinline__ void sample_stream(const DecodeParams& dp, const Inpu
     KeccakState s;
 #pragma unroll
     for (int i = 0; i < 25; ++i) { s.lo[i] = 0; s.hi[i] = 0; }
-    // Big-endian bit cursor: `cur` is the stream word being consumed (`off` bits of it already used),
-    // `nxt` the word after it; a field of n <= 32 bits is one funnel shift.  fetch() is the only place
-    // that touches the sponge: the first call absorbs every input block, later ones squeeze.
-    int wpos = RATE_WORDS;
-    auto fetch = [&]() -> uint32_t {
-        if (wpos == RATE_WORDS) {
+    int rp = 0;                 // read cursor, in bits from the start of the window
+    int nw = 0;                 // valid words in the window
+    auto ensure = [&](int bits) {
+        if (rp + bits > 32 * nw) {
+            const int drop = rp >> 5, keep = nw - drop;          // keep <= RING_EXTRA
+            for (int i = 0; i < keep; ++i) sc.ring[i * P] = sc.ring[(drop + i) * P];
+            rp -= 32 * drop;
             do {
                 if (in_blk < in_blocks) {
+                    // the not-yet-valid part of the window doubles as staging for the input block
                     for (int w = 0; w < RATE_WORDS; ++w)
-                        sc.rate[w * P] = iv.word_at(in_blk * RATE_WORDS + w, in_total, in_last);
+                        sc.ring[(keep + w) * P] = iv.word_at(in_blk * RATE_WORDS + w, in_total, in_last);
 #pragma unroll
                     for (int i = 0; i < 17; ++i) {
-                        s.lo[i] ^= sc.rate[(2 * i) * P];
-                        s.hi[i] ^= sc.rate[(2 * i + 1) * P];
+                        s.lo[i] ^= sc.ring[(keep + 2 * i) * P];
+                        s.hi[i] ^= sc.ring[(keep + 2 * i + 1) * P];
                     }
                     ++in_blk;
                 }
@@ -114,97 +135,94 @@ __device__ __forceinline__ void sample_stream(const DecodeParams& dp, const Inpu
             } while (in_blk < in_blocks);
 #pragma unroll
             for (int i = 0; i < 17; ++i) {
-                sc.rate[(2 * i) * P] = __byte_perm(s.lo[i], 0, 0x0123);
-                sc.rate[(2 * i + 1) * P] = __byte_perm(s.hi[i], 0, 0x0123);
+                sc.ring[(keep + 2 * i) * P] = __byte_perm(s.lo[i], 0, 0x0123);
+                sc.ring[(keep + 2 * i + 1) * P] = __byte_perm(s.hi[i], 0, 0x0123);
             }
-            wpos = 0;
+            nw = keep + RATE_WORDS;
         }
-        return sc.rate[(wpos++) * P];
     };
-    // `nxt` runs one word ahead of `cur`; the refill loop is the single call site of fetch() (it also
-    // performs the two initial fetches: off starts at 64).
-    uint32_t cur = 0, nxt = 0;
-    unsigned off = 64;
-    auto get = [&](int n) -> uint32_t {       // next n bits (1 <= n <= 32), most significant first
-        while (off >= 32) {
-            off -= 32;
-            cur = nxt;
-            nxt = fetch();
-        }
-        const uint32_t v = __funnelshift_l(nxt, cur, off) >> (32 - n);
-        off += n;
+    auto take = [&](int n) -> uint32_t {      // next n bits (1 <= n <= 32), most significant first; no refill
+        const int wi = rp >> 5;
+        const uint32_t v = __funnelshift_l(sc.ring[(wi + 1) * P], sc.ring[wi * P], rp & 31) >> (32 - n);
+        rp += n;
         return v;
     };
-    const uint32_t bd_mu = 0xFFFFFFFFu / (uint32_t)dp.bd, bd_r16 = 65536u % (uint32_t)dp.bd;
+    // value of the next `width` bits modulo m (2 <= m <= 256), most significant piece first
+    auto field_small = [&](int width, uint32_t m, uint32_t mu, uint32_t r16) -> uint32_t {
+        const int head = (width & 31) ? (width & 31) : 32;
+        uint32_t c = take(head);
+        uint32_t acc = barrett_small((c >> 16) * r16 + (c & 0xFFFFu), mu, m);
+        for (int left = width - head; left > 0; left -= 32) {
+            c = take(32);
+            acc = barrett_small((acc * r16 + (c >> 16)) * r16 + (c & 0xFFFFu), mu, m);
+        }
+        return acc;
+    };
+    const uint32_t bd = (uint32_t)dp.bd;
+    const uint32_t bd_mu = 0xFFFFFFFFu / bd, bd_r16 = 65536u % bd;
     const int wt = dp.wt;
     for (int poly = 0; poly < dp.vec_len; ++poly) {
 #pragma unroll
         for (int w = 0; w < 8; ++w) sc.bmap[w * P] = 0xFFFFFFFFu;
         for (int f = 0; f <= 2 * wt; ++f) {
-            // ---- field description (warp-uniform)
-            int width;                 // value bits after the optional sign bit
-            uint32_t mod;              // 0: raw value (<= 32 bits);  1: value not needed (skip)
-            const bool is_coef = f >= wt && f < 2 * wt;
-            if (f == 0) { width = LOGD; mod = 0; }
-            else if (f < wt) { width = dp.idx_bits; mod = (uint32_t)(D - f); }
-            else if (is_coef) { width = dp.mag_bits; mod = (uint32_t)dp.bd; }
-            else { width = dp.pad_bits; mod = 1; }
-            const bool small = mod >= 2 && mod <= 256, big = mod > 256;
-            const uint32_t mu = is_coef ? bd_mu : (small ? sc.mutab[mod] : 0u);
-            const uint32_t r16 = is_coef ? bd_r16 : (small ? sc.r16tab[mod] : 0u);
-            // ---- consume it, most significant bits first, through the single call site of the cursor
-            uint32_t sign = 0, r = 0;
-            bool want_sign = is_coef;
-            int rem = width + (is_coef ? 1 : 0);
-            while (rem > 0) {
-                const int mask = big ? 15 : 31;
-                const int take = want_sign ? 1 : ((rem & mask) ? (rem & mask) : mask + 1);
-                const uint32_t c = get(take);
-                rem -= take;
-                if (want_sign) { sign = c; want_sign = false; }
-                else if (mod == 0) r = c;
-                else if (mod != 1) {
-                    const uint32_t x = small ? (r * r16 + (c >> 16)) * r16 + (c & 0xFFFFu) : ((r << take) | c);
-                    uint32_t t = x - __umulhi(x, mu) * mod;
-                    t = t >= mod ? t - mod : t;
-                    r = t >= mod ? t - mod : t;
-                }
-            }
-            // ---- act on it
-            if (f < wt) {
+            const bool is_idx = f < wt, is_coef = f >= wt && f < 2 * wt;
+            ensure(f == 0 ? LOGD : (is_idx ? dp.idx_bits : (is_coef ? 1 + dp.mag_bits : dp.pad_bits)));   // the one call site
+            if (is_idx) {
+                // ---- one position of the index set
                 uint32_t selw, word, pos;
                 if (f == 0) {
+                    const uint32_t r = take(LOGD);
                     selw = r >> 5;
                     pos = r & 31;
                     word = sc.bmap[selw * P];
                 } else {
-                    // r-th (0-based) still-unused position in ascending order
-                    uint32_t k = r;
+                    const uint32_t m = (uint32_t)(D - f);
+                    uint32_t k = 0;
+                    if (m == 1) rp += dp.idx_bits;
+                    else k = field_small(dp.idx_bits, m, sc.mutab[m], sc.r16tab[m]);
+                    // k-th (0-based) still-unused position in ascending order
                     bool found = false;
                     selw = 0; word = 0;
 #pragma unroll
                     for (uint32_t w = 0; w < 8; ++w) {
-                        uint32_t cand = sc.bmap[w * P];
-                        uint32_t c = __popc(cand);
+                        const uint32_t cand = sc.bmap[w * P];
+                        const uint32_t cnt = __popc(cand);
                         if (!found) {
-                            if (k < c) { found = true; selw = w; word = cand; }
-                            else k -= c;
+                            if (k < cnt) { found = true; selw = w; word = cand; }
+                            else k -= cnt;
                         }
                     }
-                    uint32_t wd = word, c;
+                    uint32_t wd = word, cnt;
                     pos = 0;
-                    c = __popc(wd & 0xFFFFu); if (k >= c) { k -= c; pos += 16; wd >>= 16; }
-                    c = __popc(wd & 0xFFu);   if (k >= c) { k -= c; pos += 8;  wd >>= 8; }
-                    c = __popc(wd & 0xFu);    if (k >= c) { k -= c; pos += 4;  wd >>= 4; }
-                    c = __popc(wd & 0x3u);    if (k >= c) { k -= c; pos += 2;  wd >>= 2; }
-                    c = wd & 1u;              if (k >= c) { pos += 1; }
+                    cnt = __popc(wd & 0xFFFFu); if (k >= cnt) { k -= cnt; pos += 16; wd >>= 16; }
+                    cnt = __popc(wd & 0xFFu);   if (k >= cnt) { k -= cnt; pos += 8;  wd >>= 8; }
+                    cnt = __popc(wd & 0xFu);    if (k >= cnt) { k -= cnt; pos += 4;  wd >>= 4; }
+                    cnt = __popc(wd & 0x3u);    if (k >= cnt) { k -= cnt; pos += 2;  wd >>= 2; }
+                    cnt = wd & 1u;              if (k >= cnt) { pos += 1; }
                 }
                 sc.bmap[selw * P] = word & ~(1u << pos);
-                sc.idxb[f * P] = (uint8_t)(selw * 32 + pos);
+                sc.idxs[f * sc.idx_stride] = (uint8_t)(selw * 32 + pos);
             } else if (is_coef) {
+                // ---- one coefficient
                 const int e = f - wt;
+                const uint32_t sign = take(1);
+                uint32_t r = 0;
+                if (bd == 1) {
+                    rp += dp.mag_bits;
+                } else if (bd <= 256) {
+                    r = field_small(dp.mag_bits, bd, bd_mu, bd_r16);
+                } else {
+                    int rem = dp.mag_bits;
+                    while (rem > 0) {
+                        const int n = (rem & 15) ? (rem & 15) : 16;
+                        r = barrett_small((r << n) | take(n), bd_mu, bd);
+                        rem -= n;
+                    }
+                }
                 const int mag = 1 + (int)r;
-                emit(poly, e, (int)sc.idxb[e * P], sign ? mag : -mag);
+                emit(poly, e, (int)sc.idxs[e * sc.idx_stride], sign ? mag : -mag);
+            } else {
+                rp += dp.pad_bits;
             }
         }
     }
