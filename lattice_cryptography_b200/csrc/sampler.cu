@@ -204,9 +204,10 @@ cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    // Grids of at most two 128-stream blocks per SM (small batches of long streams) run as 64-stream
-    // blocks instead, which spreads them over twice as many scheduler slots.
-    const bool narrow = (a.n + SBS - 1) / SBS <= (int64_t)num_sms * 2;
+    // Grids under two full waves (5 resident 128-stream blocks per SM) run as 64-stream blocks instead:
+    // the ALU-bound streams then spread evenly (e.g. 2^16 streams: 6.92 blocks per SM, at most 7) instead
+    // of leaving SMs with 3 blocks waiting for SMs with 4.
+    const bool narrow = (a.n + SBS - 1) / SBS < (int64_t)num_sms * 10;
     const int threads = narrow ? SBS / 2 : SBS;
     if (!a.idx_scratch || a.idx_stride < (a.n + threads - 1) / threads * threads) return cudaErrorInvalidValue;
     size_t smem = (size_t)(RING_WORDS + 8) * threads * 4 + 2 * 260 * 4;
