@@ -439,8 +439,14 @@ def engine_arm(a):
                        'l2': f'inputs {(sig.numel() * 2 + vk_ntt.numel() * 2 + d_ch.numel()) / 1e9:.2f} GB per pass '
                              f'>> 126 MB L2, no flush needed'},
             'roofline': {'bound': 'hbm', 'kernel': 'k_verify', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': None, 'peak_source': 'MEASURED_PEAKS.json hbm_gbs'
-                         if peaks else 'fallback', 'algorithmic_bytes_per_unit': unit_bytes,
+                         'frac': achieved / peak,
+                         # DRAM bytes per launch from the ncu --set full capture of this kernel
+                         # (profiles/prof_r1_verify.summary.txt: 2.0343 GB read + 4.9 MB written for 2^18
+                         # verifies = 7,779 B per verify), scaled to this launch's batch
+                         'traffic': 7779 * n if a.secpar == 128 else None,
+                         'algorithmic_bytes_per_launch': unit_bytes * n,
+                         'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback',
+                         'algorithmic_bytes_per_unit': unit_bytes,
                          'kernel_ms_per_launch': k_ms, 'kernel_share_of_step': v_ms / total_ms,
                          'sampler_ms_per_launch': s_ms / max(s_n, 1),
                          'note': 'k_verify is integer-issue bound by design (see DESIGN.md); HBM fraction is the '
@@ -454,7 +460,7 @@ def engine_arm(a):
         }
         # integer-pipe view of the same kernel: thread-instructions per verify from the ncu instruction
         # count of this build (profiles/README.md), against 148 SM x 64 lanes x max clock per pipe
-        instr_per_unit = 32 * 3718            # smsp__inst_executed.sum / verifies, k_verify, secpar 128
+        instr_per_unit = 32 * 3711            # smsp__inst_executed.sum / verifies, k_verify, secpar 128 (profiles/)
         pipe_peak = 148 * 64 * (clk['sm_max_mhz'] or 1965.0) * 1e6 if clk else 148 * 64 * 1965e6
         line['roofline']['int_pipe'] = {
             'thread_instr_per_unit': instr_per_unit, 'fma_pipe_share': 0.54,

@@ -402,3 +402,31 @@ def test_lm_big_batch_vs_c_oracle(engines, golden, secpar, n):
         assert np.array_equal(skl, sk_coef[i, 0]) and np.array_equal(skr, sk_coef[i, 1])
         assert np.array_equal(vkl, vk_coef[i, 0]) and np.array_equal(vkr, vk_coef[i, 1])
         assert np.array_equal(c_oracle.lm_sign(p, skl, skr, chmsgs[i]), sig[i])
+
+
+# ------------------------------------------------------------------------------------------- error contract of the ABI
+def test_abi_error_paths():
+    from lattice_cryptography_b200 import Engine, LcbError, _ffi, make_scheme
+    e = Engine(128, 11777, D, 13)
+    sch = scheme(128)
+    try:
+        with pytest.raises(LcbError) as err:            # row-vector products need key_ch first
+            e.lm_verify(sch, np.zeros((1, 2, D), np.uint16), ['m'], np.zeros((1, 13, D), np.int16), 945, 256)
+        assert err.value.status == _ffi.LCB_ERR_NO_KEY_CH
+        with pytest.raises(LcbError) as err:
+            e.lm_keygen(sch, ['0' * 128])
+        assert err.value.status == _ffi.LCB_ERR_NO_KEY_CH
+        # samplers and transforms do not need key_ch
+        dense, _ = e.hash2polyvec('S', ['x'], 5, 7, 2)
+        assert (dense != 0).sum(axis=-1).tolist() == [[7, 7]] and int(np.abs(dense).max()) <= 5
+        for bad in (dict(bd=0, wt=1), dict(bd=1, wt=0), dict(bd=1, wt=257), dict(bd=40000, wt=1)):
+            with pytest.raises(LcbError) as err:
+                e.hash2polyvec('S', ['x'], bad['bd'], bad['wt'], 1)
+            assert err.value.status == _ffi.LCB_ERR_INVALID
+        with pytest.raises(LcbError) as err:            # non-monomial aggregation coefficients are rejected
+            e.agg_coefs(make_scheme(ag_wt=2), 'msg', 0, 4)
+        assert err.value.status == _ffi.LCB_ERR_INVALID
+        with pytest.raises(ValueError):                 # non-contiguous host buffers are refused by the shim
+            e.ntt_fwd(np.zeros((4, 2 * D), np.int16)[:, ::2])
+    finally:
+        e.close()
