@@ -20,6 +20,7 @@
  *                      psi = least primitive 2d-th root of unity mod q (the reference's `rou`)
  *   pairs            : int16_t[wt][2] = (index, coefficient) in sampler DRAW ORDER
  *   ragged bytes     : uint8_t blob + int64_t off[n+1]; item i is blob[off[i] .. off[i+1])
+ * Caller-owned DEVICE buffers of 16-bit data must be 16-byte aligned (LCB_ERR_CUDA, "misaligned address", otherwise).
  */
 #ifndef LCB200_H
 #define LCB200_H
@@ -89,6 +90,9 @@ int lcb_hash2polyvec_batch(lcb_ctx* ctx, const char* salt, const uint8_t* msgs, 
 int lcb_ntt_fwd_batch(lcb_ctx* ctx, const int16_t* coef, int64_t npoly, uint16_t* ntt);
 int lcb_ntt_inv_batch(lcb_ctx* ctx, const uint16_t* ntt, int64_t npoly, int16_t* coef);
 int lcb_poly_mul_batch(lcb_ctx* ctx, const int16_t* a, const int16_t* b, int64_t npoly, int16_t* out);
+/* Polynomial.ntt_representation exactly as lattice_algebra stores it (parity level L3): the 2d-point
+ * cyclic transform of the zero-padded coefficients, natural order, centred: rep[k] = a(rou^k), int16[npoly][2d]. */
+int lcb_ntt_reference_repr_batch(lcb_ctx* ctx, const int16_t* coef, int64_t npoly, int16_t* rep);
 
 /* make_one_key / keygen_core (lm_one_time_sigs.py:64-97,126-138; adaptor_sigs.py:104-137).
  * seeds: ragged ASCII bitstrings.  Any output may be NULL.

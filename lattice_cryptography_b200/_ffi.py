@@ -56,6 +56,7 @@ PROTOTYPES = {
     'lcb_ntt_fwd_batch': (c_int, [c_void_p, _P, c_int64, _P]),
     'lcb_ntt_inv_batch': (c_int, [c_void_p, _P, c_int64, _P]),
     'lcb_poly_mul_batch': (c_int, [c_void_p, _P, _P, c_int64, _P]),
+    'lcb_ntt_reference_repr_batch': (c_int, [c_void_p, _P, c_int64, _P]),
     'lcb_lm_keygen_batch': (c_int, [c_void_p, POINTER(LcbScheme), _P, _P, c_int64, _P, _P, _P, _P]),
     'lcb_challenge_batch': (c_int, [c_void_p, POINTER(LcbScheme), _P, _P, c_int64, _P]),
     'lcb_lm_sign_batch': (c_int, [c_void_p, POINTER(LcbScheme), _P, _P, _P, c_int64, _P]),

@@ -149,10 +149,15 @@ class Staging {
         if (e == cudaSuccess) owned_.push_back(*out);
         return e;
     }
+    // polynomial data (16-bit elements) is moved with 128-bit loads / cp.async: caller-owned DEVICE
+    // buffers must be 16-byte aligned (staged host buffers always are)
+    template <typename T>
+    static bool misaligned(const T* p) { return sizeof(T) == 2 && (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
     template <typename T>
     cudaError_t in(const T** dev, const T* p, size_t count) {
         *dev = p;
-        if (p == nullptr || count == 0 || on_device(p)) return cudaSuccess;
+        if (p == nullptr || count == 0) return cudaSuccess;
+        if (on_device(p)) return misaligned(p) ? cudaErrorMisalignedAddress : cudaSuccess;
         void* d = nullptr;
         cudaError_t e = alloc(&d, count * sizeof(T));
         if (e != cudaSuccess) return e;
@@ -163,7 +168,8 @@ class Staging {
     template <typename T>
     cudaError_t out(T** dev, T* p, size_t count) {
         *dev = p;
-        if (p == nullptr || count == 0 || on_device(p)) return cudaSuccess;
+        if (p == nullptr || count == 0) return cudaSuccess;
+        if (on_device(p)) return misaligned(p) ? cudaErrorMisalignedAddress : cudaSuccess;
         void* d = nullptr;
         cudaError_t e = alloc(&d, count * sizeof(T));
         if (e != cudaSuccess) return e;
@@ -530,6 +536,19 @@ int lcb_ntt_fwd_batch(lcb_ctx* c, const int16_t* coef, int64_t npoly, uint16_t* 
     CK(c, sg.in(&d_in, coef, (size_t)npoly * D));
     CK(c, sg.out(&d_out, ntt, (size_t)npoly * D));
     CK(c, timed(c, K_NTT_FWD, [&] { return launch_ntt_fwd(c->ring, d_in, npoly, d_out, c->stream); }));
+    CK(c, sg.finish());
+    return LCB_OK;
+}
+
+int lcb_ntt_reference_repr_batch(lcb_ctx* c, const int16_t* coef, int64_t npoly, int16_t* rep) {
+    if (!c || !coef || !rep || npoly < 0) return LCB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    Staging sg(c);
+    const int16_t* d_in;
+    int16_t* d_out;
+    CK(c, sg.in(&d_in, coef, (size_t)npoly * D));
+    CK(c, sg.out(&d_out, rep, (size_t)npoly * 2 * D));
+    CK(c, timed(c, K_NTT_FWD, [&] { return launch_ntt_ref_repr(c->ring, d_in, npoly, d_out, c->stream); }));
     CK(c, sg.finish());
     return LCB_OK;
 }

@@ -122,6 +122,42 @@ __global__ void __launch_bounds__(RBS) k_ntt_fwd(ModQ m, StageConst sc, const Nt
     }
 }
 
+// The reference's own storage format (parity level L3): Polynomial.ntt_representation is the 2d-point
+// CYCLIC transform of the zero-padded coefficient list, natural order, centred: rep[k] = a(zeta^k).
+// Odd k = 2i+1 are the negacyclic slots (slot bitrev8(i)); even k = 2m are a(zeta^(2m)), i.e. the
+// negacyclic transform of the twisted polynomial c_j * zeta^(-j), slot bitrev8(m).
+__global__ void __launch_bounds__(RBS) k_ntt_ref_repr(ModQ m, StageConst sc, const NttTables* __restrict__ tab,
+                                                      const int16_t* __restrict__ coef, int64_t npoly,
+                                                      int16_t* __restrict__ out) {
+    __shared__ __align__(16) uint32_t xbuf[(RBS / 32) * XWARP];
+    const HalfWarp h = half_warp(xbuf);
+    LaneTw tw;
+    load_lane_tw(tw, tab->w, tab->ws, h.lane);
+    for (int64_t base = (int64_t)blockIdx.x * HWB; base < npoly; base += (int64_t)gridDim.x * HWB) {
+        const int64_t raw = base + h.slot;
+        const bool live = raw < npoly;
+        const int64_t item = live ? raw : npoly - 1;
+        uint32_t odd[EPT], even[EPT];
+        load_coef_a(odd, coef + item * D, h.lane, m.cq);
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            const int idx = h.lane + 16 * j;                          // coefficient index of register j (layout A)
+            even[j] = mulmod_full(barrett_full(odd[j], m), tab->pw[(512 - idx) & 511], m) + m.cq;
+        }
+        ntt_fwd_256(odd, m, sc, tw, h.xb, h.lane);
+        ntt_fwd_256(even, m, sc, tw, h.xb, h.lane);
+        if (live) {
+            int16_t* o = out + item * 2 * D;
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) {
+                const uint32_t i = __brev((uint32_t)(16 * h.lane + k)) >> 24;   // slot p -> exponent index
+                o[2 * i + 1] = (int16_t)center(barrett_full(odd[k], m), m);
+                o[2 * i] = (int16_t)center(barrett_full(even[k], m), m);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(RBS) k_ntt_inv(ModQ m, StageConst sc, const NttTables* __restrict__ tab,
                                                  const uint16_t* __restrict__ in, int64_t npoly,
                                                  int16_t* __restrict__ coef) {
@@ -561,6 +597,13 @@ cudaError_t launch_ntt_fwd(const RingCtx& c, const int16_t* coef, int64_t npoly,
     if (npoly <= 0) return cudaSuccess;
     unsigned grid = persistent_grid(npoly, HWB, c.num_sms, resident_blocks(k_ntt_fwd, RBS, 0));
     k_ntt_fwd<<<grid, RBS, 0, st>>>(c.m, c.sc, c.tab, coef, npoly, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ntt_ref_repr(const RingCtx& c, const int16_t* coef, int64_t npoly, int16_t* out, cudaStream_t st) {
+    if (npoly <= 0) return cudaSuccess;
+    unsigned grid = persistent_grid(npoly, HWB, c.num_sms, resident_blocks(k_ntt_ref_repr, RBS, 0));
+    k_ntt_ref_repr<<<grid, RBS, 0, st>>>(c.m, c.sc, c.tab, coef, npoly, out);
     return cudaGetLastError();
 }
 

@@ -165,6 +165,13 @@ class Engine(object):
         self._ck(self._lib.lcb_ntt_inv_batch(self._ctx, _addr(ntt), npoly, _addr(out)))
         return out
 
+    def ntt_reference_repr(self, coef, device: bool = False):
+        """lattice_algebra's Polynomial.ntt_representation: int16[..., 2d], rep[k] = a(rou^k), centred."""
+        npoly = int(np.prod(coef.shape[:-1]))
+        out = self._out(tuple(coef.shape[:-1]) + (2 * D,), np.int16, device)
+        self._ck(self._lib.lcb_ntt_reference_repr_batch(self._ctx, _addr(coef), npoly, _addr(out)))
+        return out
+
     def poly_mul(self, a, b, device: bool = False):
         npoly = int(np.prod(a.shape[:-1]))
         out = self._out(tuple(a.shape), np.int16, device)

@@ -12,7 +12,8 @@ no CPU arithmetic path).  `const_time_flag` is accepted and kept but has no effe
 have no secret-dependent branches or addresses except the sampler's position select, exactly
 where the reference's own decoder indexes a Python list.
 
-Not provided: the reference's raw length-2d `ntt_representation` lists.
+`Polynomial.ntt_representation` returns the reference's raw length-2d list (2d-point cyclic transform,
+parity level L3) computed on demand; it is read-only (the engine's own storage is the d-point negacyclic form).
 """
 from math import ceil, isqrt, log2
 from secrets import token_hex
@@ -142,6 +143,12 @@ class Polynomial(object):
         if self._ntt is None:
             self._ntt = engine_for(self.lp).ntt_fwd(np.ascontiguousarray(self._coef[None]))[0]
         return self._ntt
+
+    @property
+    def ntt_representation(self) -> List[int]:
+        """The reference's own storage (parity level L3): 2d-point cyclic transform of the zero-padded
+        coefficient list, natural order, centred residues - computed on the GPU on demand."""
+        return engine_for(self.lp).ntt_reference_repr(np.ascontiguousarray(self.coef[None]))[0].tolist()
 
     def get_coef_rep(self) -> Tuple[Dict[int, int], int, int]:
         c = self.coef

@@ -145,6 +145,27 @@ def test_ntt_roundtrip_and_product(engines, secpar):
         assert int(fx[p_]) == pow(psi, 2 * br + 1, q)
 
 
+@pytest.mark.parametrize('secpar', [128, 256])
+def test_reference_ntt_representation_l3(engines, golden, secpar):
+    """Parity level L3: the reference's own storage format, Polynomial.ntt_representation (2d-point cyclic
+    transform of the zero-padded coefficients, centred, natural order), against the restated lattice_algebra."""
+    import lattice_algebra as la
+    import schemes
+    arrays, _ = golden
+    e = engines[secpar]
+    p = SHIPPED[secpar]
+    lp = schemes.lattice_parameters(p['q'], D, p['l'])
+    rng = np.random.default_rng(11)
+    h = (p['q'] - 1) // 2
+    polys = np.concatenate([arrays[f's{secpar}_lm0_sig'][:3], arrays[f's{secpar}_lm0_vkL'][None],
+                            rng.integers(-h, h + 1, (3, D)).astype(np.int16), np.zeros((1, D), np.int16)])
+    rep = e.ntt_reference_repr(np.ascontiguousarray(polys))
+    assert rep.shape == (polys.shape[0], 2 * D)
+    for row, want in zip(polys, rep):
+        ref = la.Polynomial(lp=lp, coefs={i: int(v) for i, v in enumerate(row) if v})
+        assert want.tolist() == ref.ntt_representation
+
+
 def test_ntt_any_int16_input(engines):
     e = engines[128]
     q = 11777
