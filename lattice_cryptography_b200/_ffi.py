@@ -10,7 +10,7 @@ from ctypes import (POINTER, Structure, c_char, c_char_p, c_int, c_int16, c_int3
                     c_void_p)
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, 'liblcb200.so')
+LIB_PATH = os.environ.get('LCB200_LIB') or os.path.join(_PKG_DIR, 'liblcb200.so')
 LCB_SALT_MAX = 32
 
 LCB_OK = 0

@@ -14,6 +14,7 @@
 // coefficient representations (parity level L1) with half the work.
 #pragma once
 #include <cstdint>
+
 #include <cuda_runtime.h>
 
 namespace lcb {
@@ -29,7 +30,9 @@ constexpr int XWARP = 2 * XHALF;  // words per warp
 // Modulus constants; passed BY VALUE as a kernel parameter so they live in the constant bank.
 struct ModQ {
     uint32_t zero;        // always 0, but opaque to the compiler: turns `a + b` into a 3-input IADD3 (ALU pipe)
-                          // where ptxas would otherwise pick IMAD.IADD and load the FMA-heavy pipe further
+                          // where ptxas would otherwise pick IMAD.IADD and load the FMA-heavy pipe further.
+                          // Measured on k_verify (2^20 verifies): 5.46 ms with it in stages 1-4 and 5-8,
+                          // 5.60 / 5.61 ms with it in only one group, 5.74 ms without.
     uint32_t q, negq;
     uint32_t barrett;     // floor((2^32-1)/q)
     uint32_t cq;          // least multiple of q >= 32768: makes any int16 input non-negative

@@ -302,6 +302,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+template <bool CHECK_WT>   // weight test compiled out when wt >= d (every shipped parameter set: vf_wt = d)
 __global__ void __launch_bounds__(RBS, 4) k_verify(ModQ m, StageConst sc, const NttTables* __restrict__ tab,
                                                 const uint32_t* __restrict__ a_hat_g, int l,
                                                 const int16_t* __restrict__ vec_coef,
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(RBS, 4) k_verify(ModQ m, StageConst sc, const 
     unsigned char* stage = stage_base + h.slot * STAGE_HALF_BYTES;
     LaneTw tw;
     load_lane_tw(tw, tab->w, tab->ws, h.lane);
-    const bool check_wt = wt < D;
+    constexpr bool check_wt = CHECK_WT;
 
     const int64_t first = (int64_t)blockIdx.x * HWB, stride = (int64_t)gridDim.x * HWB;
     const int64_t trips = first < n ? (n - first + stride - 1) / stride : 0;   // uniform over the block
@@ -646,11 +647,12 @@ cudaError_t launch_verify(const RingCtx& c, const int16_t* vec_coef, const uint1
                           uint8_t* verdict, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     size_t smem = verify_smem(c.l);
-    cudaError_t e = allow_smem(k_verify, smem);
+    auto kern = wt < D ? k_verify<true> : k_verify<false>;
+    cudaError_t e = allow_smem(kern, smem);
     if (e != cudaSuccess) return e;
-    unsigned grid = persistent_grid(n, HWB, c.num_sms, resident_blocks(k_verify, RBS, smem));
-    k_verify<<<grid, RBS, smem, st>>>(c.m, c.sc, c.tab, c.a_hat, c.l, vec_coef, vk_ntt, ch_pairs, ch_wt, rhs_only,
-                                      extra_rhs, n, bd, wt, verdict);
+    unsigned grid = persistent_grid(n, HWB, c.num_sms, resident_blocks(kern, RBS, smem));
+    kern<<<grid, RBS, smem, st>>>(c.m, c.sc, c.tab, c.a_hat, c.l, vec_coef, vk_ntt, ch_pairs, ch_wt, rhs_only, extra_rhs,
+                                  n, bd, wt, verdict);
     return cudaGetLastError();
 }
 
