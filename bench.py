@@ -93,7 +93,11 @@ class ClockSampler(object):
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            try:        # by UUID, so that CUDA_VISIBLE_DEVICES remapping cannot point NVML at another GPU
+                import torch
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + str(torch.cuda.get_device_properties(device).uuid)).encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
             self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception:
             return
@@ -228,7 +232,7 @@ def secondary_bklm(a, rank, local, world, torch, np, dist):
     chm = [k + ', ' + m for k, m in zip(ident[start:start + count], msgs[start:start + count])]
     from lattice_cryptography_b200 import ragged
     cb, co = ragged(chm)
-    d_chm = (torch.from_numpy(cb).to(dev), torch.from_numpy(co).to(dev))
+    d_chm = (torch.from_numpy(cb.copy()).to(dev), torch.from_numpy(co).to(dev))
     _, sk_ntt, vk_ntt, _ = eng.lm_keygen(sch, seeds, want_sk_coef=False, want_vk_coef=False, device=True)
     sigs = eng.lm_sign(sch, sk_ntt, d_chm, device=True)
     res = {}

@@ -1,6 +1,7 @@
 // sampler_device.cuh — one SHAKE256 stream per thread, squeeze fused with lattice_algebra's
-// decode2polycoefs (index set + signed bounded coefficients).  Shared by k_sampler (sampler.cu) and
-// by k_verify (ring.cu), whose half-warps hash the challenges of their own upcoming signatures.
+// decode2polycoefs (index set + signed bounded coefficients).  Device-side building block of k_sampler
+// (sampler.cu); kept in a header so that other kernels can embed a stream (an experiment that hashed the
+// challenges inside k_verify was measured 15 % slower than two kernels and dropped).
 //
 // Per-thread scratch lives in shared-memory COLUMNS: element w of a thread's column is base[w*pitch]
 // (pitch = threads sharing the region), so a warp walking its streams in lock-step never conflicts.

@@ -271,7 +271,7 @@ def test_device_buffers_and_empty_batches(engines, golden):
     assert sk_ntt.is_cuda
     from lattice_cryptography_b200 import ragged
     blob, off = ragged([c['chmsg'] for c in cases])
-    dmsg = (torch.from_numpy(blob).cuda(), torch.from_numpy(off).cuda())
+    dmsg = (torch.from_numpy(blob.copy()).cuda(), torch.from_numpy(off).cuda())
     sig = e.lm_sign(sch, sk_ntt, dmsg, device=True)
     verdict = e.lm_verify(sch, vk_ntt, dmsg, sig, 945, 256, device=True)
     e.synchronize()
@@ -449,5 +449,27 @@ def test_abi_error_paths():
         assert err.value.status == _ffi.LCB_ERR_INVALID
         with pytest.raises(ValueError):                 # non-contiguous host buffers are refused by the shim
             e.ntt_fwd(np.zeros((4, 2 * D), np.int16)[:, ::2])
+    finally:
+        e.close()
+
+
+@pytest.mark.parametrize('secpar', [1, 7, 24, 64, 200, 384, 512])
+def test_sampler_field_widths_vs_c_oracle(secpar):
+    """The decoder's fields are (8 + secpar) and (ceil(log2 bd) + 1 + secpar) bits wide: exercise widths from
+    9 to 528 bits (window refills at every alignment), all three modulus paths (bd = 1, bd <= 256, bd > 256)
+    and weights from 1 to 256, against the bit-by-bit C oracle."""
+    import c_oracle
+    from lattice_cryptography_b200 import Engine
+    e = Engine(secpar, 11777, D, 2)
+    try:
+        rng = np.random.default_rng(secpar)
+        cases = [(1, 1), (1, 256), (2, 3), (45, 256), (255, 17), (256, 64), (257, 5), (5888, 256), (5000, 31)]
+        for bd, wt in cases:
+            msgs = [bytes(rng.integers(0, 256, int(n), dtype=np.uint8)) for n in (0, 1, 135, 136, 137, 300)]
+            dense, pairs = e.hash2polyvec('S' * (secpar % 9), msgs, bd, wt, 2, want_pairs=True)
+            for i, msg in enumerate(msgs):
+                od, op = c_oracle.hash2polyvec(secpar, D, 'S' * (secpar % 9), msg, bd, wt, 2)
+                assert np.array_equal(pairs[i], op), (secpar, bd, wt, i)
+                assert np.array_equal(dense[i], od), (secpar, bd, wt, i)
     finally:
         e.close()
