@@ -351,6 +351,12 @@ int lcb_ctx_create(lcb_ctx** out, int device, int secpar, int q, int d, int l) {
         t.iws[k] = shoup(iw, uq);
         t.oddexp[k] = (uint16_t)(2 * bitrev8(k) + 1);
     }
+    for (uint32_t k = 0; k < 256; ++k) {      // FP32-assisted forward twiddles (lcb_device.cuh, StageConstF)
+        const float wq = (float)((double)t.w[k] / (double)uq);
+        t.f_wq[k] = wq;
+        t.f_cst[k] = (float)(12582912.0 - 8388608.0 * (double)wq);
+        t.f_kw[k] = (uint32_t)((uint64_t)(0x4B400000u + 2u) * uq - (uint64_t)FP_BIAS * t.w[k]);
+    }
     for (uint32_t e2 = 0; e2 < 512; ++e2) {
         t.pw[e2] = (uint32_t)powmod(psi, e2, uq);
         t.pws[e2] = shoup(t.pw[e2], uq);
@@ -365,6 +371,10 @@ int lcb_ctx_create(lcb_ctx** out, int device, int secpar, int q, int d, int l) {
     m.half = (uq - 1) / 2;
     m.dinv = (uint32_t)powmod((uint32_t)d, uq - 2, uq);
     m.dinv_s = shoup(m.dinv, uq);
+    m.q4 = 4 * uq;
+    m.in_off = m.cq + FP_BIAS;
+    m.in_off_q4 = m.in_off + m.q4;
+    m.bias_mod_q = FP_BIAS % uq;
     m.z1c = (int32_t)t.w[1] > (int32_t)m.half ? (int32_t)t.w[1] - (int32_t)uq : (int32_t)t.w[1];
     m.k1 = (uint32_t)((((1ull << 30) + (1ull << 15) + uq - 1) / uq) * uq);
     for (int k = 0; k < 16; ++k) {
@@ -372,6 +382,10 @@ int lcb_ctx_create(lcb_ctx** out, int device, int secpar, int q, int d, int l) {
         c->ring.sc.ws[k] = t.ws[k];
         c->ring.sc.iw[k] = t.iw[k];
         c->ring.sc.iws[k] = t.iws[k];
+        c->ring.scf.w[k] = t.w[k];
+        c->ring.scf.wq[k] = t.f_wq[k];
+        c->ring.scf.cst[k] = t.f_cst[k];
+        c->ring.scf.kw[k] = t.f_kw[k];
     }
     if ((e = cudaMalloc(&c->d_tab, sizeof(NttTables))) != cudaSuccess) return bail(e, "cudaMalloc tables");
     if ((e = cudaMemcpy(c->d_tab, &t, sizeof(NttTables), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy tables");

@@ -38,6 +38,7 @@ cudaError_t launch_agg_coefs(const SamplerArgs& a, cudaStream_t st);   // shared
 struct RingCtx {
     ModQ m;
     StageConst sc;
+    StageConstF scf;
     const NttTables* tab;      // device
     const uint32_t* a_hat;     // device, uint32[l][256]: NTT(key_ch), slot order
     int l;

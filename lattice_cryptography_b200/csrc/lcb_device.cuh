@@ -39,6 +39,10 @@ struct ModQ {
     uint32_t cq2;         // least multiple of q >= 65536 + 2q: bound for u16-derived lazy values
     uint32_t half;        // (q-1)/2
     uint32_t dinv, dinv_s;  // d^-1 mod q and its Shoup companion
+    uint32_t q4;          // 4q: positivity offset of the FP32-assisted butterflies
+    uint32_t in_off;      // cq + FP_BIAS: raw int16 coefficient -> biased non-negative lazy value
+    uint32_t in_off_q4;   // in_off + 4q
+    uint32_t bias_mod_q;  // FP_BIAS mod q
     int32_t z1c;          // zetas[1] (the stage-1 twiddle) as a centred residue, |z1c| < 2^15
     uint32_t k1;          // least multiple of q >= 2^30 + 2^15: offset of the reduction-free first stage
 };
@@ -53,8 +57,33 @@ struct LaneTw {
     uint32_t w[15], ws[15];
 };
 
+// ---- FP32-assisted butterflies (forward transform of k_verify) -----------------------------------
+// IMAD.HI issues at a quarter of the IMAD rate on sm_100 (tools/pipe_bench.cu: 30 vs 63 thread-instr/clk/SM),
+// so the quotient estimate of a twiddle multiplication is taken from the FP32 pipe instead, where an FFMA
+// is full rate and can issue beside the IMADs.  Lazy values r < 2^23 are carried BIASED, b = r + 0x4B000000:
+// the same 32 bits read as the float 2^23 + r, so no conversion instruction exists at all.
+//   qf  = fma(as_float(yb), w/q, 1.5*2^23 - 2^23*(w/q))        = 1.5*2^23 + round(y*w/q) (+-1.13)
+//   t   = yb*w + kw                                            kw = (0x4B400000 + 2)*q - 0x4B000000*w  (mod 2^32)
+//   T   = as_uint(qf)*(-q) + t  =  y*w - qhat*q + 2q           in (0.87 q, 3.13 q)
+// One FFMA + two IMAD per multiplication instead of IMAD.HI + two IMAD; butterflies add at most 4q per stage.
+constexpr uint32_t FP_BIAS = 0x4B000000u;
+
+struct StageConstF {            // warp-uniform stages 1..4, zeta index k = 1..15 (kernel-parameter constant bank)
+    uint32_t w[16];
+    float wq[16], cst[16];
+    uint32_t kw[16];
+};
+
+struct LaneTwF {                // per-lane stages 5..8, same indexing as LaneTw
+    uint32_t w[15];
+    float wq[15], cst[15];
+    uint32_t kw[15];
+};
+
 // Device-resident tables of one ctx.
 struct NttTables {
+    float f_wq[256], f_cst[256];   // FP32-assisted forward twiddles (see StageConstF)
+    uint32_t f_kw[256];
     uint32_t w[256], ws[256];      // zetas[k] = psi^bitrev8(k) and Shoup companions
     uint32_t iw[256], iws[256];    // zetas[k]^-1
     uint32_t pw[512], pws[512];    // psi^e, e in [0, 512): NTT image of monomials (BKLM)
@@ -206,6 +235,71 @@ __device__ __forceinline__ void ntt_fwd_256_raw(const int (&x)[EPT], uint32_t (&
             r[j] = r[j] + t + m.zero;
         }
     }
+}
+
+__device__ __forceinline__ void load_lane_tw_f(LaneTwF& t, const NttTables* __restrict__ tab, int lane) {
+    auto put = [&](int dst, int k) {
+        t.w[dst] = __ldg(tab->w + k);
+        t.wq[dst] = __ldg(tab->f_wq + k);
+        t.cst[dst] = __ldg(tab->f_cst + k);
+        t.kw[dst] = __ldg(tab->f_kw + k);
+    };
+    put(0, 16 + lane);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) put(1 + i, 32 + 2 * lane + i);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) put(3 + i, 64 + 4 * lane + i);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) put(7 + i, 128 + 8 * lane + i);
+}
+
+// yb biased (y < 2^22)  ->  y*w mod q + {0,1,2,3}q, in (0.87 q, 3.13 q), NOT biased
+__device__ __forceinline__ uint32_t fp_mul(uint32_t yb, uint32_t w, float wq, float cst, uint32_t kw, const ModQ& m) {
+    const float qf = __fmaf_rn(__uint_as_float(yb), wq, cst);
+    const uint32_t t = yb * w + kw;
+    return __float_as_uint(qf) * m.negq + t;
+}
+
+// Forward transform of RAW centred int16 coefficients with FP32-assisted butterflies.  Values stay biased
+// throughout (inputs x + cq < 2^17, +4q per stage: < 2^17 + 32 q < 2^21 < 2^23); outputs are UNBIASED lazy
+// values < 2^21 PLUS FP_BIAS in layout B (what ntt_fwd_256 would deliver, up to multiples of q, plus the bias).
+__device__ __forceinline__ void ntt_fwd_256_fp(const int (&x)[EPT], uint32_t (&r)[EPT], const ModQ& m,
+                                               const StageConstF& sc, const LaneTwF& tw, uint32_t* xb, int lane) {
+    // stage 1: only the multiplied operands are biased explicitly; the others take the input offset
+    // inside the butterfly's 3-input adds
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t t = fp_mul((uint32_t)x[j + 8] + m.in_off, sc.w[1], sc.wq[1], sc.cst[1], sc.kw[1], m);
+        r[j + 8] = (uint32_t)x[j] + m.in_off_q4 - t;
+        r[j] = (uint32_t)x[j] + m.in_off + t;
+    }
+#pragma unroll
+    for (int s = 2; s <= 4; ++s) {
+        const int len = 8 >> (s - 1);
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            if (j & len) continue;
+            const int k = (1 << (s - 1)) + (j >> (5 - s));
+            const uint32_t t = fp_mul(r[j + len], sc.w[k], sc.wq[k], sc.cst[k], sc.kw[k], m);
+            r[j + len] = r[j] + m.q4 - t;
+            r[j] = r[j] + t + m.zero;
+        }
+    }
+    xpose_a_to_b(r, xb, lane);
+#pragma unroll
+    for (int s = 5; s <= 8; ++s) {
+        const int len = 256 >> s;
+        const int base = (1 << (s - 5)) - 1;
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            if (j & len) continue;
+            const int k = base + (j >> (9 - s));
+            const uint32_t t = fp_mul(r[j + len], tw.w[k], tw.wq[k], tw.cst[k], tw.kw[k], m);
+            r[j + len] = r[j] + m.q4 - t;
+            r[j] = r[j] + t + m.zero;
+        }
+    }
+    // outputs stay BIASED (r + FP_BIAS): the caller's multiply-accumulate removes the bias once per slot
 }
 
 // ---- inverse, Gentleman-Sande, bit-reversed in (layout B) -> natural order out (layout A), UNSCALED

@@ -303,7 +303,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <bool CHECK_WT>   // weight test compiled out when wt >= d (every shipped parameter set: vf_wt = d)
-__global__ void __launch_bounds__(RBS, 4) k_verify(ModQ m, StageConst sc, const NttTables* __restrict__ tab,
+__global__ void __launch_bounds__(RBS, 3) k_verify(ModQ m, StageConst sc, StageConstF scf, const NttTables* __restrict__ tab,
                                                 const uint32_t* __restrict__ a_hat_g, int l,
                                                 const int16_t* __restrict__ vec_coef,
                                                 const uint16_t* __restrict__ vk_ntt,
@@ -319,7 +319,23 @@ __global__ void __launch_bounds__(RBS, 4) k_verify(ModQ m, StageConst sc, const 
     const HalfWarp h = half_warp(xbuf);
     unsigned char* stage = stage_base + h.slot * STAGE_HALF_BYTES;
     LaneTw tw;
-    load_lane_tw(tw, tab->w, tab->ws, h.lane);
+    load_lane_tw(tw, tab->w, tab->ws, h.lane);       // Shoup twiddles: challenge transform only
+    LaneTwF twf;
+    load_lane_tw_f(twf, tab, h.lane);                // FP32-assisted twiddles: the l signature transforms
+    // The FP32-assisted transform returns biased values (r + FP_BIAS); the row-vector product then carries
+    // FP_BIAS * sum_i a_hat[i][slot], removed once per slot before the comparison.
+    uint32_t corr[EPT];
+    {
+        uint32_t colsum[EPT];
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) colsum[k] = 0;
+        for (int i = 0; i < l; ++i) {
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) colsum[k] += a_hat[i * AROW + XROW * h.lane + k];
+        }
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) corr[k] = mulmod_full(barrett_full(colsum[k], m), m.bias_mod_q, m);
+    }
     constexpr bool check_wt = CHECK_WT;
 
     const int64_t first = (int64_t)blockIdx.x * HWB, stride = (int64_t)gridDim.x * HWB;
@@ -356,10 +372,11 @@ __global__ void __launch_bounds__(RBS, 4) k_verify(ModQ m, StageConst sc, const 
         for (int i = 0; i < l; ++i) {
             cp_async_wait<1>();
             __syncwarp();
-            const int16_t* sp = reinterpret_cast<const int16_t*>(stage + cur * (D * 2)) + h.lane;
+            const unsigned sp = (unsigned)__cvta_generic_to_shared(stage + cur * (D * 2) + 2 * h.lane);
             int pre[EPT];
 #pragma unroll
-            for (int j = 0; j < EPT; ++j) pre[j] = sp[16 * j];
+            for (int j = 0; j < EPT; ++j)      // sign-extending 16-bit shared load (plain C++ yields LDS.U16 + PRMT)
+                asm volatile("ld.shared.s16 %0, [%1];" : "=r"(pre[j]) : "r"(sp + 32 * j));
             __syncwarp();
             issue();                            // refill the buffer just drained with polynomial (+2)
             cur ^= 1u;
@@ -377,7 +394,7 @@ __global__ void __launch_bounds__(RBS, 4) k_verify(ModQ m, StageConst sc, const 
                 for (int o = 8; o >= 1; o >>= 1) nz += __shfl_xor_sync(0xFFFFFFFFu, nz, o);
                 bad |= nz > wt;
             }
-            ntt_fwd_256_raw(pre, r, m, sc, tw, h.xb, h.lane);
+            ntt_fwd_256_fp(pre, r, m, scf, twf, h.xb, h.lane);
             mac_row(acc, r, a_hat + i * AROW, h.lane);
         }
         bad |= hi > bd || lo < -bd;
@@ -401,7 +418,7 @@ __global__ void __launch_bounds__(RBS, 4) k_verify(ModQ m, StageConst sc, const 
         }
         bool eq = true;
 #pragma unroll
-        for (int k = 0; k < EPT; ++k) eq &= reduce64(acc[k], m) == barrett_full(rhs[k], m);
+        for (int k = 0; k < EPT; ++k) eq &= reduce64(acc[k], m) == barrett_full(rhs[k] + corr[k], m);
         const unsigned votes = __ballot_sync(0xFFFFFFFFu, eq && !bad);
         if (live && h.lane == 0) verdict[item] = (votes & h.mask) == h.mask ? 1 : 0;
     }
@@ -651,8 +668,8 @@ cudaError_t launch_verify(const RingCtx& c, const int16_t* vec_coef, const uint1
     cudaError_t e = allow_smem(kern, smem);
     if (e != cudaSuccess) return e;
     unsigned grid = persistent_grid(n, HWB, c.num_sms, resident_blocks(kern, RBS, smem));
-    kern<<<grid, RBS, smem, st>>>(c.m, c.sc, c.tab, c.a_hat, c.l, vec_coef, vk_ntt, ch_pairs, ch_wt, rhs_only, extra_rhs,
-                                  n, bd, wt, verdict);
+    kern<<<grid, RBS, smem, st>>>(c.m, c.sc, c.scf, c.tab, c.a_hat, c.l, vec_coef, vk_ntt, ch_pairs, ch_wt, rhs_only,
+                                  extra_rhs, n, bd, wt, verdict);
     return cudaGetLastError();
 }
 
