@@ -79,6 +79,24 @@ __device__ __forceinline__ void load_pairs_a(uint32_t (&r)[EPT], const int16_t* 
 // transposition buffer) so that the 128-bit reads of a quarter-warp fall in 8 distinct bank groups.
 constexpr int AROW = LANES * XROW;   // 320 words per row
 
+// same, but as raw signed coefficients (input of the FP32-assisted transform)
+__device__ __forceinline__ void load_pairs_raw(int (&x)[EPT], const int16_t* __restrict__ pairs, int wt, uint32_t* xb,
+                                               int lane) {
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) xb[XROW * j + lane] = 0;
+    __syncwarp();
+    const uint32_t* pp = reinterpret_cast<const uint32_t*>(pairs);
+    for (int e = lane; e < wt; e += LANES) {
+        uint32_t pr = __ldg(pp + e);
+        int idx = (int)(pr & 0xFFu);
+        xb[XROW * (idx >> 4) + (idx & 15)] = (uint32_t)(int)(int16_t)(pr >> 16);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) x[j] = (int)xb[XROW * j + lane];
+    __syncwarp();
+}
+
 __device__ __forceinline__ void copy_a_hat(uint32_t* dst, const uint32_t* __restrict__ src, int l) {
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
     for (int i = threadIdx.x; i < l * (D / 4); i += blockDim.x) {
@@ -318,10 +336,8 @@ __global__ void __launch_bounds__(RBS, 3) k_verify(ModQ m, StageConst sc, StageC
     copy_a_hat(a_hat, a_hat_g, l);
     const HalfWarp h = half_warp(xbuf);
     unsigned char* stage = stage_base + h.slot * STAGE_HALF_BYTES;
-    LaneTw tw;
-    load_lane_tw(tw, tab->w, tab->ws, h.lane);       // Shoup twiddles: challenge transform only
     LaneTwF twf;
-    load_lane_tw_f(twf, tab, h.lane);                // FP32-assisted twiddles: the l signature transforms
+    load_lane_tw_f(twf, tab, h.lane);                // FP32-assisted twiddles, in registers for the life of the kernel
     // The FP32-assisted transform returns biased values (r + FP_BIAS); the row-vector product then carries
     // FP_BIAS * sum_i a_hat[i][slot], removed once per slot before the comparison.
     uint32_t corr[EPT];
@@ -401,11 +417,12 @@ __global__ void __launch_bounds__(RBS, 3) k_verify(ModQ m, StageConst sc, StageC
         uint32_t rhs[EPT];
         if (vk_ntt) {
             uint32_t c[EPT], vl[EPT];
-            load_pairs_a(c, ch_pairs + item * ch_wt * 2, ch_wt, h.xb, h.lane, m.cq);
-            ntt_fwd_256(c, m, sc, tw, h.xb, h.lane);
+            int cx[EPT];
+            load_pairs_raw(cx, ch_pairs + item * ch_wt * 2, ch_wt, h.xb, h.lane);
+            ntt_fwd_256_fp(cx, c, m, scf, twf, h.xb, h.lane);
             load_u16x16(vl, vk_ntt + item * 2 * D + 16 * h.lane);
 #pragma unroll
-            for (int k = 0; k < EPT; ++k) acc[k] += (uint64_t)c[k] * (m.cq2 - vl[k]);
+            for (int k = 0; k < EPT; ++k) acc[k] += (uint64_t)(c[k] - FP_BIAS) * (m.cq2 - vl[k]);
             load_u16x16(rhs, vk_ntt + item * 2 * D + D + 16 * h.lane);
         } else {
             load_u16x16(rhs, rhs_only + item * D + 16 * h.lane);
