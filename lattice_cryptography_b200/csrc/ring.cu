@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(RBS) k_poly_mul(ModQ m, StageConst sc, const N
 
 // ------------------------------------------------------------------------------------------------
 // y = key_ch * v  (v: nvec coefficient-form vectors of l polynomials)
-__global__ void __launch_bounds__(RBS) k_matvec(ModQ m, StageConst sc, const NttTables* __restrict__ tab,
+__global__ void __launch_bounds__(RBS, 3) k_matvec(ModQ m, StageConst sc, StageConstF scf, const NttTables* __restrict__ tab,
                                                 const uint32_t* __restrict__ a_hat_g, int l,
                                                 const int16_t* __restrict__ vec_coef, int64_t nvec,
                                                 uint16_t* __restrict__ vec_ntt, uint16_t* __restrict__ y_ntt,
@@ -233,8 +233,8 @@ __global__ void __launch_bounds__(RBS) k_matvec(ModQ m, StageConst sc, const Ntt
     uint32_t* xbuf = smem + l * AROW;
     copy_a_hat(a_hat, a_hat_g, l);
     const HalfWarp h = half_warp(xbuf);
-    LaneTw tw;
-    load_lane_tw(tw, tab->w, tab->ws, h.lane);
+    LaneTwF twf;
+    load_lane_tw_f(twf, tab, h.lane);
     for (int64_t base = (int64_t)blockIdx.x * HWB; base < nvec; base += (int64_t)gridDim.x * HWB) {
         const int64_t raw = base + h.slot;
         const bool live = raw < nvec;
@@ -246,7 +246,9 @@ __global__ void __launch_bounds__(RBS) k_matvec(ModQ m, StageConst sc, const Ntt
             uint32_t r[EPT];
             int x[EPT];
             load_coef_raw(x, vec_coef + (item * l + i) * D, h.lane);
-            ntt_fwd_256_raw(x, r, m, sc, tw, h.xb, h.lane);
+            ntt_fwd_256_fp(x, r, m, scf, twf, h.xb, h.lane);
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) r[k] -= FP_BIAS;
             if (vec_ntt) {
 #pragma unroll
                 for (int k = 0; k < EPT; ++k) r[k] = barrett_full(r[k], m);
@@ -664,7 +666,7 @@ cudaError_t launch_matvec(const RingCtx& c, const int16_t* vec_coef, int64_t nve
     cudaError_t e = allow_smem(k_matvec, smem);
     if (e != cudaSuccess) return e;
     unsigned grid = persistent_grid(nvec, HWB, c.num_sms, resident_blocks(k_matvec, RBS, smem));
-    k_matvec<<<grid, RBS, smem, st>>>(c.m, c.sc, c.tab, c.a_hat, c.l, vec_coef, nvec, vec_ntt, y_ntt, y_coef);
+    k_matvec<<<grid, RBS, smem, st>>>(c.m, c.sc, c.scf, c.tab, c.a_hat, c.l, vec_coef, nvec, vec_ntt, y_ntt, y_coef);
     return cudaGetLastError();
 }
 
