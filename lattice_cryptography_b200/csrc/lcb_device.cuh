@@ -362,9 +362,11 @@ __device__ __forceinline__ void store_u16x16(uint16_t* __restrict__ p, const uin
 
 // ---- Keccak-f[1600] -----------------------------------------------------------------------------
 // State as 25 (lo, hi) pairs of 32-bit registers; written so that ptxas emits exactly the minimum:
-// per round 132 LOP3 (5-way column parities as two xor3, theta application, chi as one LOP3 each)
-// and 58 SHF (funnel shifts for rho and the theta rotation), no register moves.  Measured
-// 4.05 Gperm/s on B200 = the ALU-pipe issue limit (64 lanes/clk/SM) for 24 x 190 instructions.
+// per round 122 LOP3 (5-way column parities as two xor3; theta applied as a ^ C[x-1] ^ rotl(C[x+1],1)
+// in one LOP3 without forming D; chi as one LOP3 each) and 58 SHF (funnel shifts for rho and the
+// theta rotation), no register moves.  Measured 4.28 Gperm/s on B200 = the ALU-pipe issue limit
+// (64 lanes/clk/SM) for 24 x 180 instructions (tools/keccak_bench2.cu; moving rotations onto the FMA
+// pipe as IMAD.WIDE/IMAD.HI multiplies by 2^n was measured there too and loses).
 #define LCB_KECCAK_RC_INIT                                                                           \
     {0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,     \
      0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,     \
@@ -402,37 +404,35 @@ __device__ __forceinline__ void rotl64_pair(uint32_t lo, uint32_t hi, uint32_t& 
 }
 template <int I>
 struct KeccakRhoPi {
-    __device__ static __forceinline__ void run(const KeccakState& s, const uint32_t (&dlo)[5], const uint32_t (&dhi)[5],
-                                               KeccakState& b) {
+    // theta folded into the rotation input: a ^ C[x-1] ^ rotl(C[x+1], 1) is ONE LOP3, so D is never formed
+    __device__ static __forceinline__ void run(const KeccakState& s, const uint32_t (&clo)[5], const uint32_t (&chi)[5],
+                                               const uint32_t (&rlo)[5], const uint32_t (&rhi)[5], KeccakState& b) {
         constexpr int R[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
-        rotl64_pair<R[I]>(s.lo[I] ^ dlo[I % 5], s.hi[I] ^ dhi[I % 5], b.lo[keccak_pi(I)], b.hi[keccak_pi(I)]);
-        KeccakRhoPi<I + 1>::run(s, dlo, dhi, b);
+        constexpr int x = I % 5;
+        rotl64_pair<R[I]>(lop_xor3(s.lo[I], clo[(x + 4) % 5], rlo[(x + 1) % 5]),
+                          lop_xor3(s.hi[I], chi[(x + 4) % 5], rhi[(x + 1) % 5]), b.lo[keccak_pi(I)], b.hi[keccak_pi(I)]);
+        KeccakRhoPi<I + 1>::run(s, clo, chi, rlo, rhi, b);
     }
 };
 template <>
 struct KeccakRhoPi<25> {
     __device__ static __forceinline__ void run(const KeccakState&, const uint32_t (&)[5], const uint32_t (&)[5],
-                                               KeccakState&) {}
+                                               const uint32_t (&)[5], const uint32_t (&)[5], KeccakState&) {}
 };
 
 __device__ __forceinline__ void keccak_f1600(KeccakState& s, const uint64_t* __restrict__ rc) {
 #pragma unroll 2
     for (int round = 0; round < 24; ++round) {
-        uint32_t clo[5], chi[5], dlo[5], dhi[5];
+        uint32_t clo[5], chi[5], rlo[5], rhi[5];
 #pragma unroll
         for (int x = 0; x < 5; ++x) {
             clo[x] = lop_xor3(lop_xor3(s.lo[x], s.lo[x + 5], s.lo[x + 10]), s.lo[x + 15], s.lo[x + 20]);
             chi[x] = lop_xor3(lop_xor3(s.hi[x], s.hi[x + 5], s.hi[x + 10]), s.hi[x + 15], s.hi[x + 20]);
         }
 #pragma unroll
-        for (int x = 0; x < 5; ++x) {
-            uint32_t rl, rh;
-            rotl64_pair<1>(clo[(x + 1) % 5], chi[(x + 1) % 5], rl, rh);
-            dlo[x] = clo[(x + 4) % 5] ^ rl;
-            dhi[x] = chi[(x + 4) % 5] ^ rh;
-        }
+        for (int x = 0; x < 5; ++x) rotl64_pair<1>(clo[x], chi[x], rlo[x], rhi[x]);
         KeccakState b;
-        KeccakRhoPi<0>::run(s, dlo, dhi, b);
+        KeccakRhoPi<0>::run(s, clo, chi, rlo, rhi, b);
 #pragma unroll
         for (int y = 0; y < 5; ++y)
 #pragma unroll
