@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(SBS) k_shake256(const uint8_t* __restrict__ in
 
 // ------------------------------------------------------------------------------------------------
 // Fused SHAKE256 squeeze + decode2polycoefs (sampler_device.cuh), one stream per thread.
-// Shared memory per block: rate [34][SBS] u32, bmap [8][SBS] u32, two modulus tables, idxb [wt][SBS] u8.
+// Shared memory per block: ring [54][P] u32, bmap [8][P] u32, two modulus tables, the piece-weight table.
 template <int P>   // streams (threads) per block; compile-time so that column addressing is shifts, not multiplies
 __global__ void __launch_bounds__(P) k_sampler(SamplerArgs a) {
     extern __shared__ uint32_t smem[];
@@ -72,18 +72,20 @@ __global__ void __launch_bounds__(P) k_sampler(SamplerArgs a) {
     uint32_t* bmap = ring + RING_WORDS * P;      // [8][P]   (directly after the ring, see StreamCols)
     uint32_t* mutab = bmap + 8 * P;
     uint32_t* r16tab = mutab + 260;
+    uint8_t* wtab = reinterpret_cast<uint8_t*>(r16tab + 260);     // [257][WT_K]
 
     const int tid = threadIdx.x;
     const int64_t inst_raw = (int64_t)blockIdx.x * P + tid;
     const bool live = inst_raw < a.n;
     const int64_t inst = live ? inst_raw : a.n - 1;
     fill_mod_tables(mutab, r16tab);
+    fill_weight_table(wtab, a.wt, a.bd, max(2, (max(a.idx_bits, a.mag_bits) + 31) >> 5));
     __syncthreads();
 
     const InputView iv{reinterpret_cast<const uint32_t*>(a.salt), a.salt_len, a.msgs + a.off[inst],
                        a.off[inst + 1] - a.off[inst]};
     const DecodeParams dp{a.bd, a.wt, a.vec_len, a.idx_bits, a.mag_bits, a.pad_bits};
-    const StreamCols sc{ring + tid, bmap + tid, P, mutab, r16tab, a.idx_scratch + inst_raw, a.idx_stride};
+    const StreamCols sc{ring + tid, bmap + tid, P, mutab, r16tab, wtab, a.idx_scratch + inst_raw, a.idx_stride};
     int16_t* dense = a.out_dense ? a.out_dense + inst * a.dense_stride : nullptr;
     uint32_t* pairs = a.out_pairs ? reinterpret_cast<uint32_t*>(a.out_pairs) + inst * a.vec_len * (int64_t)a.wt : nullptr;
     const int wt = a.wt;
@@ -210,7 +212,7 @@ cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st) {
     const bool narrow = (a.n + SBS - 1) / SBS < (int64_t)num_sms * 10;
     const int threads = narrow ? SBS / 2 : SBS;
     if (!a.idx_scratch || a.idx_stride < (a.n + threads - 1) / threads * threads) return cudaErrorInvalidValue;
-    size_t smem = (size_t)(RING_WORDS + 8) * threads * 4 + 2 * 260 * 4;
+    size_t smem = (size_t)(RING_WORDS + 8) * threads * 4 + 2 * 260 * 4 + 260 * WT_K;
     auto kern = narrow ? k_sampler<SBS / 2> : k_sampler<SBS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

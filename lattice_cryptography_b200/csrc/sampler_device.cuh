@@ -70,6 +70,7 @@ struct StreamCols {
     int pitch;
     const uint32_t* mutab;     // [257] floor((2^32-1)/m)   (block-shared)
     const uint32_t* r16tab;    // [257] 2^16 mod m
+    const uint8_t* wtab;       // [257][WT_K] 2^(32k) mod m, rows filled by fill_weight_table
     uint8_t* idxs;             // global scratch, byte e of this stream at idxs[e * idx_stride]
     int64_t idx_stride;
 };
@@ -78,6 +79,20 @@ __device__ __forceinline__ void fill_mod_tables(uint32_t* mutab, uint32_t* r16ta
     for (int m = 1 + threadIdx.x; m <= 256; m += blockDim.x) {
         mutab[m] = 0xFFFFFFFFu / (uint32_t)m;
         r16tab[m] = 65536u % (uint32_t)m;
+    }
+}
+
+// Weights of the 32-bit pieces of a big-endian field modulo m <= 256: wtab[m][k] = 2^(32k) mod m.
+// Only the rows a sampler call can touch are filled: the index moduli D-wt+1 .. D-1 and bd.
+constexpr int WT_K = 20;          // pieces per row: MAX_FIELD_BITS / 32 + 1
+__device__ __forceinline__ void fill_weight_table(uint8_t* wtab, int wt, int bd, int pieces) {
+    const int m_lo = max(2, D - wt + 1), m_hi = D - 1;
+    for (int i = m_lo + (int)threadIdx.x; i <= m_hi + 1; i += blockDim.x) {
+        const uint32_t m = i <= m_hi ? (uint32_t)i : (uint32_t)bd;
+        if (m < 2 || m > 256) continue;
+        const uint32_t r16 = 65536u % m, r32 = (r16 * r16) % m;
+        uint32_t w = 1;
+        for (int k = 0; k < pieces; ++k) { wtab[m * WT_K + k] = (uint8_t)w; w = (w * r32) % m; }
     }
 }
 
@@ -94,9 +109,9 @@ __device__ __forceinline__ uint32_t barrett_small(uint32_t x, uint32_t mu, uint3
 // tops the window up by one 136-byte block whenever the field would not fit (the first call absorbs
 // every input block).  Inside a field the cursor is a pure funnel shift over two window words, so the
 // per-field code is straight-line and specialised:
-//   index field   : (8 + secpar) bits reduced mod (#unused positions) as one head piece + 32-bit pieces,
-//                   acc <- ((acc*r16 + c>>16)*r16 + (c&0xFFFF)) mod m with r16 = 2^16 mod m, then the
-//                   acc-th unused position is taken from a 256-bit bitmap (popcount search);
+//   index field   : (8 + secpar) bits reduced mod (#unused positions) as a weighted sum of 32-bit pieces
+//                   (weights 2^(32k) mod m from a block-shared table, 64-bit accumulator, one fold), then
+//                   the acc-th unused position is taken from a 256-bit bitmap (popcount search);
 //   coefficient   : sign bit, then magnitude 1 + (field mod bd) the same way (bd <= 256), or a 16-bit
 //                   Horner recurrence (larger bd, only key_ch), or nothing at all when bd == 1;
 //   pad bits      : skipped.
@@ -148,16 +163,30 @@ __device__ __forceinline__ void sample_stream(const DecodeParams& dp, const Inpu
         rp += n;
         return v;
     };
-    // value of the next `width` bits modulo m (2 <= m <= 256), most significant piece first
-    auto field_small = [&](int width, uint32_t m, uint32_t mu, uint32_t r16) -> uint32_t {
-        const int head = (width & 31) ? (width & 31) : 32;
-        uint32_t c = take(head);
-        uint32_t acc = barrett_small((c >> 16) * r16 + (c & 0xFFFFu), mu, m);
-        for (int left = width - head; left > 0; left -= 32) {
-            c = take(32);
-            acc = barrett_small((acc * r16 + (c >> 16)) * r16 + (c & 0xFFFFu), mu, m);
+    // Value of the next `width` bits modulo m (2 <= m <= 256).  The field is cut into 32-bit pieces
+    // aligned to its END (the most significant piece holds the `head` odd bits); their weighted sum
+    // sum_k piece_k * (2^(32k) mod m) < 2^45 is accumulated in 64 bits - independent multiply-adds
+    // on the FMA pipe instead of a serial reduce-per-piece chain on the ALU pipe - and folded once.
+    auto field_small = [&](int width, uint32_t m, uint32_t mu, uint32_t r16, const uint8_t* wrow) -> uint32_t {
+        const int np = (width + 31) >> 5;
+        const int head = width - 32 * (np - 1);
+        const uint32_t* rw = sc.ring + (rp >> 5) * P;
+        uint32_t c = __funnelshift_l(rw[P], rw[0], rp & 31) >> (32 - head);
+        uint64_t acc = (uint64_t)c * wrow[np - 1];
+        rp += head;
+        rw = sc.ring + (rp >> 5) * P;
+        const int sh = rp & 31;
+        uint32_t prev = rw[0];
+        for (int k = np - 2; k >= 0; --k) {
+            rw += P;
+            const uint32_t nxt = rw[0];
+            c = __funnelshift_l(nxt, prev, sh);
+            prev = nxt;
+            acc += (uint64_t)c * wrow[k];
         }
-        return acc;
+        rp += 32 * (np - 1);
+        const uint32_t lo = (uint32_t)acc, hi = (uint32_t)(acc >> 32);     // hi < 2^13
+        return barrett_small(hi * wrow[1] + (lo >> 16) * r16 + (lo & 0xFFFFu), mu, m);
     };
     const uint32_t bd = (uint32_t)dp.bd;
     const uint32_t bd_mu = 0xFFFFFFFFu / bd, bd_r16 = 65536u % bd;
@@ -180,7 +209,7 @@ __device__ __forceinline__ void sample_stream(const DecodeParams& dp, const Inpu
                     const uint32_t m = (uint32_t)(D - f);
                     uint32_t k = 0;
                     if (m == 1) rp += dp.idx_bits;
-                    else k = field_small(dp.idx_bits, m, sc.mutab[m], sc.r16tab[m]);
+                    else k = field_small(dp.idx_bits, m, sc.mutab[m], sc.r16tab[m], sc.wtab + m * WT_K);
                     // k-th (0-based) still-unused position in ascending order
                     bool found = false;
                     selw = 0; word = 0;
@@ -211,7 +240,7 @@ __device__ __forceinline__ void sample_stream(const DecodeParams& dp, const Inpu
                 if (bd == 1) {
                     rp += dp.mag_bits;
                 } else if (bd <= 256) {
-                    r = field_small(dp.mag_bits, bd, bd_mu, bd_r16);
+                    r = field_small(dp.mag_bits, bd, bd_mu, bd_r16, sc.wtab + bd * WT_K);
                 } else {
                     int rem = dp.mag_bits;
                     while (rem > 0) {
