@@ -117,6 +117,24 @@ int lcb_lm_verify_batch(lcb_ctx* ctx, const lcb_scheme* sch, const uint16_t* vk_
                         const int64_t* chmsg_off, const int16_t* sig, const uint16_t* st_ntt, int64_t n,
                         int bd, int wt, uint8_t* verdict);
 
+/* ---- Packed wire format.  The reference has no serialisation: keys print as memory
+ * addresses and signatures are live Python objects (one_time_keys.py:197-237), so this format is the
+ * engine's own and opt-in.  A polynomial is its 256 values v_i = (x_i + bias) mod 2^16, `bits` bits each,
+ * value i at bit offset i*bits, least significant bit first: 32*bits bytes per polynomial, polynomials
+ * back to back.  Signatures: x = centred coefficient, bias = vf_bd, bits = ceil(log2(2*vf_bd+1)) (11 at
+ * secpar 128, 13 at 256).  NTT-form keys: x = slot value, bias = 0, bits = ceil(log2 q) (14 / 16).
+ * `values` is int16 or uint16 [npoly][d]; packed buffers must be 4-byte aligned.
+ * in_range (nullable) uint8[npoly]: 1 when every value of the polynomial was representable. */
+int lcb_pack_batch(lcb_ctx* ctx, const void* values, int64_t npoly, int bits, int bias, uint8_t* packed,
+                   uint8_t* in_range);
+int lcb_unpack_batch(lcb_ctx* ctx, const uint8_t* packed, int64_t npoly, int bits, int bias, void* values);
+
+/* lcb_lm_verify_batch (verify, lm_one_time_sigs.py:173-191) on packed inputs: vk_packed uint8[n][2][32*vk_bits]
+ * (bias 0), sig_packed uint8[n][l][32*sig_bits] (bias sig_bias).  Same verdicts as unpacking first. */
+int lcb_lm_verify_packed_batch(lcb_ctx* ctx, const lcb_scheme* sch, const uint8_t* vk_packed, int vk_bits,
+                               const uint8_t* chmsg, const int64_t* chmsg_off, const uint8_t* sig_packed,
+                               int sig_bits, int sig_bias, int64_t n, int bd, int wt, uint8_t* verdict);
+
 /* make_agg_coefs (bklm_one_time_agg_sigs.py:78-81): coefficient i = H2P(ag_salt+str(first+i) || agmsg),
  * wt = ag_wt (1 supported), out_pairs int16[count][ag_wt][2]. */
 int lcb_bklm_agg_coefs(lcb_ctx* ctx, const lcb_scheme* sch, const uint8_t* agmsg, int64_t agmsg_len,

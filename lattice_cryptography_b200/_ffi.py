@@ -61,6 +61,10 @@ PROTOTYPES = {
     'lcb_challenge_batch': (c_int, [c_void_p, POINTER(LcbScheme), _P, _P, c_int64, _P]),
     'lcb_lm_sign_batch': (c_int, [c_void_p, POINTER(LcbScheme), _P, _P, _P, c_int64, _P]),
     'lcb_lm_verify_batch': (c_int, [c_void_p, POINTER(LcbScheme), _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
+    'lcb_pack_batch': (c_int, [c_void_p, _P, c_int64, c_int, c_int, _P, _P]),
+    'lcb_unpack_batch': (c_int, [c_void_p, _P, c_int64, c_int, c_int, _P]),
+    'lcb_lm_verify_packed_batch': (c_int, [c_void_p, POINTER(LcbScheme), _P, c_int, _P, _P, _P, c_int, c_int, c_int64,
+                                           c_int, c_int, _P]),
     'lcb_bklm_agg_coefs': (c_int, [c_void_p, POINTER(LcbScheme), _P, c_int64, c_int64, c_int64, _P]),
     'lcb_bklm_aggregate_partial': (c_int, [c_void_p, POINTER(LcbScheme), _P, _P, _P, c_int64, c_int64, c_int64, _P]),
     'lcb_bklm_aggregate_finish': (c_int, [c_void_p, _P, _P]),

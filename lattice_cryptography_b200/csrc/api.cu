@@ -54,10 +54,10 @@ int fail_cuda(lcb_ctx* c, cudaError_t e, const char* what) {
     } while (0)
 
 enum KernelId { K_SAMPLER = 0, K_SHAKE, K_NTT_FWD, K_NTT_INV, K_POLY_MUL, K_MATVEC, K_SIGN, K_VERIFY, K_ADDSUB,
-                K_AGG_COEFS, K_AGG_PARTIAL, K_AGG_FINISH, K_AGGV_PARTIAL, K_AGGV_FINISH, K_COUNT };
+                K_AGG_COEFS, K_AGG_PARTIAL, K_AGG_FINISH, K_AGGV_PARTIAL, K_AGGV_FINISH, K_PACK, K_UNPACK, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"sampler", "shake256", "ntt_fwd", "ntt_inv", "poly_mul", "matvec", "sign",
                                            "verify", "vec_addsub", "agg_coefs", "agg_partial", "agg_finish",
-                                           "aggv_partial", "aggv_finish"};
+                                           "aggv_partial", "aggv_finish", "pack", "unpack"};
 
 // Launch wrapper: counts the launch and, when profiling is on, brackets it with CUDA events on the
 // ctx stream (resolved lazily in lcb_profile_read).
@@ -723,6 +723,90 @@ int lcb_lm_verify_batch(lcb_ctx* c, const lcb_scheme* sch, const uint16_t* vk_nt
     if (st != LCB_OK) return st;
     CK(c, timed(c, K_VERIFY, [&] { return launch_verify(c->ring, d_sig, d_vk, d_pairs, sch->ch_wt, nullptr, d_st, n, bd > 32767 ? 32767 : bd, wt,
                         d_verdict, c->stream); }));
+    CK(c, sg.finish());
+    return LCB_OK;
+}
+
+// ---- wire format ----------------------------------------------------------------------
+int lcb_pack_batch(lcb_ctx* c, const void* values, int64_t npoly, int bits, int bias, uint8_t* packed,
+                   uint8_t* in_range) {
+    if (!c || !values || !packed || npoly < 0 || bits < 1 || bits > 16 || bias < 0 || bias > 65535) return LCB_ERR_INVALID;
+    if (npoly == 0) return LCB_OK;
+    CK(c, cudaSetDevice(c->device));
+    Staging sg(c);
+    const uint16_t* d_in;
+    uint8_t *d_out, *d_ok;
+    CK(c, sg.in(&d_in, static_cast<const uint16_t*>(values), (size_t)npoly * D));
+    CK(c, sg.out(&d_out, packed, (size_t)npoly * 32 * bits));
+    CK(c, sg.out(&d_ok, in_range, (size_t)npoly));
+    if (reinterpret_cast<uintptr_t>(d_out) & 3u) return fail(c, LCB_ERR_INVALID, "packed buffer must be 4-byte aligned");
+    CK(c, timed(c, K_PACK, [&] { return launch_pack(c->ring, d_in, npoly, bits, bias, d_out, d_ok, c->stream); }));
+    CK(c, sg.finish());
+    return LCB_OK;
+}
+
+int lcb_unpack_batch(lcb_ctx* c, const uint8_t* packed, int64_t npoly, int bits, int bias, void* values) {
+    if (!c || !values || !packed || npoly < 0 || bits < 1 || bits > 16 || bias < 0 || bias > 65535) return LCB_ERR_INVALID;
+    if (npoly == 0) return LCB_OK;
+    CK(c, cudaSetDevice(c->device));
+    Staging sg(c);
+    const uint8_t* d_in;
+    uint16_t* d_out;
+    CK(c, sg.in(&d_in, packed, (size_t)npoly * 32 * bits));
+    CK(c, sg.out(&d_out, static_cast<uint16_t*>(values), (size_t)npoly * D));
+    if (reinterpret_cast<uintptr_t>(d_in) & 3u) return fail(c, LCB_ERR_INVALID, "packed buffer must be 4-byte aligned");
+    CK(c, timed(c, K_UNPACK, [&] { return launch_unpack(c->ring, d_in, npoly, bits, bias, d_out, c->stream); }));
+    CK(c, sg.finish());
+    return LCB_OK;
+}
+
+// lcb_lm_verify_batch on packed verification keys and signatures.  The batch is processed in chunks
+// (unpack -> challenge sampler -> verify) so that the unpacked copies never exceed ~2 GB of scratch.
+int lcb_lm_verify_packed_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* vk_packed, int vk_bits,
+                               const uint8_t* chmsg, const int64_t* chmsg_off, const uint8_t* sig_packed, int sig_bits,
+                               int sig_bias, int64_t n, int bd, int wt, uint8_t* verdict) {
+    if (!c || !sch || !vk_packed || !chmsg_off || !sig_packed || !verdict || n < 0 || bd < 0 || wt < 0 ||
+        vk_bits < 1 || vk_bits > 16 || sig_bits < 1 || sig_bits > 16 || sig_bias < 0 || sig_bias > 32767)
+        return LCB_ERR_INVALID;
+    if (!c->has_key_ch) return fail(c, LCB_ERR_NO_KEY_CH, "lcb_lm_verify_packed_batch before lcb_set_key_ch");
+    if (n == 0) return LCB_OK;
+    CK(c, cudaSetDevice(c->device));
+    const int l = c->l;
+    int64_t total = 0;
+    CK(c, last_offset(c, chmsg, chmsg_off, n, &total));
+    Staging sg(c);
+    const uint8_t *d_vkp, *d_sigp, *d_msg;
+    const int64_t* d_off;
+    uint8_t* d_verdict;
+    CK(c, sg.in(&d_vkp, vk_packed, (size_t)n * 2 * 32 * vk_bits));
+    CK(c, sg.in(&d_msg, chmsg, (size_t)total));
+    CK(c, sg.in(&d_off, chmsg_off, (size_t)n + 1));
+    CK(c, sg.in(&d_sigp, sig_packed, (size_t)n * l * 32 * sig_bits));
+    CK(c, sg.out(&d_verdict, verdict, (size_t)n));
+    if ((reinterpret_cast<uintptr_t>(d_vkp) | reinterpret_cast<uintptr_t>(d_sigp)) & 3u)
+        return fail(c, LCB_ERR_INVALID, "packed buffers must be 4-byte aligned");
+    const int64_t chunk = n < (1 << 18) ? n : (1 << 18);
+    uint16_t* d_vk;
+    int16_t *d_sig, *d_pairs;
+    CK(c, sg.alloc((void**)&d_vk, (size_t)chunk * 2 * D * sizeof(uint16_t)));
+    CK(c, sg.alloc((void**)&d_sig, (size_t)chunk * l * D * sizeof(int16_t)));
+    CK(c, sg.alloc((void**)&d_pairs, (size_t)chunk * sch->ch_wt * 2 * sizeof(int16_t)));
+    for (int64_t first = 0; first < n; first += chunk) {
+        const int64_t m = n - first < chunk ? n - first : chunk;
+        CK(c, timed(c, K_UNPACK, [&] {
+            return launch_unpack(c->ring, d_vkp + (size_t)first * 2 * 32 * vk_bits, m * 2, vk_bits, 0, d_vk, c->stream);
+        }));
+        CK(c, timed(c, K_UNPACK, [&] {
+            return launch_unpack(c->ring, d_sigp + (size_t)first * l * 32 * sig_bits, m * l, sig_bits, sig_bias, d_sig,
+                                 c->stream);
+        }));
+        int st = run_challenge(c, sch, d_msg, d_off + first, m, d_pairs);
+        if (st != LCB_OK) return st;
+        CK(c, timed(c, K_VERIFY, [&] {
+            return launch_verify(c->ring, d_sig, d_vk, d_pairs, sch->ch_wt, nullptr, nullptr, m, bd > 32767 ? 32767 : bd,
+                                 wt, d_verdict + first, c->stream);
+        }));
+    }
     CK(c, sg.finish());
     return LCB_OK;
 }

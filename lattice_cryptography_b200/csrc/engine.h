@@ -69,4 +69,10 @@ cudaError_t launch_aggv_partial(const RingCtx& c, const uint16_t* vk_ntt, const 
 cudaError_t launch_aggv_finish(const RingCtx& c, const int32_t* partial, const int16_t* ag_sig, int64_t total,
                                int ag_cap, int avf_bd, int avf_wt, uint8_t* verdict, cudaStream_t st);
 
+// wire format (wire.cu): `bits`-bit little-endian packing of (x + bias) mod 2^16, 32*bits bytes per polynomial
+cudaError_t launch_pack(const RingCtx& c, const void* in, int64_t npoly, int bits, int bias, uint8_t* out,
+                        uint8_t* in_range, cudaStream_t st);
+cudaError_t launch_unpack(const RingCtx& c, const uint8_t* in, int64_t npoly, int bits, int bias, void* out,
+                          cudaStream_t st);
+
 }  // namespace lcb

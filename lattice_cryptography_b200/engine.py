@@ -215,6 +215,33 @@ class Engine(object):
                                                _addr(sig), _addr(st_ntt), n, bd, wt, _addr(verdict)))
         return verdict
 
+    # ------------------------------------------------------------------ packed wire format
+    def pack(self, values, bits: int, bias: int, device: bool = False, want_range: bool = False):
+        """values int16/uint16 [..., 256] -> uint8 [..., 32*bits] (include/lcb200.h, lcb_pack_batch)."""
+        lead = tuple(values.shape[:-1])
+        npoly = int(np.prod(lead)) if lead else 1
+        packed = self._out(lead + (32 * bits,), np.uint8, device)
+        ok = self._out(lead, np.uint8, device) if want_range else None
+        self._ck(self._lib.lcb_pack_batch(self._ctx, _addr(values), npoly, bits, bias, _addr(packed), _addr(ok)))
+        return (packed, ok) if want_range else packed
+
+    def unpack(self, packed, bits: int, bias: int, dtype=np.int16, device: bool = False):
+        lead = tuple(packed.shape[:-1])
+        npoly = int(np.prod(lead)) if lead else 1
+        out = self._out(lead + (D,), dtype, device)
+        self._ck(self._lib.lcb_unpack_batch(self._ctx, _addr(packed), npoly, bits, bias, _addr(out)))
+        return out
+
+    def lm_verify_packed(self, sch: LcbScheme, vk_packed, vk_bits: int, chmsgs, sig_packed, sig_bits: int,
+                         sig_bias: int, bd: int, wt: int, device: bool = False, out=None):
+        blob, off = self._rag(chmsgs)
+        n = self._count(off)
+        verdict = out if out is not None else self._out((n,), np.uint8, device)
+        self._ck(self._lib.lcb_lm_verify_packed_batch(self._ctx, byref(sch), _addr(vk_packed), vk_bits, _addr(blob),
+                                                      _addr(off), _addr(sig_packed), sig_bits, sig_bias, n, bd, wt,
+                                                      _addr(verdict)))
+        return verdict
+
     # ------------------------------------------------------------------ BKLM aggregation
     def agg_coefs(self, sch: LcbScheme, agmsg, first: int, count: int, device: bool = False):
         if isinstance(agmsg, (str, bytes, bytearray)):

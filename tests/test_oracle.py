@@ -152,3 +152,23 @@ def test_oracle_equals_reference_modules_live():
         assert bpp[k] == obp[k]
     for k in ('pvf_bd', 'pvf_wt', 'vf_bd', 'vf_wt', 'ext_wit_bd', 'ext_wit_wt', 'wit_bd', 'wit_wt', 'wit_salt'):
         assert app[k] == oap[k]
+
+
+def test_wire_format_oracle_roundtrip_and_layout():
+    """oracle/wire.py: value i sits at bit offset i*bits, LSB first; out-of-range values are flagged."""
+    import numpy as np
+    import wire as owire
+    x = np.zeros((2, 256), dtype=np.int16)
+    x[0, 0], x[0, 1], x[0, 255] = -945, 945, 3
+    p, ok = owire.pack(x, 11, 945)
+    assert p.shape == (2, 352) and ok.tolist() == [1, 1]
+    word = int.from_bytes(bytes(p[0, :4]), 'little')
+    assert word & 0x7FF == 0 and (word >> 11) & 0x7FF == 1890
+    tail = int.from_bytes(bytes(p[0, -4:]), 'little')
+    assert tail >> (32 - 11) == 948
+    assert np.array_equal(owire.unpack(p, 11, 945), x)
+    x[1, 9] = 1103                                   # 1103 + 945 = 2^11
+    assert owire.pack(x, 11, 945)[1].tolist() == [1, 0]
+    rng = np.random.default_rng(0)
+    u = rng.integers(0, 11777, size=(4, 2, 256)).astype(np.uint16)
+    assert np.array_equal(owire.unpack(owire.pack(u, 14, 0)[0], 14, 0, np.uint16), u)
