@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -620,10 +621,16 @@ int lcb_lm_keygen_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* seeds,
     CK(c, sg.out(&d_vk_coef, vk_coef, (size_t)n * 2 * D));
     // Signing keys pass through HBM in coefficient form between the sampler and the row-vector
     // product; when the caller does not want them, a bounded scratch chunk is reused.
-    // The chunk is two full waves of sampler blocks (4 resident blocks of 128 streams per SM), so that
-    // every launch fills the machine: 151,552 keys = 2.0 GB (secpar 128) / 3.6 GB (secpar 256) of scratch.
-    const int64_t wave = (int64_t)c->ring.num_sms * 4 * 128;
-    const int64_t chunk = d_sk_coef ? n : (n < 2 * wave ? n : 2 * wave);
+    // The chunk is four full waves of sampler blocks (5 resident blocks of 128 streams per SM), so that
+    // every launch fills the machine and tails are rare: 378,880 keys = 5.0 GB (secpar 128) / 8.9 GB
+    // (secpar 256) of scratch (tools/keygen_chunk_sweep.py: 2.07 M keys/s at secpar 128 vs 1.85-2.0 M
+    // for one or two waves).
+    const int64_t wave = (int64_t)c->ring.num_sms * 5 * 128;
+    int64_t chunk = d_sk_coef ? n : (n < 4 * wave ? n : 4 * wave);
+    if (const char* env = getenv("LCB_KEYGEN_CHUNK")) {            // tuning knob (keys per sampler launch)
+        const int64_t v = atoll(env);
+        if (v > 0 && !d_sk_coef) chunk = v < n ? v : n;
+    }
     int16_t* scratch = nullptr;
     if (!d_sk_coef) CK(c, sg.alloc((void**)&scratch, (size_t)chunk * 2 * l * D * sizeof(int16_t)));
     for (int64_t start = 0; start < n; start += chunk) {

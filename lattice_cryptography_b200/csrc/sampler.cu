@@ -72,20 +72,21 @@ __global__ void __launch_bounds__(P) k_sampler(SamplerArgs a) {
     uint32_t* bmap = ring + RING_WORDS * P;      // [8][P]   (directly after the ring, see StreamCols)
     uint32_t* mutab = bmap + 8 * P;
     uint32_t* r16tab = mutab + 260;
-    uint8_t* wtab = reinterpret_cast<uint8_t*>(r16tab + 260);     // [257][WT_K]
+    uint8_t* wtab = reinterpret_cast<uint8_t*>(r16tab + 260);     // [257][pieces]
+    const int pieces = weight_pieces(a.idx_bits, a.mag_bits);
 
     const int tid = threadIdx.x;
     const int64_t inst_raw = (int64_t)blockIdx.x * P + tid;
     const bool live = inst_raw < a.n;
     const int64_t inst = live ? inst_raw : a.n - 1;
     fill_mod_tables(mutab, r16tab);
-    fill_weight_table(wtab, a.wt, a.bd, max(2, (max(a.idx_bits, a.mag_bits) + 31) >> 5));
+    fill_weight_table(wtab, a.wt, a.bd, pieces);
     __syncthreads();
 
     const InputView iv{reinterpret_cast<const uint32_t*>(a.salt), a.salt_len, a.msgs + a.off[inst],
                        a.off[inst + 1] - a.off[inst]};
     const DecodeParams dp{a.bd, a.wt, a.vec_len, a.idx_bits, a.mag_bits, a.pad_bits};
-    const StreamCols sc{ring + tid, bmap + tid, P, mutab, r16tab, wtab, a.idx_scratch + inst_raw, a.idx_stride};
+    const StreamCols sc{ring + tid, bmap + tid, P, mutab, r16tab, wtab, pieces, a.idx_scratch + inst_raw, a.idx_stride};
     int16_t* dense = a.out_dense ? a.out_dense + inst * a.dense_stride : nullptr;
     uint32_t* pairs = a.out_pairs ? reinterpret_cast<uint32_t*>(a.out_pairs) + inst * a.vec_len * (int64_t)a.wt : nullptr;
     const int wt = a.wt;
@@ -206,13 +207,15 @@ cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    // Grids under two full waves (5 resident 128-stream blocks per SM) run as 64-stream blocks instead:
+    // Grids under two full waves (5 resident 128-stream blocks per SM, register-limited) run as 64-stream blocks instead:
     // the ALU-bound streams then spread evenly (e.g. 2^16 streams: 6.92 blocks per SM, at most 7) instead
     // of leaving SMs with 3 blocks waiting for SMs with 4.
     const bool narrow = (a.n + SBS - 1) / SBS < (int64_t)num_sms * 10;
     const int threads = narrow ? SBS / 2 : SBS;
     if (!a.idx_scratch || a.idx_stride < (a.n + threads - 1) / threads * threads) return cudaErrorInvalidValue;
-    size_t smem = (size_t)(RING_WORDS + 8) * threads * 4 + 2 * 260 * 4 + 260 * WT_K;
+    const int pieces = weight_pieces(a.idx_bits, a.mag_bits);
+    if (pieces > WT_K) return cudaErrorInvalidValue;
+    size_t smem = (size_t)(RING_WORDS + 8) * threads * 4 + 2 * 260 * 4 + (size_t)(257 * pieces + 15) / 16 * 16;
     auto kern = narrow ? k_sampler<SBS / 2> : k_sampler<SBS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

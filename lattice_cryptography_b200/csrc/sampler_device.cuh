@@ -70,7 +70,8 @@ struct StreamCols {
     int pitch;
     const uint32_t* mutab;     // [257] floor((2^32-1)/m)   (block-shared)
     const uint32_t* r16tab;    // [257] 2^16 mod m
-    const uint8_t* wtab;       // [257][WT_K] 2^(32k) mod m, rows filled by fill_weight_table
+    const uint8_t* wtab;       // [257][wstride] 2^(32k) mod m, rows filled by fill_weight_table
+    int wstride;               // pieces per row
     uint8_t* idxs;             // global scratch, byte e of this stream at idxs[e * idx_stride]
     int64_t idx_stride;
 };
@@ -83,8 +84,14 @@ __device__ __forceinline__ void fill_mod_tables(uint32_t* mutab, uint32_t* r16ta
 }
 
 // Weights of the 32-bit pieces of a big-endian field modulo m <= 256: wtab[m][k] = 2^(32k) mod m.
-// Only the rows a sampler call can touch are filled: the index moduli D-wt+1 .. D-1 and bd.
-constexpr int WT_K = 20;          // pieces per row: MAX_FIELD_BITS / 32 + 1
+// Only the rows a sampler call can touch are filled: the index moduli D-wt+1 .. D-1 and bd.  A row holds
+// `pieces` = max(2, ceil(widest field / 32)) <= WT_K bytes.
+constexpr int WT_K = 20;          // MAX_FIELD_BITS / 32 + 1
+__host__ __device__ __forceinline__ int weight_pieces(int idx_bits, int mag_bits) {
+    const int w = idx_bits > mag_bits ? idx_bits : mag_bits;
+    const int p = (w + 31) >> 5;
+    return p < 2 ? 2 : p;
+}
 __device__ __forceinline__ void fill_weight_table(uint8_t* wtab, int wt, int bd, int pieces) {
     const int m_lo = max(2, D - wt + 1), m_hi = D - 1;
     for (int i = m_lo + (int)threadIdx.x; i <= m_hi + 1; i += blockDim.x) {
@@ -92,7 +99,7 @@ __device__ __forceinline__ void fill_weight_table(uint8_t* wtab, int wt, int bd,
         if (m < 2 || m > 256) continue;
         const uint32_t r16 = 65536u % m, r32 = (r16 * r16) % m;
         uint32_t w = 1;
-        for (int k = 0; k < pieces; ++k) { wtab[m * WT_K + k] = (uint8_t)w; w = (w * r32) % m; }
+        for (int k = 0; k < pieces; ++k) { wtab[m * pieces + k] = (uint8_t)w; w = (w * r32) % m; }
     }
 }
 
@@ -209,7 +216,7 @@ __device__ __forceinline__ void sample_stream(const DecodeParams& dp, const Inpu
                     const uint32_t m = (uint32_t)(D - f);
                     uint32_t k = 0;
                     if (m == 1) rp += dp.idx_bits;
-                    else k = field_small(dp.idx_bits, m, sc.mutab[m], sc.r16tab[m], sc.wtab + m * WT_K);
+                    else k = field_small(dp.idx_bits, m, sc.mutab[m], sc.r16tab[m], sc.wtab + m * sc.wstride);
                     // k-th (0-based) still-unused position in ascending order
                     bool found = false;
                     selw = 0; word = 0;
@@ -240,7 +247,7 @@ __device__ __forceinline__ void sample_stream(const DecodeParams& dp, const Inpu
                 if (bd == 1) {
                     rp += dp.mag_bits;
                 } else if (bd <= 256) {
-                    r = field_small(dp.mag_bits, bd, bd_mu, bd_r16, sc.wtab + bd * WT_K);
+                    r = field_small(dp.mag_bits, bd, bd_mu, bd_r16, sc.wtab + bd * sc.wstride);
                 } else {
                     int rem = dp.mag_bits;
                     while (rem > 0) {
