@@ -190,8 +190,9 @@ def _engine(secpar, local, np):
 
 
 def secondary_keygen_sign(a, rank, local, world, torch, np, dist):
-    """configs[2]: keygen + sign from synthetic seeds at secpar 256 (2^16 seeds per GPU here)."""
-    class A: secpar, log2n = 256, 16
+    """configs[2]: keygen + sign from synthetic seeds at secpar 256; 2^17 seeds per GPU (the config's 2^20
+    seeds over 8 GPUs)."""
+    class A: secpar, log2n = 256, 17
     eng, sch, p = _engine(256, local, np)
     dev = f'cuda:{local}'
     n = 1 << A.log2n
@@ -492,9 +493,9 @@ def engine_arm(a):
             'roofline': {'bound': 'hbm', 'kernel': 'k_verify', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak,
                          # DRAM bytes per launch from the ncu --set full capture of this kernel
-                         # (profiles/prof_r1_verify.summary.txt: 2.0343 GB read + 4.9 MB written for 2^18
-                         # verifies = 7,779 B per verify), scaled to this launch's batch
-                         'traffic': 7779 * n if a.secpar == 128 else None,
+                         # (profiles/prof_r1_verify.summary.txt: 2.0343 GB read + 5.3 MB written for 2^18
+                         # verifies = 7,781 B per verify), scaled to this launch's batch
+                         'traffic': 7781 * n if a.secpar == 128 else None,
                          'algorithmic_bytes_per_launch': unit_bytes * n,
                          'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback',
                          'algorithmic_bytes_per_unit': unit_bytes,
@@ -510,16 +511,20 @@ def engine_arm(a):
             'setup': {'keygen_s': t_keygen, 'sign_s': t_sign, 'keygen_keys_per_s': n / t_keygen,
                       'sign_sigs_per_s': n / t_sign},
         }
-        # integer-pipe view of the same kernel: thread-instructions per verify from the ncu instruction
-        # count of this build (profiles/README.md), against 148 SM x 64 lanes x max clock per pipe
-        instr_per_unit = 32 * 3711            # smsp__inst_executed.sum / verifies, k_verify, secpar 128 (profiles/)
-        pipe_peak = 148 * 64 * (clk['sm_max_mhz'] or 1965.0) * 1e6 if clk else 148 * 64 * 1965e6
-        line['roofline']['int_pipe'] = {
-            'thread_instr_per_unit': instr_per_unit, 'fma_pipe_share': 0.54,
-            'achieved_tinstr_s': instr_per_unit * n / (k_ms * 1e-3) / 1e12,
-            'issue_peak_tinstr_s': 2 * pipe_peak / 1e12,
-            'fma_pipe_frac': 0.54 * instr_per_unit * n / (k_ms * 1e-3) / pipe_peak,
-            'note': 'fraction of the FMA-heavy (IMAD) pipe issue limit, the binding unit of k_verify'}
+        # instruction-issue view of the same kernel: warp-instructions per verify from the ncu count of this
+        # build (profiles/prof_r1_verify.summary.txt: 992.49 M for 2^18 verifies), against the issue limit of
+        # 4 schedulers x 148 SMs x 1 warp-instruction per clock at the max clock
+        instr_per_unit = 32 * 3786 if a.secpar == 128 else None
+        clk_hz = ((clk or {}).get('sm_max_mhz') or 1965.0) * 1e6
+        if instr_per_unit:
+            achieved_t = instr_per_unit * n / (k_ms * 1e-3) / 1e12
+            issue_peak = 148 * 128 * clk_hz / 1e12
+            line['roofline']['int_pipe'] = {
+                'thread_instr_per_unit': instr_per_unit, 'achieved_tinstr_s': achieved_t,
+                'issue_peak_tinstr_s': issue_peak, 'issue_frac': achieved_t / issue_peak,
+                'ncu_pipe_utilisation': {'issue_active': 0.734, 'alu': 0.505, 'fma': 0.351, 'lsu': 0.263},
+                'note': 'k_verify is bound by instruction issue: 5-instruction FP32-assisted butterflies spread '
+                        'over the ALU, FMA-heavy and FMA-lite pipes (DESIGN.md 3.3)'}
         if cpu is not None:
             line['cpu_baseline'] = cpu
     del sig, sig_v, vk_ntt, d_ch, h_sig, h_vk, h_ch, np_sig, np_vk, np_ch
