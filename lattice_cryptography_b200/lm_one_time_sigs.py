@@ -75,10 +75,24 @@ def keygen_batch(pp: PublicParameters, seeds: Sequence[Any], want_coef: bool = T
     """N keys from N seeds (SecretSeed objects or bitstrings) in one engine call.
     -> dict(sk_ntt uint16[N,2,l,d], vk_ntt uint16[N,2,d][, sk_coef int16[N,2,l,d], vk_coef int16[N,2,d]])"""
     eng, sch = _ctx(pp)
-    strs = [s.seed if isinstance(s, SecretSeed) else s for s in seeds]
+    if isinstance(seeds, tuple) and len(seeds) == 2 and not isinstance(seeds[0], (str, SecretSeed)):
+        strs = seeds                # already (byte blob, int64 offsets), e.g. from random_seed_batch
+    else:
+        strs = [s.seed if isinstance(s, SecretSeed) else s for s in seeds]
     sk_coef, sk_ntt, vk_ntt, vk_coef = eng.lm_keygen(sch, strs, want_sk_coef=want_coef, want_vk_coef=want_coef,
                                                      device=device)
     return {'sk_ntt': sk_ntt, 'vk_ntt': vk_ntt, 'sk_coef': sk_coef, 'vk_coef': vk_coef}
+
+
+def random_seed_batch(pp: PublicParameters, n: int):
+    """The unseeded keygen path (make_random_seed, reference lm_one_time_sigs.py:58-61) for a batch: n fresh
+    secpar-bit seeds from the OS entropy source (`secrets`), as the ASCII bitstrings the reference hashes, in
+    the (blob, offsets) form keygen_batch takes.  Row i of blob.reshape(n, secpar) is seed i."""
+    from secrets import token_bytes
+    secpar = pp['scheme_parameters'].secpar
+    raw = np.frombuffer(token_bytes(n * secpar // 8), dtype=np.uint8)
+    blob = (np.unpackbits(raw) + ord('0')).astype(np.uint8)
+    return blob, np.arange(n + 1, dtype=np.int64) * secpar
 
 
 def sign_batch(pp: PublicParameters, sk_ntt, chmsgs, device: bool = False):

@@ -130,3 +130,9 @@ def test_wire_module_and_seeded_key_ch(golden):
     assert wire.verify_batch_packed(pp, vkp, chm, packed).tolist() == [1] * 9
     chm[4] += '?'
     assert wire.verify_batch_packed(pp, vkp, chm, packed).tolist() == [1, 1, 1, 1, 0, 1, 1, 1, 1]
+    # unseeded batch path: fresh seeds as (blob, offsets) give the same keys as their bitstrings
+    blob, off = lm.random_seed_batch(pp, 5)
+    fresh = lm.keygen_batch(pp, (blob, off))
+    again = lm.keygen_batch(pp, [bytes(r).decode() for r in blob.reshape(5, 128)])
+    assert np.array_equal(fresh['sk_coef'], again['sk_coef']) and np.array_equal(fresh['vk_ntt'], again['vk_ntt'])
+    assert lm.verify_batch(pp, fresh['vk_ntt'], chm[:5], lm.sign_batch(pp, fresh['sk_ntt'], chm[:5])).tolist() == [1] * 5

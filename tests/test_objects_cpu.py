@@ -1,0 +1,56 @@
+"""Host-only behaviour of the drop-in objects (no GPU needed: nothing here multiplies or transforms):
+deepcopy / pickle round trips (the reference deep-copies polynomials in every operator and pickles key
+tuples across its multiprocessing Pool, lm_one_time_sigs.py:100-123), equality, container indexing and the
+batched form of the unseeded keygen path (make_random_seed, lm_one_time_sigs.py:58-61)."""
+import copy
+import pickle
+
+import numpy as np
+
+
+def _lp():
+    from lattice_cryptography_b200.lattice_algebra import LatticeParameters
+    return LatticeParameters(modulus=11777, degree=256, length=13)
+
+
+def test_polynomial_objects_deepcopy_and_pickle():
+    from lattice_cryptography_b200.lattice_algebra import Polynomial, PolynomialVector
+    lp = _lp()
+    f = Polynomial(lp=lp, coefs={0: 1, 7: -5888, 255: 5888}, const_time_flag=False)
+    g = Polynomial(lp=lp, coefs={3: 2})
+    v = PolynomialVector(lp=lp, entries=[f] + [g] * 12)
+    for obj in (lp, f, v):
+        for clone in (copy.deepcopy(obj), pickle.loads(pickle.dumps(obj))):
+            assert clone == obj and clone is not obj
+    c = copy.deepcopy(f)
+    assert c.get_coef_rep() == ({0: 1, 7: -5888, 255: 5888}, 5888, 3) and c.const_time_flag is False
+    c._coef[0] = 2                                   # a deep copy owns its storage
+    assert f.get_coef_rep()[0][0] == 1 and c != f
+
+
+def test_key_objects_pickle_and_index():
+    from lattice_cryptography_b200.lattice_algebra import Polynomial, PolynomialVector
+    from lattice_cryptography_b200.one_time_keys import OneTimeSigningKey, OneTimeVerificationKey, SecretSeed
+    lp = _lp()
+    seed = SecretSeed(secpar=128, lp=lp, seed='01' * 64)
+    half = PolynomialVector(lp=lp, entries=[Polynomial(lp=lp, coefs={i: i + 1}) for i in range(13)])
+    sk = OneTimeSigningKey(secpar=128, lp=lp, left_key=half, right_key=copy.deepcopy(half))
+    vk = OneTimeVerificationKey(secpar=128, lp=lp, left_key=Polynomial(lp=lp, coefs={1: 1}),
+                                right_key=Polynomial(lp=lp, coefs={2: -1}))
+    seed2, sk2, vk2 = pickle.loads(pickle.dumps((seed, sk, vk)))
+    assert seed2 == seed and sk2 == sk and vk2 == vk
+    assert sk2[0] == sk.left_key and vk2[1] == vk.right_key
+    # as in the reference, str() of a key is its identity, so the copy is a different signer
+    assert str(vk2) != str(vk)
+
+
+def test_random_seed_batch_shape_and_alphabet():
+    from lattice_cryptography_b200 import lm_one_time_sigs as lm
+
+    class _SP:
+        secpar = 256
+    blob, off = lm.random_seed_batch({'scheme_parameters': _SP()}, 1000)
+    assert blob.dtype == np.uint8 and blob.shape == (256000,) and set(np.unique(blob)) <= {48, 49}
+    assert off.dtype == np.int64 and off[0] == 0 and off[-1] == 256000 and (np.diff(off) == 256).all()
+    rows = blob.reshape(1000, 256)
+    assert len({bytes(r) for r in rows}) == 1000 and 0.45 < (rows == 49).mean() < 0.55
