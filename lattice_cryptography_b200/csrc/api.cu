@@ -17,6 +17,7 @@ struct lcb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;  // H2D of large host inputs, chunk by chunk, under the kernels (lazy)
     int secpar = 0, q = 0, d = 0, l = 0, rou = 0;
     RingCtx ring{};
     NttTables* d_tab = nullptr;
@@ -53,6 +54,9 @@ int fail_cuda(lcb_ctx* c, cudaError_t e, const char* what) {
         cudaError_t e_ = (call);                                 \
         if (e_ != cudaSuccess) return fail_cuda((c), e_, #call); \
     } while (0)
+
+// host signatures are moved and verified 2^17 triples at a time (0.87 / 1.5 GB per chunk)
+constexpr int64_t kPipeChunk = 1 << 17;
 
 enum KernelId { K_SAMPLER = 0, K_SHAKE, K_NTT_FWD, K_NTT_INV, K_POLY_MUL, K_MATVEC, K_SIGN, K_VERIFY, K_ADDSUB,
                 K_AGG_COEFS, K_AGG_PARTIAL, K_AGG_FINISH, K_AGGV_PARTIAL, K_AGGV_FINISH, K_PACK, K_UNPACK, K_COUNT };
@@ -141,6 +145,9 @@ class Staging {
   public:
     explicit Staging(lcb_ctx* c) : c_(c) {}
     ~Staging() {
+        // an early error return must not free buffers a chunked copy is still writing
+        if (piped_ && c_->copy_stream) cudaStreamSynchronize(c_->copy_stream);
+        for (cudaEvent_t e : events_) cudaEventDestroy(e);
         for (void* p : owned_) cudaFreeAsync(p, c_->stream);
     }
     cudaError_t alloc(void** out, size_t bytes) {
@@ -165,6 +172,44 @@ class Staging {
         host_touched_ = true;
         *dev = static_cast<const T*>(d);
         return cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, c_->stream);
+    }
+    // Like in(), but a HOST buffer is only given device room: the caller moves it with pipe_chunk(), one
+    // chunk at a time on the copy stream, so that the transfer of chunk i+1 runs under the kernels of chunk i.
+    template <typename T>
+    cudaError_t in_piped(const T** dev, const T* p, size_t count, bool* piped) {
+        *piped = false;
+        if (p == nullptr || count == 0 || on_device(p)) return in(dev, p, count);
+        void* d = nullptr;
+        cudaError_t e = alloc(&d, count * sizeof(T));
+        if (e != cudaSuccess) return e;
+        host_touched_ = true;
+        *dev = static_cast<const T*>(d);
+        *piped = true;
+        return cudaSuccess;
+    }
+    // Call once after every allocation of this call and before the first pipe_chunk(): the copy stream may
+    // not touch the stream-ordered allocations before the main stream has made them.
+    cudaError_t pipe_begin() {
+        cudaError_t e;
+        if (!c_->copy_stream &&
+            (e = cudaStreamCreateWithFlags(&c_->copy_stream, cudaStreamNonBlocking)) != cudaSuccess)
+            return e;
+        cudaEvent_t ready;
+        if ((e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming)) != cudaSuccess) return e;
+        events_.push_back(ready);
+        if ((e = cudaEventRecord(ready, c_->stream)) != cudaSuccess) return e;
+        piped_ = true;
+        return cudaStreamWaitEvent(c_->copy_stream, ready, 0);
+    }
+    // H2D of one chunk on the copy stream; returns the event the consumer stream has to wait for.
+    cudaError_t pipe_chunk(const void* dev, const void* host, size_t bytes, cudaEvent_t* done) {
+        cudaError_t e;
+        if ((e = cudaEventCreateWithFlags(done, cudaEventDisableTiming)) != cudaSuccess) return e;
+        events_.push_back(*done);
+        if ((e = cudaMemcpyAsync(const_cast<void*>(dev), host, bytes, cudaMemcpyHostToDevice, c_->copy_stream)) !=
+            cudaSuccess)
+            return e;
+        return cudaEventRecord(*done, c_->copy_stream);
     }
     template <typename T>
     cudaError_t out(T** dev, T* p, size_t count) {
@@ -194,7 +239,9 @@ class Staging {
     lcb_ctx* c_;
     std::vector<void*> owned_;
     std::vector<Back> back_;
+    std::vector<cudaEvent_t> events_;
     bool host_touched_ = false;
+    bool piped_ = false;
 };
 
 // off[n] = total blob length; needed only to stage a HOST blob, so a device blob costs nothing here
@@ -407,6 +454,10 @@ int lcb_ctx_destroy(lcb_ctx* c) {
     if (c->d_a_hat) cudaFree(c->d_a_hat);
     if (c->idx_scratch) cudaFree(c->idx_scratch);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamDestroy(c->copy_stream);
+    }
     delete c;
     return LCB_OK;
 }
@@ -722,14 +773,38 @@ int lcb_lm_verify_batch(lcb_ctx* c, const lcb_scheme* sch, const uint16_t* vk_nt
     CK(c, sg.in(&d_vk, vk_ntt, (size_t)n * 2 * D));
     CK(c, sg.in(&d_msg, chmsg, (size_t)total));
     CK(c, sg.in(&d_off, chmsg_off, (size_t)n + 1));
-    CK(c, sg.in(&d_sig, sig, (size_t)n * l * D));
+    bool piped = false;
+    CK(c, sg.in_piped(&d_sig, sig, (size_t)n * l * D, &piped));
     CK(c, sg.in(&d_st, st_ntt, (size_t)n * D));
     CK(c, sg.out(&d_verdict, verdict, (size_t)n));
     CK(c, sg.alloc((void**)&d_pairs, (size_t)n * sch->ch_wt * 2 * sizeof(int16_t)));
-    int st = run_challenge(c, sch, d_msg, d_off, n, d_pairs);
-    if (st != LCB_OK) return st;
-    CK(c, timed(c, K_VERIFY, [&] { return launch_verify(c->ring, d_sig, d_vk, d_pairs, sch->ch_wt, nullptr, d_st, n, bd > 32767 ? 32767 : bd, wt,
-                        d_verdict, c->stream); }));
+    const int vbd = bd > 32767 ? 32767 : bd;
+    // Signatures in HOST memory (the bulk of the bytes) cross PCIe in chunks on the copy stream while the
+    // sampler and verify kernels of the previous chunk run; everything else is one launch over the batch.
+    const int64_t chunk = piped && n > kPipeChunk ? kPipeChunk : n;
+    std::vector<cudaEvent_t> arrived;
+    if (piped) {
+        CK(c, sg.pipe_begin());
+        for (int64_t first = 0; first < n; first += chunk) {
+            const int64_t m = n - first < chunk ? n - first : chunk;
+            cudaEvent_t ev;
+            CK(c, sg.pipe_chunk(d_sig + (size_t)first * l * D, sig + (size_t)first * l * D,
+                                (size_t)m * l * D * sizeof(int16_t), &ev));
+            arrived.push_back(ev);
+        }
+    }
+    for (int64_t first = 0, k = 0; first < n; first += chunk, ++k) {
+        const int64_t m = n - first < chunk ? n - first : chunk;
+        int16_t* pairs = d_pairs + (size_t)first * sch->ch_wt * 2;
+        int st = run_challenge(c, sch, d_msg, d_off + first, m, pairs);
+        if (st != LCB_OK) return st;
+        if (piped) CK(c, cudaStreamWaitEvent(c->stream, arrived[k], 0));
+        CK(c, timed(c, K_VERIFY, [&] {
+            return launch_verify(c->ring, d_sig + (size_t)first * l * D, d_vk + (size_t)first * 2 * D, pairs, sch->ch_wt,
+                                 nullptr, d_st ? d_st + (size_t)first * D : nullptr, m, vbd, wt, d_verdict + first,
+                                 c->stream);
+        }));
+    }
     CK(c, sg.finish());
     return LCB_OK;
 }
@@ -767,7 +842,7 @@ int lcb_unpack_batch(lcb_ctx* c, const uint8_t* packed, int64_t npoly, int bits,
     return LCB_OK;
 }
 
-// lcb_lm_verify_batch on packed verification keys and signatures.  The batch is processed in chunks
+// lcb_lm_verify_batch on packed verification keys and signatures.  The batch is processed in chunks of 2^18
 // (unpack -> challenge sampler -> verify) so that the unpacked copies never exceed ~2 GB of scratch.
 int lcb_lm_verify_packed_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* vk_packed, int vk_bits,
                                const uint8_t* chmsg, const int64_t* chmsg_off, const uint8_t* sig_packed, int sig_bits,
@@ -788,21 +863,36 @@ int lcb_lm_verify_packed_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t*
     CK(c, sg.in(&d_vkp, vk_packed, (size_t)n * 2 * 32 * vk_bits));
     CK(c, sg.in(&d_msg, chmsg, (size_t)total));
     CK(c, sg.in(&d_off, chmsg_off, (size_t)n + 1));
-    CK(c, sg.in(&d_sigp, sig_packed, (size_t)n * l * 32 * sig_bits));
+    bool piped = false;
+    CK(c, sg.in_piped(&d_sigp, sig_packed, (size_t)n * l * 32 * sig_bits, &piped));
     CK(c, sg.out(&d_verdict, verdict, (size_t)n));
     if ((reinterpret_cast<uintptr_t>(d_vkp) | reinterpret_cast<uintptr_t>(d_sigp)) & 3u)
         return fail(c, LCB_ERR_INVALID, "packed buffers must be 4-byte aligned");
-    const int64_t chunk = n < (1 << 18) ? n : (1 << 18);
+    const int64_t chunk = n < 2 * kPipeChunk ? n : 2 * kPipeChunk;
     uint16_t* d_vk;
     int16_t *d_sig, *d_pairs;
     CK(c, sg.alloc((void**)&d_vk, (size_t)chunk * 2 * D * sizeof(uint16_t)));
     CK(c, sg.alloc((void**)&d_sig, (size_t)chunk * l * D * sizeof(int16_t)));
     CK(c, sg.alloc((void**)&d_pairs, (size_t)chunk * sch->ch_wt * 2 * sizeof(int16_t)));
-    for (int64_t first = 0; first < n; first += chunk) {
+    // packed signatures in HOST memory cross PCIe chunk by chunk under the kernels of the previous chunk
+    std::vector<cudaEvent_t> arrived;
+    const size_t sig_row = (size_t)l * 32 * sig_bits;
+    if (piped) {
+        CK(c, sg.pipe_begin());
+        for (int64_t first = 0; first < n; first += chunk) {
+            const int64_t m = n - first < chunk ? n - first : chunk;
+            cudaEvent_t ev;
+            CK(c, sg.pipe_chunk(d_sigp + (size_t)first * sig_row, sig_packed + (size_t)first * sig_row,
+                                (size_t)m * sig_row, &ev));
+            arrived.push_back(ev);
+        }
+    }
+    for (int64_t first = 0, k = 0; first < n; first += chunk, ++k) {
         const int64_t m = n - first < chunk ? n - first : chunk;
         CK(c, timed(c, K_UNPACK, [&] {
             return launch_unpack(c->ring, d_vkp + (size_t)first * 2 * 32 * vk_bits, m * 2, vk_bits, 0, d_vk, c->stream);
         }));
+        if (piped) CK(c, cudaStreamWaitEvent(c->stream, arrived[k], 0));
         CK(c, timed(c, K_UNPACK, [&] {
             return launch_unpack(c->ring, d_sigp + (size_t)first * l * 32 * sig_bits, m * l, sig_bits, sig_bias, d_sig,
                                  c->stream);

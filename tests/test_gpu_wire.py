@@ -136,3 +136,34 @@ def test_wire_module_and_seeded_key_ch(golden):
     again = lm.keygen_batch(pp, [bytes(r).decode() for r in blob.reshape(5, 128)])
     assert np.array_equal(fresh['sk_coef'], again['sk_coef']) and np.array_equal(fresh['vk_ntt'], again['vk_ntt'])
     assert lm.verify_batch(pp, fresh['vk_ntt'], chm[:5], lm.sign_batch(pp, fresh['sk_ntt'], chm[:5])).tolist() == [1] * 5
+
+
+def test_host_buffers_pipeline_over_several_chunks(engines):
+    """Host-resident signatures are copied and verified in 2^17-triple chunks on a second stream
+    (api.cu, Staging::pipe_chunk): more than one chunk, ragged tail, tampered triples in every chunk -
+    verdicts must equal the all-device path, for the int16 and the packed entry points."""
+    import torch
+    from lattice_cryptography_b200 import ragged
+    e = engines[128]
+    sch = scheme(128)
+    n = (1 << 17) + 4099
+    rng = np.random.default_rng(17)
+    seeds = (rng.integers(0, 2, (n, 128), dtype=np.uint8) + 48).astype(np.uint8)
+    seed_off = np.arange(n + 1, dtype=np.int64) * 128
+    msgs = rng.integers(33, 127, (n, 40), dtype=np.uint8)
+    msg_off = np.arange(n + 1, dtype=np.int64) * 40
+    d_seeds = (torch.from_numpy(seeds).cuda().view(-1), torch.from_numpy(seed_off).cuda())
+    d_msgs = (torch.from_numpy(msgs).cuda().view(-1), torch.from_numpy(msg_off).cuda())
+    _, sk_ntt, vk_ntt, _ = e.lm_keygen(sch, d_seeds, want_sk_coef=False, want_vk_coef=False, device=True)
+    sig = e.lm_sign(sch, sk_ntt, d_msgs, device=True)
+    del sk_ntt
+    bad = torch.arange(5, n, 997, device='cuda')
+    sig.view(torch.int16)[bad, bad % 13, (5 * bad) % D] += 1
+    want = e.lm_verify(sch, vk_ntt, d_msgs, sig, 945, 256, device=True).cpu().numpy()
+    assert want.sum() == n - len(bad) and not want[bad.cpu().numpy()].any()
+    h_sig, h_vk = sig.cpu().numpy(), vk_ntt.cpu().numpy()
+    h_msgs = (msgs.reshape(-1), msg_off)
+    assert np.array_equal(e.lm_verify(sch, h_vk, h_msgs, h_sig, 945, 256), want)
+    sig_p = e.pack(sig, 11, 945, device=True).cpu().numpy()
+    vk_p = e.pack(vk_ntt, 14, 0, device=True).cpu().numpy()
+    assert np.array_equal(e.lm_verify_packed(sch, vk_p, 14, h_msgs, sig_p, 11, 945, 945, 256), want)
