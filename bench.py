@@ -493,9 +493,9 @@ def engine_arm(a):
             'roofline': {'bound': 'hbm', 'kernel': 'k_verify', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak,
                          # DRAM bytes per launch from the ncu --set full capture of this kernel
-                         # (profiles/prof_r1_verify.summary.txt: 2.0343 GB read + 5.3 MB written for 2^18
-                         # verifies = 7,781 B per verify), scaled to this launch's batch
-                         'traffic': 7781 * n if a.secpar == 128 else None,
+                         # (profiles/prof_r1_verify.summary.txt: 2.0344 GB read + 6.9 MB written for 2^18
+                         # verifies = 7,787 B per verify), scaled to this launch's batch
+                         'traffic': 7787 * n if a.secpar == 128 else None,
                          'algorithmic_bytes_per_launch': unit_bytes * n,
                          'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback',
                          'algorithmic_bytes_per_unit': unit_bytes,

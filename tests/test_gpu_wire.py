@@ -44,6 +44,7 @@ def test_pack_device_buffers_and_errors(engines):
     sig = rng.integers(-3315, 3316, size=(33, 23, D)).astype(np.int16)
     dsig = torch.from_numpy(sig).cuda()
     packed = e.pack(dsig, 13, 3315, device=True)
+    e.synchronize()
     assert packed.is_cuda and tuple(packed.shape) == (33, 23, 416)
     assert np.array_equal(packed.cpu().numpy(), owire.pack(sig, 13, 3315)[0])
     back = e.unpack(packed, 13, 3315, device=True)
@@ -156,14 +157,19 @@ def test_host_buffers_pipeline_over_several_chunks(engines):
     d_msgs = (torch.from_numpy(msgs).cuda().view(-1), torch.from_numpy(msg_off).cuda())
     _, sk_ntt, vk_ntt, _ = e.lm_keygen(sch, d_seeds, want_sk_coef=False, want_vk_coef=False, device=True)
     sig = e.lm_sign(sch, sk_ntt, d_msgs, device=True)
+    e.synchronize()                      # the engine runs on its own stream, torch on another
     del sk_ntt
     bad = torch.arange(5, n, 997, device='cuda')
     sig.view(torch.int16)[bad, bad % 13, (5 * bad) % D] += 1
-    want = e.lm_verify(sch, vk_ntt, d_msgs, sig, 945, 256, device=True).cpu().numpy()
+    torch.cuda.synchronize()
+    want = e.lm_verify(sch, vk_ntt, d_msgs, sig, 945, 256, device=True)
+    e.synchronize()
+    want = want.cpu().numpy()
     assert want.sum() == n - len(bad) and not want[bad.cpu().numpy()].any()
     h_sig, h_vk = sig.cpu().numpy(), vk_ntt.cpu().numpy()
     h_msgs = (msgs.reshape(-1), msg_off)
     assert np.array_equal(e.lm_verify(sch, h_vk, h_msgs, h_sig, 945, 256), want)
-    sig_p = e.pack(sig, 11, 945, device=True).cpu().numpy()
-    vk_p = e.pack(vk_ntt, 14, 0, device=True).cpu().numpy()
+    sig_p, vk_p = e.pack(sig, 11, 945, device=True), e.pack(vk_ntt, 14, 0, device=True)
+    e.synchronize()
+    sig_p, vk_p = sig_p.cpu().numpy(), vk_p.cpu().numpy()
     assert np.array_equal(e.lm_verify_packed(sch, vk_p, 14, h_msgs, sig_p, 11, 945, 945, 256), want)

@@ -6,6 +6,7 @@ set -u
 R=${ROUND:-r1}
 O=gpurun_out
 mkdir -p $O
+python -m pytest tests -m gpu -x -q 2>&1 | tail -1 | tee $O/pytest_gpu_${R}.txt
 python bench.py > $O/bench_${R}_final.json 2> $O/bench_${R}_final.err || { echo "bench failed"; tail -5 $O/bench_${R}_final.err; exit 1; }
 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_${R}_reference.json 2> $O/bench_${R}_reference.err || echo "reference arm failed"
 SHORT="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 --bklm-log2n 12"
