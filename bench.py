@@ -273,6 +273,40 @@ def secondary_bklm(a, rank, local, world, torch, np, dist):
             'agg_coefs_gperm_s_per_gpu': perms / (coef_ms * 1e-3) / 1e9, 'keccak_roofline_gperm_s': 4.28}
 
 
+def secondary_single_ops(a, rank, local, world, torch, np, dist):
+    """configs[0]: one key / one signature / one verification through the drop-in Python API (the reference's own
+    calls, benchmarks/demo_signing.py), median wall-clock latency of 20 calls per secpar on rank 0."""
+    if rank != 0:
+        return None
+    import statistics
+    from lattice_cryptography_b200 import lattice_algebra as gla
+    from lattice_cryptography_b200 import lm_one_time_sigs as lm
+    gla.set_default_device(local)
+    out = {}
+    for secpar in (128, 256):
+        pp = lm.make_setup_parameters(secpar)
+        key = lm.keygen(pp=pp, num_keys_to_gen=1)[0]
+        sig = lm.sign(pp=pp, otk=key, msg='QRL is awesome!')
+        assert lm.verify(pp=pp, otvk=key[2], msg='QRL is awesome!', sig=sig)
+        t = {'keygen': [], 'sign': [], 'verify': []}
+        for _ in range(20):
+            t0 = time.perf_counter()
+            key = lm.keygen(pp=pp, num_keys_to_gen=1)[0]
+            t1 = time.perf_counter()
+            sig = lm.sign(pp=pp, otk=key, msg='QRL is awesome!')
+            t2 = time.perf_counter()
+            ok = lm.verify(pp=pp, otvk=key[2], msg='QRL is awesome!', sig=sig)
+            t3 = time.perf_counter()
+            assert ok
+            t['keygen'].append(t1 - t0)
+            t['sign'].append(t2 - t1)
+            t['verify'].append(t3 - t2)
+        out[f'secpar{secpar}_ms'] = {k: 1e3 * statistics.median(v) for k, v in t.items()}
+    out['note'] = ('host-visible latency of single drop-in calls (Python objects in, Python objects out); the published '
+                   'CPU log of the reference has 122 / 20 / 65-106 ms (secpar 128) for the same three calls')
+    return out
+
+
 def secondary_adaptor(a, rank, local, world, torch, np, dist):
     """configs[4]: adaptor pre-sign / pre-verify / adapt / verify / extract / witness-verify, 2^15 instances per GPU."""
     class A: secpar, log2n = 128, 15
@@ -532,7 +566,7 @@ def engine_arm(a):
     secondary = {}
     if not a.no_secondary:
         for name, fn in (('keygen_sign_secpar256', secondary_keygen_sign), ('bklm', secondary_bklm),
-                         ('adaptor', secondary_adaptor)):
+                         ('adaptor', secondary_adaptor), ('single_ops', secondary_single_ops)):
             try:
                 secondary[name] = fn(a, rank, local, world, torch, np, dist)
             except Exception as exc:          # the headline line must survive a secondary failure

@@ -273,6 +273,8 @@ int fill_sampler(lcb_ctx* c, SamplerArgs& a, const char* salt, const char* suffi
     a.mag_bits = btd - 1;
     const int64_t bits = (int64_t)LOGD + (int64_t)(wt - 1) * a.idx_bits + (int64_t)wt * btd;
     a.pad_bits = (int)(8 * ((bits + 7) / 8) - bits);
+    a.paired = 0;
+    a.salt2_len = 0;
     a.shared_msg = 0;
     a.shared_len = 0;
     a.index_first = 0;
@@ -672,10 +674,14 @@ int lcb_lm_keygen_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* seeds,
     CK(c, sg.out(&d_vk_coef, vk_coef, (size_t)n * 2 * D));
     // Signing keys pass through HBM in coefficient form between the sampler and the row-vector
     // product; when the caller does not want them, a bounded scratch chunk is reused.
-    // The chunk is four full waves of sampler blocks (5 resident blocks of 128 streams per SM), so that
-    // every launch fills the machine and tails are rare: 378,880 keys = 5.0 GB (secpar 128) / 8.9 GB
-    // (secpar 256) of scratch (tools/keygen_chunk_sweep.py: 2.07 M keys/s at secpar 128 vs 1.85-2.0 M
-    // for one or two waves).
+    // Both halves of a key come from ONE paired sampler launch (stream 2i = left, 2i+1 = right: twice the
+    // parallelism for small batches, half the launches).  The chunk is eight full waves of sampler streams
+    // (5 resident blocks of 128 streams per SM) = 378,880 keys = 5.0 GB (secpar 128) / 8.9 GB (secpar 256)
+    // of scratch, so that every launch fills the machine and tails are rare (tools/keygen_chunk_sweep.py:
+    // 2.12 M keys/s at secpar 128 against 2.02-2.08 M for two or four waves).
+    left.paired = 1;
+    std::memcpy(left.salt2, right.salt, sizeof(left.salt2));
+    left.salt2_len = right.salt_len;
     const int64_t wave = (int64_t)c->ring.num_sms * 5 * 128;
     int64_t chunk = d_sk_coef ? n : (n < 4 * wave ? n : 4 * wave);
     if (const char* env = getenv("LCB_KEYGEN_CHUNK")) {            // tuning knob (keys per sampler launch)
@@ -688,16 +694,13 @@ int lcb_lm_keygen_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* seeds,
         const int64_t cnt = (n - start < chunk) ? n - start : chunk;
         int16_t* skc = d_sk_coef ? d_sk_coef + start * 2 * l * D : scratch;
         if (sch->sk_wt < D) CK(c, cudaMemsetAsync(skc, 0, (size_t)cnt * 2 * l * D * sizeof(int16_t), c->stream));
-        left.msgs = right.msgs = d_seeds;
-        left.off = right.off = d_off + start;
-        left.n = right.n = cnt;
-        left.dense_stride = right.dense_stride = (int64_t)2 * l * D;
+        left.msgs = d_seeds;
+        left.off = d_off + start;
+        left.n = 2 * cnt;
+        left.dense_stride = (int64_t)l * D;
         left.out_dense = skc;
-        right.out_dense = skc + (int64_t)l * D;
         CK(c, sampler_scratch(c, left));
         CK(c, timed(c, K_SAMPLER, [&] { return launch_sampler(left, c->stream); }));
-        CK(c, sampler_scratch(c, right));
-        CK(c, timed(c, K_SAMPLER, [&] { return launch_sampler(right, c->stream); }));
         CK(c, timed(c, K_MATVEC, [&] {
             return launch_matvec(c->ring, skc, cnt * 2, d_sk_ntt ? d_sk_ntt + start * 2 * l * D : nullptr,
                                  d_vk_ntt ? d_vk_ntt + start * 2 * D : nullptr,

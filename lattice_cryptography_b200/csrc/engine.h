@@ -17,6 +17,11 @@ struct SamplerArgs {
     int shared_msg;
     alignas(8) uint8_t salt[SALT_BYTES];
     int salt_len;
+    // paired mode (key generation): stream j hashes item j >> 1 under salt (j even) or salt2 (j odd), so the two
+    // halves of a key are sampled by ONE launch of 2 * items streams; n counts streams
+    alignas(8) uint8_t salt2[SALT_BYTES];
+    int salt2_len;
+    int paired;
     int secpar, bd, wt, vec_len;
     int idx_bits;              // LOGD + secpar
     int mag_bits;              // btd - 1

@@ -83,8 +83,10 @@ __global__ void __launch_bounds__(P) k_sampler(SamplerArgs a) {
     fill_weight_table(wtab, a.wt, a.bd, pieces);
     __syncthreads();
 
-    const InputView iv{reinterpret_cast<const uint32_t*>(a.salt), a.salt_len, a.msgs + a.off[inst],
-                       a.off[inst + 1] - a.off[inst]};
+    const int64_t item = a.paired ? inst >> 1 : inst;
+    const bool second = a.paired && (inst & 1);
+    const InputView iv{reinterpret_cast<const uint32_t*>(second ? a.salt2 : a.salt), second ? a.salt2_len : a.salt_len,
+                       a.msgs + a.off[item], a.off[item + 1] - a.off[item]};
     const DecodeParams dp{a.bd, a.wt, a.vec_len, a.idx_bits, a.mag_bits, a.pad_bits};
     const StreamCols sc{ring + tid, bmap + tid, P, mutab, r16tab, wtab, pieces, a.idx_scratch + inst_raw, a.idx_stride};
     int16_t* dense = a.out_dense ? a.out_dense + inst * a.dense_stride : nullptr;
