@@ -37,6 +37,27 @@ def _secpar_msg(secpar, middle: str) -> str:
     return INVALID_DATA_VALUES_ERR + f' Input security parameter must be{middle} {ALLOWABLE_SECPARS} but had {secpar}.'
 
 
+# Opt-in: when True, str() of a verification key / public statement is a digest of its CONTENT
+# instead of CPython's address-based default (reference one_time_keys.py:197-237 defines no __str__).  The string
+# is part of every challenge hash input (lm_one_time_sigs.py:148, adaptor_sigs.py:176,
+# bklm_one_time_agg_sigs.py:65), so switching it on changes the signatures - and makes them verifiable against a
+# pickled / re-created key object, which the reference's signatures are not.  Off by default.
+CONTENT_STR: bool = False
+
+
+def set_content_str(on: bool) -> None:
+    global CONTENT_STR
+    CONTENT_STR = bool(on)
+
+
+def _content_digest(name: str, secpar: int, polys) -> str:
+    from hashlib import shake_256
+    h = shake_256(name.encode() + secpar.to_bytes(2, 'little'))
+    for f in polys:
+        h.update(f.coef.astype('<i2').tobytes())       # centred coefficients, natural order, little-endian int16
+    return f'<{name} {h.hexdigest(16)}>'
+
+
 class _Comparable(object):
     """__eq__/__bool__ over a fixed tuple of attribute names (the reference compares attribute by attribute)."""
     _fields = ()
@@ -92,6 +113,9 @@ class OneTimePublicStatement(_Comparable):
         self.secpar, self.lp, self.key = secpar, lp, key
         self.key.const_time_flag = False         # public material: reference one_time_keys.py:126
 
+    def __repr__(self) -> str:          # str() falls back to this; repr() is what str(list(...)) uses (BKLM)
+        return _content_digest('OneTimePublicStatement', self.secpar, [self.key]) if CONTENT_STR else object.__repr__(self)
+
 
 class _LeftRight(_Comparable):
     """A (left_key, right_key) pair addressed as [0] / [1]."""
@@ -137,6 +161,11 @@ class OneTimeVerificationKey(_LeftRight):
         elif left_key.lp != lp or right_key.lp != lp:
             raise ValueError(SECWIT_INST_ERR_LP_MISMATCH)
         self._install(secpar, lp, left_key, right_key)
+
+    def __repr__(self) -> str:          # str() falls back to this; repr() is what str(list(...)) uses (BKLM)
+        if CONTENT_STR:
+            return _content_digest('OneTimeVerificationKey', self.secpar, [self.left_key, self.right_key])
+        return object.__repr__(self)
 
 
 def bits_per_index_set(secpar: int, degree: int, wt: int) -> int:

@@ -13,6 +13,10 @@ module is therefore OPT-IN and does not change what the drop-in API computes:
   the GPU with the reference's own distribution parameters (bd = q//2, wt = d), so that two parties derive
   the same row from a short public string.
 
+* `one_time_keys.set_content_str(True)` (re-exported here as `set_content_str`): `str()` / `repr()` of
+  verification keys and public statements become content digests, so signatures verify against pickled or
+  re-created key objects (changes the challenge bytes, hence every signature; off by default).
+
 Bit layout (include/lcb200.h): value i of a polynomial at bit offset i*bits, least significant bit first.
 """
 from math import ceil, log2
@@ -21,7 +25,7 @@ from typing import Any, Dict
 import numpy as np
 
 from .lattice_algebra import PolynomialVector, engine_for
-from .one_time_keys import SchemeParameters
+from .one_time_keys import SchemeParameters, set_content_str  # noqa: F401
 
 KEY_CH_SALT = 'KEY_CH_SALT'
 

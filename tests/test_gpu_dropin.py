@@ -50,6 +50,35 @@ def test_lm_dropin_identities(secpar):
         lm.keygen_core(pp=pp, num_keys_to_gen=2, seeds=seeds)
 
 
+def test_content_str_mode_survives_pickling():
+    """Opt-in content-based str(otvk) (one_time_keys.set_content_str): a signature then verifies against a
+    pickled copy of the key; with the reference's address-based default it does not."""
+    import pickle
+    from lattice_cryptography_b200 import bklm_one_time_agg_sigs as bk
+    from lattice_cryptography_b200 import lm_one_time_sigs as lm
+    from lattice_cryptography_b200 import one_time_keys as otk
+    pp = lm.make_setup_parameters(128)
+    key = lm.keygen(pp=pp, num_keys_to_gen=1)[0]
+    sig = lm.sign(pp=pp, otk=key, msg='0110')
+    assert lm.verify(pp=pp, otvk=pickle.loads(pickle.dumps(key[2])), msg='0110', sig=sig) is False
+    otk.set_content_str(True)
+    try:
+        sig = lm.sign(pp=pp, otk=key, msg='0110')
+        clone = pickle.loads(pickle.dumps(key[2]))
+        assert lm.verify(pp=pp, otvk=clone, msg='0110', sig=sig) is True
+        assert lm.verify(pp=pp, otvk=clone, msg='0111', sig=sig) is False
+        # BKLM builds its aggregation message from repr() of the keys inside a list
+        bpp = bk.make_setup_parameters(128)
+        keys = lm.keygen(pp=bpp, num_keys_to_gen=2)
+        msgs = ['0101', '1100']
+        sigs = [lm.sign(pp=bpp, otk=k, msg=m) for k, m in zip(keys, msgs)]
+        ag = bk.aggregate(pp=bpp, otvks=[k[2] for k in keys], msgs=msgs, sigs=sigs)
+        clones = [pickle.loads(pickle.dumps(k[2])) for k in keys]
+        assert bk.aggregate_verify(pp=bpp, otvks=clones, msgs=msgs, ag_sig=ag) is True
+    finally:
+        otk.set_content_str(False)
+
+
 def test_lm_dropin_matches_oracle():
     """Same key_ch, seed and full hash input -> same keys, challenge and signature as the CPU oracle."""
     import schemes

@@ -40,8 +40,19 @@ def test_key_objects_pickle_and_index():
     seed2, sk2, vk2 = pickle.loads(pickle.dumps((seed, sk, vk)))
     assert seed2 == seed and sk2 == sk and vk2 == vk
     assert sk2[0] == sk.left_key and vk2[1] == vk.right_key
-    # as in the reference, str() of a key is its identity, so the copy is a different signer
-    assert str(vk2) != str(vk)
+    # as in the reference, str() of a key is its identity, so the copy is a different signer ...
+    assert str(vk2) != str(vk) and ' object at 0x' in str(vk)
+    # ... unless the opt-in content-based form is switched on
+    from lattice_cryptography_b200 import one_time_keys as otk
+    otk.set_content_str(True)
+    try:
+        assert str(vk2) == str(vk) == repr(vk) and str(vk).startswith('<OneTimeVerificationKey ')
+        other = OneTimeVerificationKey(secpar=128, lp=lp, left_key=Polynomial(lp=lp, coefs={1: 1}),
+                                       right_key=Polynomial(lp=lp, coefs={2: 1}))
+        assert str(other) != str(vk) and str([vk])[1:-1] == str(vk)
+    finally:
+        otk.set_content_str(False)
+    assert ' object at 0x' in str(vk)
 
 
 def test_random_seed_batch_shape_and_alphabet():
