@@ -543,7 +543,9 @@ def engine_arm(a):
             'gpu_launches': launches,
             'clocks': clk,
             'setup': {'keygen_s': t_keygen, 'sign_s': t_sign, 'keygen_keys_per_s': n / t_keygen,
-                      'sign_sigs_per_s': n / t_sign},
+                      'sign_sigs_per_s': n / t_sign,
+                      'note': 'cold first calls of this process (memory-pool growth and output allocation inside); '
+                              'warm rates are in secondary and profiles/README.md'},
         }
         # instruction-issue view of the same kernel: warp-instructions per verify from the ncu count of this
         # build (profiles/prof_r1_verify.summary.txt: 992.49 M for 2^18 verifies), against the issue limit of
