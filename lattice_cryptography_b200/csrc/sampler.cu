@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(SBS) k_shake256(const uint8_t* __restrict__ in
 // Fused SHAKE256 squeeze + decode2polycoefs (sampler_device.cuh), one stream per thread.
 // Shared memory per block: ring [54][P] u32, bmap [8][P] u32, two modulus tables, the piece-weight table.
 template <int P>   // streams (threads) per block; compile-time so that column addressing is shifts, not multiplies
-__global__ void __launch_bounds__(P) k_sampler(SamplerArgs a) {
+__global__ void __launch_bounds__(P, 640 / P) k_sampler(SamplerArgs a) {   // 5 x 128 streams resident per SM
     extern __shared__ uint32_t smem[];
     uint32_t* ring = smem;                       // [RING_WORDS][P]
     uint32_t* bmap = ring + RING_WORDS * P;      // [8][P]   (directly after the ring, see StreamCols)

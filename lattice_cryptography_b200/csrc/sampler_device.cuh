@@ -51,6 +51,37 @@ struct InputView {
         }
         return v;
     }
+    // One whole 136-byte rate block (stream words 34*blk .. 34*blk+33) into the shared-memory column `col`
+    // (element w at col[w * P]).  Because 136 is a multiple of 4, every stream word of every block sits at
+    // the same byte phase of the message: 35 aligned, mutually independent loads (batched by the compiler,
+    // one round trip instead of 34 dependent ones) and 34 funnel shifts produce the interior words; only the
+    // words that touch the salt, the end of the message or the padding are patched through word_at().
+    __device__ __forceinline__ void load_block(int64_t blk, int64_t tot, int64_t last, uint32_t* col, int P) const {
+        const int64_t k0 = blk * RATE_WORDS;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(msg) + (uintptr_t)(4 * k0 - salt_len);   // stream byte 4*k0
+        const uint32_t* aw = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        const unsigned sh = (unsigned)(a & 3) * 8;
+        // an aligned word may be read iff it overlaps [msg, msg + msg_len)
+        const uintptr_t lo = reinterpret_cast<uintptr_t>(msg), hi = lo + (uintptr_t)msg_len;
+        uint32_t prev;
+        {
+            const uintptr_t x = reinterpret_cast<uintptr_t>(aw);
+            prev = (x + 4 > lo && x < hi) ? __ldg(aw) : 0u;
+        }
+#pragma unroll
+        for (int w = 0; w < RATE_WORDS; ++w) {
+            const uintptr_t x = reinterpret_cast<uintptr_t>(aw + w + 1);
+            const uint32_t next = (x + 4 > lo && x < hi) ? __ldg(aw + w + 1) : 0u;
+            col[w * P] = __funnelshift_r(prev, next, sh);
+            prev = next;
+        }
+        const int64_t ks = ((int64_t)salt_len + 3) >> 2;          // stream words [0, ks) touch the salt
+        for (int64_t k = k0; k < ks && k < k0 + RATE_WORDS; ++k) col[(k - k0) * P] = word_at(k, tot, last);
+        const int64_t kt = tot >> 2;                               // the word that holds the 0x1F marker
+        if (kt >= k0 && kt < k0 + RATE_WORDS) col[(kt - k0) * P] = word_at(kt, tot, last);
+        for (int64_t k = (kt + 1 > k0 ? kt + 1 : k0); k < k0 + RATE_WORDS; ++k)
+            col[(k - k0) * P] = (k == (last >> 2)) ? 0x80000000u : 0u;
+    }
 };
 
 struct DecodeParams {
@@ -145,8 +176,7 @@ __device__ __forceinline__ void sample_stream(const DecodeParams& dp, const Inpu
             do {
                 if (in_blk < in_blocks) {
                     // the not-yet-valid part of the window doubles as staging for the input block
-                    for (int w = 0; w < RATE_WORDS; ++w)
-                        sc.ring[(keep + w) * P] = iv.word_at(in_blk * RATE_WORDS + w, in_total, in_last);
+                    iv.load_block(in_blk, in_total, in_last, sc.ring + keep * P, P);
 #pragma unroll
                     for (int i = 0; i < 17; ++i) {
                         s.lo[i] ^= sc.ring[(keep + 2 * i) * P];
