@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(P, 640 / P) k_sampler(SamplerArgs a) {   // 5 
     const int64_t inst_raw = (int64_t)blockIdx.x * P + tid;
     const bool live = inst_raw < a.n;
     const int64_t inst = live ? inst_raw : a.n - 1;
-    fill_mod_tables(mutab, r16tab);
+    fill_mod_tables(mutab, r16tab, a.wt);
     fill_weight_table(wtab, a.wt, a.bd, pieces);
     __syncthreads();
 

@@ -61,17 +61,15 @@ struct InputView {
         const uintptr_t a = reinterpret_cast<uintptr_t>(msg) + (uintptr_t)(4 * k0 - salt_len);   // stream byte 4*k0
         const uint32_t* aw = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
         const unsigned sh = (unsigned)(a & 3) * 8;
-        // an aligned word may be read iff it overlaps [msg, msg + msg_len)
-        const uintptr_t lo = reinterpret_cast<uintptr_t>(msg), hi = lo + (uintptr_t)msg_len;
-        uint32_t prev;
-        {
-            const uintptr_t x = reinterpret_cast<uintptr_t>(aw);
-            prev = (x + 4 > lo && x < hi) ? __ldg(aw) : 0u;
-        }
+        // an aligned word may be read iff it overlaps [msg, msg + msg_len): word indices [j_lo, j_hi) of aw[]
+        const int64_t first = (int64_t)((reinterpret_cast<uintptr_t>(msg) & ~(uintptr_t)3) - reinterpret_cast<uintptr_t>(aw)) >> 2;
+        const int64_t end = (int64_t)(reinterpret_cast<uintptr_t>(msg) + (uintptr_t)msg_len + 3 - reinterpret_cast<uintptr_t>(aw)) >> 2;
+        const int j_lo = (int)(first < 0 ? 0 : (first > RATE_WORDS + 1 ? RATE_WORDS + 1 : first));
+        const int j_hi = msg_len > 0 ? (int)(end < 0 ? 0 : (end > RATE_WORDS + 1 ? RATE_WORDS + 1 : end)) : 0;
+        uint32_t prev = (0 >= j_lo && 0 < j_hi) ? __ldg(aw) : 0u;
 #pragma unroll
         for (int w = 0; w < RATE_WORDS; ++w) {
-            const uintptr_t x = reinterpret_cast<uintptr_t>(aw + w + 1);
-            const uint32_t next = (x + 4 > lo && x < hi) ? __ldg(aw + w + 1) : 0u;
+            const uint32_t next = (w + 1 >= j_lo && w + 1 < j_hi) ? __ldg(aw + w + 1) : 0u;
             col[w * P] = __funnelshift_r(prev, next, sh);
             prev = next;
         }
@@ -107,8 +105,9 @@ struct StreamCols {
     int64_t idx_stride;
 };
 
-__device__ __forceinline__ void fill_mod_tables(uint32_t* mutab, uint32_t* r16tab) {
-    for (int m = 1 + threadIdx.x; m <= 256; m += blockDim.x) {
+// Only the rows a sampler call can touch: the index moduli D-wt+1 .. D-1 (bd keeps its constants in registers).
+__device__ __forceinline__ void fill_mod_tables(uint32_t* mutab, uint32_t* r16tab, int wt) {
+    for (int m = max(1, D - wt + 1) + (int)threadIdx.x; m <= D; m += blockDim.x) {
         mutab[m] = 0xFFFFFFFFu / (uint32_t)m;
         r16tab[m] = 65536u % (uint32_t)m;
     }
