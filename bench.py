@@ -162,17 +162,22 @@ def build_inputs(a, rank, torch, np):
 # Secondary measurements (BASELINE.json configs[2..4] at sizes that keep the default run short).  Timed
 # with CUDA events on the engine's stream, max over ranks; none of them is the headline metric.
 def _timed(torch, dist, world, dev, fn, reps=3):
+    """Median device time of `reps` calls after one warm-up call (max over ranks).  The median keeps a one-off
+    allocator hiccup (torch or the stream-ordered pool growing) out of the secondary figures."""
     fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
-    e0.record()
+    times = []
     for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         fn()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    times.sort()
+    ms = torch.tensor([times[len(times) // 2]], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     return float(ms.item())
@@ -205,7 +210,7 @@ def secondary_keygen_sign(a, rank, local, world, torch, np, dist):
         _, sk_ntt, vk_ntt, _ = eng.lm_keygen(sch, d_seeds, want_sk_coef=False, want_vk_coef=False, device=True)
         out['sig'] = eng.lm_sign(sch, sk_ntt, d_ch, device=True)
         out['vk'] = vk_ntt
-    ms = _timed(torch, dist, world, dev, run, reps=2)
+    ms = _timed(torch, dist, world, dev, run, reps=3)
     ok = bool(eng.lm_verify(sch, out['vk'], d_ch, out['sig'], p['vf_bd'], p['vf_wt'], device=True).all().item())
     eng.close()
     perms = 2 * 2853 + 26

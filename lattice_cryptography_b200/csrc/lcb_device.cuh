@@ -78,6 +78,18 @@ struct LaneTwF {                // per-lane stages 5..8, same indexing as LaneTw
     uint32_t w[15];
     float wq[15], cst[15];
     uint32_t kw[15];
+    __device__ __forceinline__ void get(int k, uint32_t& w_, float& wq_, float& cst_, uint32_t& kw_) const {
+        w_ = w[k]; wq_ = wq[k]; cst_ = cst[k]; kw_ = kw[k];
+    }
+};
+// The same 15 twiddles read from a shared-memory row {w, wq, cst, kw}[15] at every use (one LDS.128 each):
+// frees 60 registers per thread at the price of 15 shared loads per transform.
+struct LaneTwFShared {
+    const uint4* row;
+    __device__ __forceinline__ void get(int k, uint32_t& w_, float& wq_, float& cst_, uint32_t& kw_) const {
+        const uint4 v = row[k];
+        w_ = v.x; wq_ = __uint_as_float(v.y); cst_ = __uint_as_float(v.z); kw_ = v.w;
+    }
 };
 
 // Device-resident tables of one ctx.
@@ -263,8 +275,9 @@ __device__ __forceinline__ uint32_t fp_mul(uint32_t yb, uint32_t w, float wq, fl
 // Forward transform of RAW centred int16 coefficients with FP32-assisted butterflies.  Values stay biased
 // throughout (inputs x + cq < 2^17, +4q per stage: < 2^17 + 32 q < 2^21 < 2^23); outputs are UNBIASED lazy
 // values < 2^21 PLUS FP_BIAS in layout B (what ntt_fwd_256 would deliver, up to multiples of q, plus the bias).
+template <typename TW>
 __device__ __forceinline__ void ntt_fwd_256_fp(const int (&x)[EPT], uint32_t (&r)[EPT], const ModQ& m,
-                                               const StageConstF& sc, const LaneTwF& tw, uint32_t* xb, int lane) {
+                                               const StageConstF& sc, const TW& tw, uint32_t* xb, int lane) {
     // stage 1: only the multiplied operands are biased explicitly; the others take the input offset
     // inside the butterfly's 3-input adds
 #pragma unroll
@@ -294,7 +307,10 @@ __device__ __forceinline__ void ntt_fwd_256_fp(const int (&x)[EPT], uint32_t (&r
         for (int j = 0; j < EPT; ++j) {
             if (j & len) continue;
             const int k = base + (j >> (9 - s));
-            const uint32_t t = fp_mul(r[j + len], tw.w[k], tw.wq[k], tw.cst[k], tw.kw[k], m);
+            uint32_t w_, kw_;
+            float wq_, cst_;
+            tw.get(k, w_, wq_, cst_, kw_);
+            const uint32_t t = fp_mul(r[j + len], w_, wq_, cst_, kw_, m);
             r[j + len] = r[j] + m.q4 - t;
             r[j] = r[j] + t + m.zero;
         }

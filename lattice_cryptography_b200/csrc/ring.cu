@@ -223,7 +223,21 @@ __global__ void __launch_bounds__(RBS) k_poly_mul(ModQ m, StageConst sc, const N
 
 // ------------------------------------------------------------------------------------------------
 // y = key_ch * v  (v: nvec coefficient-form vectors of l polynomials)
-__global__ void __launch_bounds__(RBS, 3) k_matvec(ModQ m, StageConst sc, StageConstF scf, const NttTables* __restrict__ tab,
+// FP32-assisted per-lane twiddles of stages 5..8 in SHARED memory ({w, wq, cst, kw} per entry, one LDS.128 per
+// use): 60 registers fewer than keeping them resident, which buys a fourth resident block per SM.
+constexpr int TW_ROW = 15;           // uint4 per lane: 60-word pitch, conflict-free LDS.128
+constexpr int TW_BYTES = LANES * TW_ROW * 16;
+__device__ __forceinline__ void fill_tw_shared(uint4* twtab, const NttTables* __restrict__ tab) {
+    for (int e = threadIdx.x; e < LANES * 15; e += blockDim.x) {
+        const int ln = e / 15, i = e % 15;
+        const int k = i == 0 ? 16 + ln : (i < 3 ? 32 + 2 * ln + (i - 1) : (i < 7 ? 64 + 4 * ln + (i - 3) : 128 + 8 * ln + (i - 7)));
+        twtab[ln * TW_ROW + i] = make_uint4(__ldg(tab->w + k), __float_as_uint(__ldg(tab->f_wq + k)),
+                                            __float_as_uint(__ldg(tab->f_cst + k)), __ldg(tab->f_kw + k));
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(RBS, 4) k_matvec(ModQ m, StageConst sc, StageConstF scf, const NttTables* __restrict__ tab,
                                                 const uint32_t* __restrict__ a_hat_g, int l,
                                                 const int16_t* __restrict__ vec_coef, int64_t nvec,
                                                 uint16_t* __restrict__ vec_ntt, uint16_t* __restrict__ y_ntt,
@@ -233,8 +247,9 @@ __global__ void __launch_bounds__(RBS, 3) k_matvec(ModQ m, StageConst sc, StageC
     uint32_t* xbuf = smem + l * AROW;
     copy_a_hat(a_hat, a_hat_g, l);
     const HalfWarp h = half_warp(xbuf);
-    LaneTwF twf;
-    load_lane_tw_f(twf, tab, h.lane);
+    uint4* twtab = reinterpret_cast<uint4*>(xbuf + (RBS / 32) * XWARP);
+    fill_tw_shared(twtab, tab);
+    const LaneTwFShared twf{twtab + h.lane * TW_ROW};
     for (int64_t base = (int64_t)blockIdx.x * HWB; base < nvec; base += (int64_t)gridDim.x * HWB) {
         const int64_t raw = base + h.slot;
         const bool live = raw < nvec;
@@ -322,8 +337,10 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+constexpr int VERIFY_BLOCKS = 4;     // resident blocks per SM k_verify is compiled for
+
 template <bool CHECK_WT>   // weight test compiled out when wt >= d (every shipped parameter set: vf_wt = d)
-__global__ void __launch_bounds__(RBS, 3) k_verify(ModQ m, StageConst sc, StageConstF scf, const NttTables* __restrict__ tab,
+__global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageConst sc, StageConstF scf, const NttTables* __restrict__ tab,
                                                 const uint32_t* __restrict__ a_hat_g, int l,
                                                 const int16_t* __restrict__ vec_coef,
                                                 const uint16_t* __restrict__ vk_ntt,
@@ -338,8 +355,9 @@ __global__ void __launch_bounds__(RBS, 3) k_verify(ModQ m, StageConst sc, StageC
     copy_a_hat(a_hat, a_hat_g, l);
     const HalfWarp h = half_warp(xbuf);
     unsigned char* stage = stage_base + h.slot * STAGE_HALF_BYTES;
-    LaneTwF twf;
-    load_lane_tw_f(twf, tab, h.lane);                // FP32-assisted twiddles, in registers for the life of the kernel
+    uint4* twtab = reinterpret_cast<uint4*>(stage_base + HWB * STAGE_HALF_BYTES);
+    fill_tw_shared(twtab, tab);
+    const LaneTwFShared twf{twtab + h.lane * TW_ROW};
     // The FP32-assisted transform returns biased values (r + FP_BIAS); the row-vector product then carries
     // FP_BIAS * sum_i a_hat[i][slot], removed once per slot before the comparison.
     uint32_t corr[EPT];
@@ -621,7 +639,7 @@ inline unsigned persistent_grid(int64_t items, int per_block, int num_sms, int r
 }
 
 inline size_t ring_smem(int l) { return (size_t)l * AROW * 4 + (size_t)(RBS / 32) * XWARP * 4; }
-inline size_t verify_smem(int l) { return ring_smem(l) + (size_t)HWB * STAGE_HALF_BYTES; }
+inline size_t verify_smem(int l) { return ring_smem(l) + (size_t)HWB * STAGE_HALF_BYTES + (size_t)TW_BYTES; }
 
 template <typename K>
 cudaError_t allow_smem(K kernel, size_t smem) {
@@ -662,7 +680,7 @@ cudaError_t launch_poly_mul(const RingCtx& c, const int16_t* a, const int16_t* b
 cudaError_t launch_matvec(const RingCtx& c, const int16_t* vec_coef, int64_t nvec, uint16_t* vec_ntt,
                           uint16_t* y_ntt, int16_t* y_coef, cudaStream_t st) {
     if (nvec <= 0) return cudaSuccess;
-    size_t smem = ring_smem(c.l);
+    size_t smem = ring_smem(c.l) + TW_BYTES;
     cudaError_t e = allow_smem(k_matvec, smem);
     if (e != cudaSuccess) return e;
     unsigned grid = persistent_grid(nvec, HWB, c.num_sms, resident_blocks(k_matvec, RBS, smem));
