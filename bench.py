@@ -532,9 +532,9 @@ def engine_arm(a):
             'roofline': {'bound': 'hbm', 'kernel': 'k_verify', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak,
                          # DRAM bytes per launch from the ncu --set full capture of this kernel
-                         # (profiles/prof_r1_verify.summary.txt: 2.0344 GB read + 6.9 MB written for 2^18
-                         # verifies = 7,787 B per verify), scaled to this launch's batch
-                         'traffic': 7787 * n if a.secpar == 128 else None,
+                         # (profiles/prof_r1_verify.summary.txt: 2.0344 GB read + 5.0 MB written for 2^18
+                         # verifies = 7,780 B per verify), scaled to this launch's batch
+                         'traffic': 7780 * n if a.secpar == 128 else None,
                          'algorithmic_bytes_per_launch': unit_bytes * n,
                          'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback',
                          'algorithmic_bytes_per_unit': unit_bytes,
@@ -553,9 +553,9 @@ def engine_arm(a):
                               'warm rates are in secondary and profiles/README.md'},
         }
         # instruction-issue view of the same kernel: warp-instructions per verify from the ncu count of this
-        # build (profiles/prof_r1_verify.summary.txt: 992.49 M for 2^18 verifies), against the issue limit of
+        # build (profiles/prof_r1_verify.summary.txt: 1,004.7 M for 2^18 verifies), against the issue limit of
         # 4 schedulers x 148 SMs x 1 warp-instruction per clock at the max clock
-        instr_per_unit = 32 * 3786 if a.secpar == 128 else None
+        instr_per_unit = 32 * 3833 if a.secpar == 128 else None
         clk_hz = ((clk or {}).get('sm_max_mhz') or 1965.0) * 1e6
         if instr_per_unit:
             achieved_t = instr_per_unit * n / (k_ms * 1e-3) / 1e12
@@ -563,7 +563,7 @@ def engine_arm(a):
             line['roofline']['int_pipe'] = {
                 'thread_instr_per_unit': instr_per_unit, 'achieved_tinstr_s': achieved_t,
                 'issue_peak_tinstr_s': issue_peak, 'issue_frac': achieved_t / issue_peak,
-                'ncu_pipe_utilisation': {'issue_active': 0.734, 'alu': 0.505, 'fma': 0.351, 'lsu': 0.263},
+                'ncu_pipe_utilisation': {'issue_active': 0.751, 'alu': 0.523, 'fma': 0.355, 'lsu': 0.342},
                 'note': 'k_verify is bound by instruction issue: 5-instruction FP32-assisted butterflies spread '
                         'over the ALU, FMA-heavy and FMA-lite pipes (DESIGN.md 3.3)'}
         if cpu is not None:
