@@ -82,6 +82,30 @@ def reference_arm(a):
 
 
 # ---------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU, BEFORE any pinned host buffer is
+    allocated: the end-to-end legs stream 6-8 GB per step from pinned memory, and first-touch placement on the
+    GPU's own NUMA node keeps that traffic off the inter-socket link.  Best effort; returns what it did."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(('GPU-' + str(torch.cuda.get_device_properties(local).uuid)).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler(object):
     """SM clock / power / throttle reasons sampled every 5 ms by NVML in a thread DURING the timed region."""
     REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
@@ -354,6 +378,7 @@ def engine_arm(a):
     from lattice_cryptography_b200 import Engine, make_scheme
 
     torch.cuda.set_device(local)
+    numa_cpus = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
     eng = Engine(a.secpar, p['q'], D, p['l'], device=local)
@@ -543,7 +568,7 @@ def engine_arm(a):
                          'note': 'k_verify is integer-issue bound by design (see DESIGN.md); HBM fraction is the '
                                  'contract figure, int-pipe figures are in int_pipe'},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'steps': a.e2e_steps},
+                    'steps': a.e2e_steps, 'host_cpus_bound_per_rank': numa_cpus},
             'e2e_packed': e2e_packed,
             'gpu_launches': launches,
             'clocks': clk,
