@@ -473,3 +473,45 @@ def test_sampler_field_widths_vs_c_oracle(secpar):
                 assert np.array_equal(dense[i], od), (secpar, bd, wt, i)
     finally:
         e.close()
+
+
+# ------------------------------------------------------------------------------------------- absorb edge cases
+@pytest.mark.parametrize('salt', ['S', 'SALT', 'SALT_XY', 'SALT_12CHARS'])
+def test_absorb_block_boundaries_vs_c_oracle(engines, salt):
+    """Every message length around the 136-byte rate boundaries (salt + message = 135..138, 271..274, 407..409,
+    plus the empty message), at every byte alignment of the message inside the blob: the batched block loader of
+    the sampler (sampler_device.cuh, InputView::load_block) against oracle/lcb_oracle.c's byte-wise sponge."""
+    import c_oracle
+    e = engines[128]
+    rng = np.random.default_rng(len(salt))
+    targets = [0, 1, 2, 3, 4, 5] + [t - len(salt) + d for t in (136, 272, 408) for d in (-3, -2, -1, 0, 1, 2, 3)]
+    lens = sorted({n for n in targets if n >= 0})
+    msgs = []
+    for n in lens:
+        for _ in range(4):            # four copies at different blob offsets (the pad strings shift the alignment)
+            msgs.append(bytes(rng.integers(0, 256, n, dtype=np.uint8)))
+            msgs.append(bytes(rng.integers(0, 256, int(rng.integers(0, 4)), dtype=np.uint8)))
+    dense, pairs = e.hash2polyvec(salt, msgs, 1, 20, 1, want_pairs=True)
+    for i, m in enumerate(msgs):
+        want, want_pairs = c_oracle.hash2polyvec(128, D, salt, m, 1, 20, 1)
+        assert np.array_equal(dense[i], want) and np.array_equal(pairs[i], want_pairs), (salt, len(m), i)
+
+
+def test_keygen_seed_lengths_across_block_boundary(engines, golden):
+    """Paired key-generation launch: SK_SALTLEFT (11 bytes) and SK_SALTRIGHT (12 bytes) put the two halves of one
+    key on different sides of a rate boundary for seeds of 124 / 260 bytes - lanes of one warp then absorb a
+    different number of blocks."""
+    import c_oracle
+    arrays, _ = golden
+    for secpar, base in ((128, 120), (256, 256)):
+        s = SHIPPED[secpar]
+        e = engines[secpar]
+        p = c_oracle.params(secpar, s['q'], s['l'], s['sk_bd'], s['ch_wt'])
+        key_ch = np.ascontiguousarray(arrays[f's{secpar}_key_ch'])
+        rng = np.random.default_rng(secpar)
+        seeds = [''.join(rng.choice(['0', '1'], base + k)) for k in range(0, 10)]
+        sk_coef, _, _, vk_coef = e.lm_keygen(scheme(secpar), seeds)
+        for i in (0, 3, 4, 5, 9):
+            skl, skr, vkl, vkr = c_oracle.lm_keygen(p, key_ch, seeds[i].encode())
+            assert np.array_equal(skl, sk_coef[i, 0]) and np.array_equal(skr, sk_coef[i, 1]), (secpar, len(seeds[i]))
+            assert np.array_equal(vkl, vk_coef[i, 0]) and np.array_equal(vkr, vk_coef[i, 1])
