@@ -79,14 +79,16 @@ __global__ void __launch_bounds__(P, 640 / P) k_sampler(SamplerArgs a) {   // 5 
     const int64_t inst_raw = (int64_t)blockIdx.x * P + tid;
     const bool live = inst_raw < a.n;
     const int64_t inst = live ? inst_raw : a.n - 1;
+    // the offsets of this stream's input are requested first, so that their latency hides behind the table fill
+    const int64_t item = a.paired ? inst >> 1 : inst;
+    const bool second = a.paired && (inst & 1);
+    const int64_t msg_begin = __ldg(a.off + item), msg_end = __ldg(a.off + item + 1);
     fill_mod_tables(mutab, r16tab, a.wt);
     fill_weight_table(wtab, a.wt, a.bd, pieces);
     __syncthreads();
 
-    const int64_t item = a.paired ? inst >> 1 : inst;
-    const bool second = a.paired && (inst & 1);
     const InputView iv{reinterpret_cast<const uint32_t*>(second ? a.salt2 : a.salt), second ? a.salt2_len : a.salt_len,
-                       a.msgs + a.off[item], a.off[item + 1] - a.off[item]};
+                       a.msgs + msg_begin, msg_end - msg_begin};
     const DecodeParams dp{a.bd, a.wt, a.vec_len, a.idx_bits, a.mag_bits, a.pad_bits};
     const StreamCols sc{ring + tid, bmap + tid, P, mutab, r16tab, wtab, pieces, a.idx_scratch + inst_raw, a.idx_stride};
     int16_t* dense = a.out_dense ? a.out_dense + inst * a.dense_stride : nullptr;

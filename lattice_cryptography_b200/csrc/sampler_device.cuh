@@ -159,7 +159,8 @@ __device__ __forceinline__ void sample_stream(const DecodeParams& dp, const Inpu
                                               Emit&& emit) {
     const int P = sc.pitch;
     const int64_t in_total = iv.total();
-    const int64_t in_blocks = in_total / 136 + 1;      // the pad byte always needs room
+    // the pad byte always needs room; 32-bit division whenever the input is shorter than 4 GiB
+    const int64_t in_blocks = (in_total >> 32) == 0 ? (int64_t)((uint32_t)in_total / 136u) + 1 : in_total / 136 + 1;
     const int64_t in_last = in_blocks * 136 - 1;
     int64_t in_blk = 0;
     KeccakState s;
