@@ -242,6 +242,40 @@ def secondary_keygen_sign(a, rank, local, world, torch, np, dist):
             'keccak_gperm_s_per_gpu': n * perms / (ms * 1e-3) / 1e9, 'keccak_roofline_gperm_s': 4.28}
 
 
+def secondary_verify_secpar256(a, rank, local, world, torch, np, dist):
+    """The headline path on the other shipped parameter set: 2^18 (vk, msg, sig) triples per GPU at secpar 256
+    (q = 39937, l = 23, ch_wt = 50; 13.2 KB and 26 permutations per verify)."""
+    class A: secpar, log2n = 256, 18
+    eng, sch, p = _engine(256, local, np)
+    dev = f'cuda:{local}'
+    n = 1 << A.log2n
+    seeds, seed_off, ch, ch_off = build_inputs(A, rank, torch, np)
+    d_seeds = (torch.from_numpy(seeds).to(dev), torch.from_numpy(seed_off).to(dev))
+    d_ch = (torch.from_numpy(ch).to(dev).view(-1), torch.from_numpy(ch_off).to(dev))
+    _, sk_ntt, vk_ntt, _ = eng.lm_keygen(sch, d_seeds, want_sk_coef=False, want_vk_coef=False, device=True)
+    sig = eng.lm_sign(sch, sk_ntt, d_ch, device=True)
+    del sk_ntt
+    torch.cuda.synchronize()
+    bad = torch.arange(0, n, 64, device=dev)
+    sig.view(torch.int16)[bad, bad % p['l'], (3 * bad) % D] += 1
+    torch.cuda.synchronize()
+    verdict = torch.empty(n, dtype=torch.uint8, device=dev)
+    ms = _timed(torch, dist, world, dev, lambda: eng.lm_verify(sch, vk_ntt, d_ch, sig, p['vf_bd'], p['vf_wt'], out=verdict))
+    expect = torch.ones(n, dtype=torch.uint8, device=dev)
+    expect[bad] = 0
+    ok = bool(torch.equal(verdict, expect))
+    eng.profile(True)
+    eng.profile_reset()
+    eng.lm_verify(sch, vk_ntt, d_ch, sig, p['vf_bd'], p['vf_wt'], out=verdict)
+    v_ms, _ = eng.profile_read('verify')
+    s_ms, _ = eng.profile_read('sampler')
+    eng.profile(False)
+    eng.close()
+    return {'verifies_per_s': world * n / (ms * 1e-3), 'ms': ms, 'n_per_gpu': n, 'verdicts_as_constructed': ok,
+            'k_verify_ms': v_ms, 'k_sampler_ms': s_ms,
+            'keccak_gperm_s_per_gpu': n * 26 / (s_ms * 1e-3) / 1e9, 'keccak_roofline_gperm_s': 4.28}
+
+
 def secondary_bklm(a, rank, local, world, torch, np, dist):
     """configs[3]: aggregate + aggregate-verify of 2^k signatures per aggregate (secpar 128), the sorted list
     sharded over the ranks, ONE reduce of int32 partial sums each."""
@@ -597,7 +631,8 @@ def engine_arm(a):
     torch.cuda.empty_cache()
     secondary = {}
     if not a.no_secondary:
-        for name, fn in (('keygen_sign_secpar256', secondary_keygen_sign), ('bklm', secondary_bklm),
+        for name, fn in (('keygen_sign_secpar256', secondary_keygen_sign),
+                         ('lm_verify_secpar256', secondary_verify_secpar256), ('bklm', secondary_bklm),
                          ('adaptor', secondary_adaptor), ('single_ops', secondary_single_ops)):
             try:
                 secondary[name] = fn(a, rank, local, world, torch, np, dist)

@@ -845,8 +845,9 @@ int lcb_unpack_batch(lcb_ctx* c, const uint8_t* packed, int64_t npoly, int bits,
     return LCB_OK;
 }
 
-// lcb_lm_verify_batch on packed verification keys and signatures.  The batch is processed in chunks of 2^18
-// (unpack -> challenge sampler -> verify) so that the unpacked copies never exceed ~2 GB of scratch.
+// lcb_lm_verify_batch on packed verification keys and signatures.  The batch is processed in chunks of 2^18:
+// challenge sampler -> k_verify reading the packed rows directly (the shipped 11/14- and 13/16-bit packings), or
+// unpack -> challenge sampler -> k_verify for any other width (unpacked copies bounded to ~2 GB of scratch).
 int lcb_lm_verify_packed_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* vk_packed, int vk_bits,
                                const uint8_t* chmsg, const int64_t* chmsg_off, const uint8_t* sig_packed, int sig_bits,
                                int sig_bias, int64_t n, int bd, int wt, uint8_t* verdict) {
@@ -872,10 +873,15 @@ int lcb_lm_verify_packed_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t*
     if ((reinterpret_cast<uintptr_t>(d_vkp) | reinterpret_cast<uintptr_t>(d_sigp)) & 3u)
         return fail(c, LCB_ERR_INVALID, "packed buffers must be 4-byte aligned");
     const int64_t chunk = n < 2 * kPipeChunk ? n : 2 * kPipeChunk;
-    uint16_t* d_vk;
-    int16_t *d_sig, *d_pairs;
-    CK(c, sg.alloc((void**)&d_vk, (size_t)chunk * 2 * D * sizeof(uint16_t)));
-    CK(c, sg.alloc((void**)&d_sig, (size_t)chunk * l * D * sizeof(int16_t)));
+    // The two shipped packings (11/14 and 13/16 bits) are expanded inside k_verify; any other width is unpacked
+    // into scratch first.
+    const bool fused = (sig_bits == 11 && vk_bits == 14) || (sig_bits == 13 && vk_bits == 16);
+    uint16_t* d_vk = nullptr;
+    int16_t *d_sig = nullptr, *d_pairs;
+    if (!fused) {
+        CK(c, sg.alloc((void**)&d_vk, (size_t)chunk * 2 * D * sizeof(uint16_t)));
+        CK(c, sg.alloc((void**)&d_sig, (size_t)chunk * l * D * sizeof(int16_t)));
+    }
     CK(c, sg.alloc((void**)&d_pairs, (size_t)chunk * sch->ch_wt * 2 * sizeof(int16_t)));
     // packed signatures in HOST memory cross PCIe chunk by chunk under the kernels of the previous chunk
     std::vector<cudaEvent_t> arrived;
@@ -892,6 +898,17 @@ int lcb_lm_verify_packed_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t*
     }
     for (int64_t first = 0, k = 0; first < n; first += chunk, ++k) {
         const int64_t m = n - first < chunk ? n - first : chunk;
+        if (fused) {
+            int st = run_challenge(c, sch, d_msg, d_off + first, m, d_pairs);
+            if (st != LCB_OK) return st;
+            if (piped) CK(c, cudaStreamWaitEvent(c->stream, arrived[k], 0));
+            CK(c, timed(c, K_VERIFY, [&] {
+                return launch_verify_packed(c->ring, d_sigp + (size_t)first * sig_row, sig_bits, sig_bias,
+                                            d_vkp + (size_t)first * 2 * 32 * vk_bits, vk_bits, d_pairs, sch->ch_wt, m,
+                                            bd > 32767 ? 32767 : bd, wt, d_verdict + first, c->stream);
+            }));
+            continue;
+        }
         CK(c, timed(c, K_UNPACK, [&] {
             return launch_unpack(c->ring, d_vkp + (size_t)first * 2 * 32 * vk_bits, m * 2, vk_bits, 0, d_vk, c->stream);
         }));

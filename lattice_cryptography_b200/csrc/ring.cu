@@ -339,7 +339,21 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 constexpr int VERIFY_BLOCKS = 4;     // resident blocks per SM k_verify is compiled for
 
-template <bool CHECK_WT>   // weight test compiled out when wt >= d (every shipped parameter set: vf_wt = d)
+// 16 NTT slots of one lane from a 14-bit packed polynomial (wire.cu layout): 16 * 14 bits = exactly 7 words
+__device__ __forceinline__ void load_u14x16(uint32_t (&r)[EPT], const uint32_t* __restrict__ p) {
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) w[i] = __ldg(p + i);
+    w[7] = 0;
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) r[k] = __funnelshift_r(w[(14 * k) >> 5], w[((14 * k) >> 5) + 1], (14 * k) & 31) & 0x3FFFu;
+}
+
+// CHECK_WT: weight test, compiled out when wt >= d (every shipped parameter set: vf_wt = d).
+// SIG_BITS / VK_BITS: 0 = int16 coefficients / uint16 slots; otherwise the inputs are rows of the packed wire
+// format (wire.cu): signatures SIG_BITS bits per coefficient with bias sig_bias, keys VK_BITS (14) bits per slot.
+// The packed rows ride through the same cp.async stage buffers and are expanded on the way into registers.
+template <bool CHECK_WT, int SIG_BITS, int VK_BITS>
 __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageConst sc, StageConstF scf, const NttTables* __restrict__ tab,
                                                 const uint32_t* __restrict__ a_hat_g, int l,
                                                 const int16_t* __restrict__ vec_coef,
@@ -347,7 +361,8 @@ __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageCons
                                                 const int16_t* __restrict__ ch_pairs, int ch_wt,
                                                 const uint16_t* __restrict__ rhs_only,
                                                 const uint16_t* __restrict__ extra_rhs, int64_t n, int bd, int wt,
-                                                uint8_t* __restrict__ verdict) {
+                                                int sig_bias, uint8_t* __restrict__ verdict) {
+    constexpr int ROW_BYTES = SIG_BITS ? 32 * SIG_BITS : D * 2;
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* a_hat = smem;
     uint32_t* xbuf = smem + l * AROW;
@@ -384,10 +399,11 @@ __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageCons
         if (pf_it < trips) {
             int64_t it_item = first + pf_it * stride + h.slot;
             it_item = it_item < n ? it_item : n - 1;
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(vec_coef + (it_item * l + pf_i) * D) + 32 * h.lane;
-            unsigned char* dst = stage + pf_buf * (D * 2) + 32 * h.lane;
-            cp_async16(dst, src);
-            cp_async16(dst + 16, src + 16);
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(vec_coef) + (it_item * l + pf_i) * ROW_BYTES;
+            unsigned char* dst = stage + pf_buf * (D * 2);
+#pragma unroll
+            for (int o = 0; o < ROW_BYTES; o += 16 * LANES)
+                if (o + 16 * h.lane < ROW_BYTES) cp_async16(dst + o + 16 * h.lane, src + o + 16 * h.lane);
             if (++pf_i == l) { pf_i = 0; ++pf_it; }
             pf_buf ^= 1u;
         }
@@ -408,11 +424,30 @@ __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageCons
         for (int i = 0; i < l; ++i) {
             cp_async_wait<1>();
             __syncwarp();
-            const unsigned sp = (unsigned)__cvta_generic_to_shared(stage + cur * (D * 2) + 2 * h.lane);
             int pre[EPT];
+            if (SIG_BITS == 0) {
+                const unsigned sp = (unsigned)__cvta_generic_to_shared(stage + cur * (D * 2) + 2 * h.lane);
 #pragma unroll
-            for (int j = 0; j < EPT; ++j)      // sign-extending 16-bit shared load (plain C++ yields LDS.U16 + PRMT)
-                asm volatile("ld.shared.s16 %0, [%1];" : "=r"(pre[j]) : "r"(sp + 32 * j));
+                for (int j = 0; j < EPT; ++j)      // sign-extending 16-bit shared load (plain C++ yields LDS.U16 + PRMT)
+                    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(pre[j]) : "r"(sp + 32 * j));
+            } else {
+                // coefficient lane + 16 j sits at bit (lane + 16 j) * SIG_BITS of the row: the word offset of j is a
+                // compile-time constant on top of one of two per-lane (word, shift) pairs (16 * SIG_BITS is a
+                // multiple of 16 bits, so the in-word phase alternates between two values)
+                const unsigned row = (unsigned)__cvta_generic_to_shared(stage + cur * (D * 2));
+                const unsigned b0 = (unsigned)h.lane * SIG_BITS, b1 = b0 + 16;
+                const unsigned sp0 = row + 4 * (b0 >> 5), sp1 = row + 4 * (b1 >> 5), sh0 = b0 & 31, sh1 = b1 & 31;
+#pragma unroll
+                for (int j = 0; j < EPT; ++j) {
+                    const int c = 16 * SIG_BITS * j;              // bit offset of j relative to j = 0
+                    const bool odd = (c & 31) != 0;               // then c = 32 k + 16
+                    const unsigned a = (odd ? sp1 : sp0) + 4 * (unsigned)((c - (odd ? 16 : 0)) >> 5);
+                    uint32_t lo_w, hi_w;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lo_w) : "r"(a));
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hi_w) : "r"(a + 4));
+                    pre[j] = (int)(__funnelshift_r(lo_w, hi_w, odd ? sh1 : sh0) & ((1u << SIG_BITS) - 1)) - sig_bias;
+                }
+            }
             __syncwarp();
             issue();                            // refill the buffer just drained with polynomial (+2)
             cur ^= 1u;
@@ -440,10 +475,16 @@ __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageCons
             int cx[EPT];
             load_pairs_raw(cx, ch_pairs + item * ch_wt * 2, ch_wt, h.xb, h.lane);
             ntt_fwd_256_fp(cx, c, m, scf, twf, h.xb, h.lane);
-            load_u16x16(vl, vk_ntt + item * 2 * D + 16 * h.lane);
+            if (VK_BITS == 14) {
+                const uint32_t* vp = reinterpret_cast<const uint32_t*>(vk_ntt) + item * (2 * 112) + 7 * h.lane;
+                load_u14x16(vl, vp);
+                load_u14x16(rhs, vp + 112);
+            } else {
+                load_u16x16(vl, vk_ntt + item * 2 * D + 16 * h.lane);
+                load_u16x16(rhs, vk_ntt + item * 2 * D + D + 16 * h.lane);
+            }
 #pragma unroll
             for (int k = 0; k < EPT; ++k) acc[k] += (uint64_t)(c[k] - FP_BIAS) * (m.cq2 - vl[k]);
-            load_u16x16(rhs, vk_ntt + item * 2 * D + D + 16 * h.lane);
         } else {
             load_u16x16(rhs, rhs_only + item * D + 16 * h.lane);
         }
@@ -696,18 +737,38 @@ cudaError_t launch_sign(const RingCtx& c, const uint16_t* sk_ntt, const int16_t*
     return cudaGetLastError();
 }
 
-cudaError_t launch_verify(const RingCtx& c, const int16_t* vec_coef, const uint16_t* vk_ntt, const int16_t* ch_pairs,
-                          int ch_wt, const uint16_t* rhs_only, const uint16_t* extra_rhs, int64_t n, int bd, int wt,
-                          uint8_t* verdict, cudaStream_t st) {
+template <int SIG_BITS, int VK_BITS>
+cudaError_t launch_verify_t(const RingCtx& c, const void* vec, const void* vk, const int16_t* ch_pairs, int ch_wt,
+                            const uint16_t* rhs_only, const uint16_t* extra_rhs, int64_t n, int bd, int wt, int sig_bias,
+                            uint8_t* verdict, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     size_t smem = verify_smem(c.l);
-    auto kern = wt < D ? k_verify<true> : k_verify<false>;
+    auto kern = wt < D ? k_verify<true, SIG_BITS, VK_BITS> : k_verify<false, SIG_BITS, VK_BITS>;
     cudaError_t e = allow_smem(kern, smem);
     if (e != cudaSuccess) return e;
     unsigned grid = persistent_grid(n, HWB, c.num_sms, resident_blocks(kern, RBS, smem));
-    kern<<<grid, RBS, smem, st>>>(c.m, c.sc, c.scf, c.tab, c.a_hat, c.l, vec_coef, vk_ntt, ch_pairs, ch_wt, rhs_only,
-                                  extra_rhs, n, bd, wt, verdict);
+    kern<<<grid, RBS, smem, st>>>(c.m, c.sc, c.scf, c.tab, c.a_hat, c.l, static_cast<const int16_t*>(vec),
+                                  static_cast<const uint16_t*>(vk), ch_pairs, ch_wt, rhs_only, extra_rhs, n, bd, wt,
+                                  sig_bias, verdict);
     return cudaGetLastError();
+}
+
+cudaError_t launch_verify(const RingCtx& c, const int16_t* vec_coef, const uint16_t* vk_ntt, const int16_t* ch_pairs,
+                          int ch_wt, const uint16_t* rhs_only, const uint16_t* extra_rhs, int64_t n, int bd, int wt,
+                          uint8_t* verdict, cudaStream_t st) {
+    return launch_verify_t<0, 0>(c, vec_coef, vk_ntt, ch_pairs, ch_wt, rhs_only, extra_rhs, n, bd, wt, 0, verdict, st);
+}
+
+// The two shipped packings are expanded inside the kernel; anything else is reported as unsupported and the
+// caller unpacks first.
+cudaError_t launch_verify_packed(const RingCtx& c, const uint8_t* sig_packed, int sig_bits, int sig_bias,
+                                 const uint8_t* vk_packed, int vk_bits, const int16_t* ch_pairs, int ch_wt, int64_t n,
+                                 int bd, int wt, uint8_t* verdict, cudaStream_t st) {
+    if (sig_bits == 11 && vk_bits == 14)
+        return launch_verify_t<11, 14>(c, sig_packed, vk_packed, ch_pairs, ch_wt, nullptr, nullptr, n, bd, wt, sig_bias, verdict, st);
+    if (sig_bits == 13 && vk_bits == 16)
+        return launch_verify_t<13, 0>(c, sig_packed, vk_packed, ch_pairs, ch_wt, nullptr, nullptr, n, bd, wt, sig_bias, verdict, st);
+    return cudaErrorNotSupported;
 }
 
 cudaError_t launch_vec_addsub(const RingCtx& c, const int16_t* a, const int16_t* b, int64_t nelem, int sub,

@@ -90,12 +90,18 @@ def test_verify_packed_equals_verify(engines, golden, secpar):
         elif kind == 2:
             msgs2[i] = chmsgs[i] + b'!'
     want = e.lm_verify(sch, vk_ntt, ragged(msgs2), bad, vf_bd, vf_wt)
-    sig_p, ok = e.pack(bad, sbits, vf_bd, want_range=True)
-    assert ok.all()
+    # the shipped widths are expanded inside k_verify; a wider packing takes the unpack-first route
+    for sb, kb in ((sbits, kbits), (sbits + 1, min(16, kbits + 1))):
+        sig_p, ok = e.pack(bad, sb, vf_bd, want_range=True)
+        assert ok.all()
+        vk_p = e.pack(vk_ntt, kb, 0)
+        got = e.lm_verify_packed(sch, vk_p, kb, ragged(msgs2), sig_p, sb, vf_bd, vf_bd, vf_wt)
+        assert np.array_equal(got, want) and 0.5 < want.mean() < 0.9
+        assert sig_p.nbytes * 16 == bad.nbytes * sb
+    # a bias other than vf_bd (still covering the coefficient range) must give the same verdicts
+    sig_p = e.pack(bad, sbits + 1, vf_bd + 7)
     vk_p = e.pack(vk_ntt, kbits, 0)
-    got = e.lm_verify_packed(sch, vk_p, kbits, ragged(msgs2), sig_p, sbits, vf_bd, vf_bd, vf_wt)
-    assert np.array_equal(got, want) and 0.5 < want.mean() < 0.9
-    assert sig_p.nbytes * 16 == bad.nbytes * sbits
+    assert np.array_equal(e.lm_verify_packed(sch, vk_p, kbits, ragged(msgs2), sig_p, sbits + 1, vf_bd + 7, vf_bd, vf_wt), want)
 
 
 def test_wire_module_and_seeded_key_ch(golden):
