@@ -130,7 +130,10 @@ int lcb_pack_batch(lcb_ctx* ctx, const void* values, int64_t npoly, int bits, in
 int lcb_unpack_batch(lcb_ctx* ctx, const uint8_t* packed, int64_t npoly, int bits, int bias, void* values);
 
 /* lcb_lm_verify_batch (verify, lm_one_time_sigs.py:173-191) on packed inputs: vk_packed uint8[n][2][32*vk_bits]
- * (bias 0), sig_packed uint8[n][l][32*sig_bits] (bias sig_bias).  Same verdicts as unpacking first. */
+ * (bias 0), sig_packed uint8[n][l][32*sig_bits] (bias sig_bias).  Same verdicts as unpacking first.  The shipped
+ * widths (sig/vk = 11/14 and 13/16 bits) are read by the verify kernel directly; other widths are unpacked
+ * into engine scratch first.  Host-resident signatures (here and in lcb_lm_verify_batch) cross PCIe in
+ * chunks on a second stream while the kernels of the previous chunk run. */
 int lcb_lm_verify_packed_batch(lcb_ctx* ctx, const lcb_scheme* sch, const uint8_t* vk_packed, int vk_bits,
                                const uint8_t* chmsg, const int64_t* chmsg_off, const uint8_t* sig_packed,
                                int sig_bits, int sig_bias, int64_t n, int bd, int wt, uint8_t* verdict);
