@@ -35,7 +35,7 @@ def parse():
     ap.add_argument('--secpar', type=int, default=128, choices=[128, 256])
     ap.add_argument('--log2n', type=int, default=20, help='log2 of triples per GPU')
     ap.add_argument('--e2e-steps', type=int, default=2)
-    ap.add_argument('--cpu-per-core', type=int, default=16, help='CPU baseline: verifies per host core')
+    ap.add_argument('--cpu-per-core', type=int, default=32, help='CPU baseline: verifies per host core')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-secondary', action='store_true', help='skip the keygen+sign / BKLM / adaptor measurements')
     ap.add_argument('--bklm-log2n', type=int, default=16, help='log2 of signatures per aggregate (whole job)')
