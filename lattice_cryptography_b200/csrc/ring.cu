@@ -285,16 +285,67 @@ __global__ void __launch_bounds__(RBS, 4) k_matvec(ModQ m, StageConst sc, StageC
 }
 
 // ------------------------------------------------------------------------------------------------
+// Asynchronous global->shared staging (LDGSTS, L2-only) used by k_sign and k_verify: each half-warp owns two
+// stage buffers and keeps the next two rows of its work list in flight while it works on the current one, so
+// HBM latency never reaches the scoreboard.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int VERIFY_BLOCKS = 4;     // resident blocks per SM k_verify is compiled for
+
+__device__ __forceinline__ void load_u16x16_smem(uint32_t (&r)[EPT], const unsigned char* p) {
+    const uint4* v = reinterpret_cast<const uint4*>(p);
+    const uint4 a = v[0], b = v[1];
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { r[2 * i] = w[i] & 0xFFFFu; r[2 * i + 1] = w[i] >> 16; }
+}
+
+constexpr int SIGN_STAGE_BYTES = 2 * (2 * D * 2) + 32;   // two (sk_left row, sk_right row) pairs per half-warp
+
 // sig = sk_left ** c + sk_right
 __global__ void __launch_bounds__(RBS) k_sign(ModQ m, StageConst sc, const NttTables* __restrict__ tab, int l,
                                               const uint16_t* __restrict__ sk_ntt, const int16_t* __restrict__ ch_pairs,
                                               int ch_wt, int64_t n, int16_t* __restrict__ sig) {
-    __shared__ __align__(16) uint32_t xbuf[(RBS / 32) * XWARP];
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint32_t* xbuf = smem;
+    unsigned char* stage = reinterpret_cast<unsigned char*>(xbuf + (RBS / 32) * XWARP);
     const HalfWarp h = half_warp(xbuf);
+    stage += h.slot * SIGN_STAGE_BYTES;
     LaneTw itw;
     load_lane_tw(itw, tab->iw, tab->iws, h.lane);
-    for (int64_t base = (int64_t)blockIdx.x * HWB; base < n; base += (int64_t)gridDim.x * HWB) {
-        const int64_t raw = base + h.slot;
+    const int64_t first = (int64_t)blockIdx.x * HWB, stride = (int64_t)gridDim.x * HWB;
+    const int64_t trips = first < n ? (n - first + stride - 1) / stride : 0;   // uniform over the block
+    // work list of this half-warp: row pair i (sk_left[i], sk_right[i]) of item(it); the cursor runs 2 ahead
+    int64_t pf_it = 0;
+    int pf_i = 0;
+    unsigned pf_buf = 0;
+    auto issue = [&]() {
+        if (pf_it < trips) {
+            int64_t it_item = first + pf_it * stride + h.slot;
+            it_item = it_item < n ? it_item : n - 1;
+            const unsigned char* left = reinterpret_cast<const unsigned char*>(sk_ntt + (it_item * 2 * l + pf_i) * D) + 32 * h.lane;
+            const unsigned char* right = left + (int64_t)l * D * 2;
+            unsigned char* dst = stage + pf_buf * (2 * D * 2) + 32 * h.lane;
+            cp_async16(dst, left);
+            cp_async16(dst + 16, left + 16);
+            cp_async16(dst + D * 2, right);
+            cp_async16(dst + D * 2 + 16, right + 16);
+            if (++pf_i == l) { pf_i = 0; ++pf_it; }
+            pf_buf ^= 1u;
+        }
+        cp_async_commit();
+    };
+    issue();
+    issue();
+    unsigned cur = 0;
+    for (int64_t it = 0; it < trips; ++it) {
+        const int64_t raw = first + it * stride + h.slot;
         const bool live = raw < n;
         const int64_t item = live ? raw : n - 1;
         uint32_t c[EPT];
@@ -306,12 +357,16 @@ __global__ void __launch_bounds__(RBS) k_sign(ModQ m, StageConst sc, const NttTa
         }
 #pragma unroll
         for (int k = 0; k < EPT; ++k) c[k] = barrett_full(c[k], m);
-        const uint16_t* skl = sk_ntt + item * 2 * l * D;
-        const uint16_t* skr = skl + (int64_t)l * D;
         for (int i = 0; i < l; ++i) {
+            cp_async_wait<1>();
+            __syncwarp();
             uint32_t a[EPT], b[EPT];
-            load_u16x16(a, skl + i * D + 16 * h.lane);
-            load_u16x16(b, skr + i * D + 16 * h.lane);
+            const unsigned char* rows = stage + cur * (2 * D * 2) + 32 * h.lane;
+            load_u16x16_smem(a, rows);
+            load_u16x16_smem(b, rows + D * 2);
+            __syncwarp();
+            issue();                            // refill the buffer just drained with row pair (+2)
+            cur ^= 1u;
 #pragma unroll
             for (int k = 0; k < EPT; ++k) a[k] = barrett_lazy(c[k] * a[k], m) + b[k];   // < 2q + 2^16 <= cq2
             ntt_inv_256(a, m, sc, itw, h.xb, h.lane, m.cq2);
@@ -328,16 +383,6 @@ __global__ void __launch_bounds__(RBS) k_sign(ModQ m, StageConst sc, const NttTa
 // half-warp owns two 512-byte stage buffers and keeps the next two polynomials of its work list
 // in flight while it transforms the current one, so HBM latency never reaches the scoreboard.
 constexpr int STAGE_HALF_BYTES = 2 * D * 2 + 32;   // two polynomials + 32 B so half-warps differ by 8 banks
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-constexpr int VERIFY_BLOCKS = 4;     // resident blocks per SM k_verify is compiled for
 
 // 16 NTT slots of one lane from a 14-bit packed polynomial (wire.cu layout): 16 * 14 bits = exactly 7 words
 __device__ __forceinline__ void load_u14x16(uint32_t (&r)[EPT], const uint32_t* __restrict__ p) {
@@ -732,8 +777,9 @@ cudaError_t launch_matvec(const RingCtx& c, const int16_t* vec_coef, int64_t nve
 cudaError_t launch_sign(const RingCtx& c, const uint16_t* sk_ntt, const int16_t* ch_pairs, int ch_wt, int64_t n,
                         int16_t* sig, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
-    unsigned grid = persistent_grid(n, HWB, c.num_sms, resident_blocks(k_sign, RBS, 0));
-    k_sign<<<grid, RBS, 0, st>>>(c.m, c.sc, c.tab, c.l, sk_ntt, ch_pairs, ch_wt, n, sig);
+    const size_t smem = (size_t)(RBS / 32) * XWARP * 4 + (size_t)HWB * SIGN_STAGE_BYTES;
+    unsigned grid = persistent_grid(n, HWB, c.num_sms, resident_blocks(k_sign, RBS, smem));
+    k_sign<<<grid, RBS, smem, st>>>(c.m, c.sc, c.tab, c.l, sk_ntt, ch_pairs, ch_wt, n, sig);
     return cudaGetLastError();
 }
 
