@@ -515,3 +515,50 @@ def test_keygen_seed_lengths_across_block_boundary(engines, golden):
             skl, skr, vkl, vkr = c_oracle.lm_keygen(p, key_ch, seeds[i].encode())
             assert np.array_equal(skl, sk_coef[i, 0]) and np.array_equal(skr, sk_coef[i, 1]), (secpar, len(seeds[i]))
             assert np.array_equal(vkl, vk_coef[i, 0]) and np.array_equal(vkr, vk_coef[i, 1])
+
+
+# ------------------------------------------------------------------------------------------- other moduli
+def _ntt_primes():
+    ps = [q for q in range(513, 65536, 512) if all(q % f for f in range(2, int(q ** 0.5) + 1))]
+    return [ps[0], ps[len(ps) // 2], ps[-1]]        # smallest, a middle one, the largest below 2^16
+
+
+@pytest.mark.parametrize('q', _ntt_primes())
+@pytest.mark.parametrize('l', [1, 2, 7])
+def test_other_ntt_friendly_moduli_vs_c_oracle(q, l):
+    """lcb_ctx_create accepts every prime q < 2^16 with q = 1 mod 512 and 1 <= l <= 64: the FP32-assisted
+    butterflies, the lazy bounds and the tables are generic in q, and l = 1 drives the 2-deep staging pipelines
+    across item boundaries on every step.  keygen -> sign -> verify (with tampering) against lcb_oracle.c."""
+    import c_oracle
+    from lattice_cryptography_b200 import Engine, make_scheme, ragged
+    secpar, sk_bd, ch_wt, n = 128, 5, 20, 300
+    vf_bd = min(q // 2, sk_bd * (1 + ch_wt))
+    rng = np.random.default_rng(q + l)
+    key_ch = rng.integers(-(q // 2), q // 2 + 1, size=(l, D)).astype(np.int16)
+    e = Engine(secpar, q, D, l)
+    try:
+        e.set_key_ch(key_ch)
+        sch = make_scheme(sk_bd=sk_bd, sk_wt=256, ch_bd=1, ch_wt=ch_wt)
+        p = c_oracle.params(secpar, q, l, sk_bd, ch_wt)
+        seeds = [''.join(rng.choice(['0', '1'], secpar)) for _ in range(n)]
+        chmsgs = [bytes(rng.integers(1, 256, int(rng.integers(0, 200)), dtype=np.uint8)) for _ in range(n)]
+        sk_coef, sk_ntt, vk_ntt, vk_coef = e.lm_keygen(sch, seeds)
+        sig = e.lm_sign(sch, sk_ntt, chmsgs)
+        for i in (0, 1, n - 1):
+            skl, skr, vkl, vkr = c_oracle.lm_keygen(p, key_ch, seeds[i].encode())
+            assert np.array_equal(skl, sk_coef[i, 0]) and np.array_equal(vkl, vk_coef[i, 0]) and np.array_equal(vkr, vk_coef[i, 1])
+            assert np.array_equal(c_oracle.lm_sign(p, skl, skr, chmsgs[i]), sig[i])
+        bad = sig.copy()
+        for i in range(0, n, 3):
+            bad[i, int(rng.integers(0, l)), int(rng.integers(0, D))] += int(rng.choice([-1, 1]))
+        blob, off = ragged(chmsgs)
+        got = e.lm_verify(sch, vk_ntt, (blob, off), bad, vf_bd, 256)
+        want = c_oracle.lm_verify_batch(p, key_ch, vk_coef, blob, off, bad, vf_bd, 256)
+        assert np.array_equal(got, want) and want.sum() == n - len(range(0, n, 3))
+        # round trip and product through the unit-surface kernels
+        a = rng.integers(-(q // 2), q // 2 + 1, size=(5, D)).astype(np.int16)
+        b = rng.integers(-(q // 2), q // 2 + 1, size=(5, D)).astype(np.int16)
+        assert np.array_equal(e.ntt_inv(e.ntt_fwd(a)), a)
+        assert np.array_equal(e.poly_mul(a, b), np.stack([negacyclic_mul(x, y, q) for x, y in zip(a, b)]).astype(np.int16))
+    finally:
+        e.close()
