@@ -65,3 +65,24 @@ def test_random_seed_batch_shape_and_alphabet():
     assert off.dtype == np.int64 and off[0] == 0 and off[-1] == 256000 and (np.diff(off) == 256).all()
     rows = blob.reshape(1000, 256)
     assert len({bytes(r) for r in rows}) == 1000 and 0.45 < (rows == 49).mean() < 0.55
+
+
+def test_wire_widths_and_ragged_helpers():
+    """Host-only arithmetic of the wire format (bits per coefficient / slot) and of the ragged-blob helper."""
+    from lattice_cryptography_b200 import ragged, wire
+
+    class _LP:
+        def __init__(self, q):
+            self.modulus = q
+
+    class _SP:
+        def __init__(self, q):
+            self.lp = _LP(q)
+    assert wire.sig_bits({'vf_bd': 945}) == 11 and wire.sig_bits({'vf_bd': 3315}) == 13
+    assert wire.sig_bits({'vf_bd': 1023}) == 11 and wire.sig_bits({'vf_bd': 1024}) == 12      # 2*bd + 1 values
+    assert wire.sig_bits({'pvf_bd': 945, 'vf_bd': 946}, bound_key='pvf_bd') == 11
+    assert wire.key_bits({'scheme_parameters': _SP(11777)}) == 14 and wire.key_bits({'scheme_parameters': _SP(39937)}) == 16
+    blob, off = ragged(['ab', b'', 'cé', b'\x00\x01\x02'])
+    assert off.tolist() == [0, 2, 2, 5, 8] and bytes(blob) == b'abc\xc3\xa9\x00\x01\x02'
+    blob, off = ragged([])
+    assert off.tolist() == [0] and blob.size >= 0
