@@ -1,0 +1,15 @@
+#!/bin/bash
+# Runs HERE (no GPU needed) after `gpurun -- bash tools/refresh_profiles.sh`: turns gpurun_out/ into the tracked
+# records under profiles/ (ncu digests, launch summary, bench lines).  ROUND=r2 tools/digest_profiles.sh for round 2.
+set -eu
+R=${ROUND:-r1}
+cd "$(dirname "$0")/.."
+for rep in gpurun_out/prof_${R}_*.ncu-rep; do
+  k=$(basename "$rep" .ncu-rep)
+  python profiles/ncu_summary.py "$rep" > "profiles/$k.summary.txt" 2>&1 || { echo "digest of $k failed"; rm -f "profiles/$k.summary.txt"; }
+done
+for f in bench_${R}_final.json bench_${R}_reference.json bench_${R}_2gpu.json bench_${R}_4gpu.json bench_${R}_8gpu.json launches_${R}.csv; do
+  [ -s "gpurun_out/$f" ] && cp "gpurun_out/$f" profiles/
+done
+[ -s "profiles/launches_${R}.csv" ] && python profiles/launch_summary.py "profiles/launches_${R}.csv" > "profiles/launches_${R}_summary.csv"
+ls -la profiles | grep "_${R}" | awk '{print $5, $9}'
