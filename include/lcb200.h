@@ -112,7 +112,10 @@ int lcb_lm_sign_batch(lcb_ctx* ctx, const lcb_scheme* sch, const uint16_t* sk_nt
 
 /* verify (lm_one_time_sigs.py:173-191), adaptor preverify / verify (adaptor_sigs.py:198-217,247-266):
  * verdict[i] = max|sig_i| <= bd && max weight <= wt && key_ch*sig == vk_left*c + vk_right (+ st).
- * st_ntt may be NULL (LM verify, preverify) or uint16[n][d] (adaptor verify). */
+ * st_ntt may be NULL (LM verify, preverify) or uint16[n][d] (adaptor verify).
+ * The bound is tested on the int16 values AS GIVEN: coefficient-form inputs MUST be centred residues (what every
+ * engine entry point emits and what the reference's get_coef_rep() returns).  A non-canonical representative
+ * such as x + q is not re-centred first; it fails the bound (verdict 0) whenever |x + q| > bd. */
 int lcb_lm_verify_batch(lcb_ctx* ctx, const lcb_scheme* sch, const uint16_t* vk_ntt, const uint8_t* chmsg,
                         const int64_t* chmsg_off, const int16_t* sig, const uint16_t* st_ntt, int64_t n,
                         int bd, int wt, uint8_t* verdict);
@@ -123,7 +126,9 @@ int lcb_lm_verify_batch(lcb_ctx* ctx, const lcb_scheme* sch, const uint16_t* vk_
  * value i at bit offset i*bits, least significant bit first: 32*bits bytes per polynomial, polynomials
  * back to back.  Signatures: x = centred coefficient, bias = vf_bd, bits = ceil(log2(2*vf_bd+1)) (11 at
  * secpar 128, 13 at 256).  NTT-form keys: x = slot value, bias = 0, bits = ceil(log2 q) (14 / 16).
- * `values` is int16 or uint16 [npoly][d]; packed buffers must be 4-byte aligned.
+ * `values` is int16 or uint16 [npoly][d]; packed buffers must be 4-byte aligned (LCB_ERR_INVALID otherwise);
+ * lcb_lm_verify_packed_batch reads the shipped widths directly only from 16-byte aligned device buffers and
+ * unpacks into scratch first when a caller-owned device buffer is merely 4-byte aligned.
  * in_range (nullable) uint8[npoly]: 1 when every value of the polynomial was representable. */
 int lcb_pack_batch(lcb_ctx* ctx, const void* values, int64_t npoly, int bits, int bias, uint8_t* packed,
                    uint8_t* in_range);

@@ -163,6 +163,8 @@ def presign(pp: PublicParameters, otk: OneTimeKeyTuple, msg: Message, st: OneTim
 
 def preverify(pp: PublicParameters, otvk: OneTimeVerificationKey, msg: Message, st: OneTimePublicStatement,
               presig: PreSignature) -> bool:
+    if not _lm.well_formed(pp['scheme_parameters'].lp, presig):
+        return False
     presig.const_time_flag = True
     verdict = preverify_batch(pp, _vk_arr(otvk), challenge_messages([st], [otvk], [msg]),
                               np.ascontiguousarray(presig.coef[None]))
@@ -179,6 +181,8 @@ def extract(pp: PublicParameters, presig: PreSignature, sig: Signature) -> OneTi
 
 
 def witness_verify(pp: PublicParameters, wit: OneTimeSecretWitness, st: OneTimePublicStatement) -> bool:
+    if not _lm.well_formed(pp['scheme_parameters'].lp, wit.key):
+        return False
     wit.const_time_flag = True
     verdict = witness_verify_batch(pp, np.ascontiguousarray(wit.key.coef[None]),
                                    np.ascontiguousarray(st.key.ntt[None]))
@@ -192,6 +196,8 @@ def sign(pp: PublicParameters, otk: OneTimeKeyTuple, msg: Message, wit_st_pair: 
 
 def verify(pp: PublicParameters, otvk: OneTimeVerificationKey, msg: Message, st: OneTimePublicStatement,
            sig: Signature) -> bool:
+    if not _lm.well_formed(pp['scheme_parameters'].lp, sig):
+        return False
     sig.const_time_flag = True
     verdict = verify_batch(pp, _vk_arr(otvk), challenge_messages([st], [otvk], [msg]),
                            np.ascontiguousarray(st.key.ntt[None]), np.ascontiguousarray(sig.coef[None]))

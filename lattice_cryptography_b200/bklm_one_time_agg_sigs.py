@@ -17,7 +17,7 @@ import numpy as np
 
 from .lattice_algebra import Polynomial, PolynomialVector, is_bitstring
 from .lm_one_time_sigs import (BDs, Message, PublicParameters, SALTs, SecurityParameter, Signature, WTs, _ctx,
-                               challenge_messages, make_setup_parameters as setup_pars, make_signature_challenge)
+                               challenge_messages, make_setup_parameters as setup_pars, make_signature_challenge, well_formed)
 from .one_time_keys import ALLOWABLE_SECPARS, OneTimeVerificationKey, bits_to_decode, bits_to_indices
 
 AggCoef = Polynomial
@@ -127,6 +127,8 @@ def aggregate(pp: PublicParameters, otvks: List[OneTimeVerificationKey], msgs: L
 def aggregate_verify(pp: PublicParameters, otvks: List[OneTimeVerificationKey], msgs: List[Message],
                      ag_sig: Signature) -> bool:
     if len(otvks) < 1 or len(otvks) > pp['ag_cap'] or len(otvks) != len(msgs):
+        return False
+    if not well_formed(pp['scheme_parameters'].lp, ag_sig):
         return False
     srt_keys, srt_msgs = prepare_make_agg_coefs(otvks=otvks, msgs=msgs)
     agmsg = str(list(zip(srt_keys, srt_msgs)))

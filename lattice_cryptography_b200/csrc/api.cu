@@ -27,6 +27,8 @@ struct lcb_ctx {
     int64_t launches = 0;
     uint8_t* idx_scratch = nullptr;      // sampler index parking (grow-only, stream-ordered reuse)
     size_t idx_scratch_bytes = 0;
+    uint2* il_scratch = nullptr;         // bit-split copies of the BKLM aggregation message (grow-only)
+    size_t il_scratch_bytes = 0;
     // optional per-kernel CUDA-event timing (lcb_profile_*)
     bool profile = false;
     struct Pending { int id; cudaEvent_t a, b; };
@@ -148,13 +150,20 @@ class Staging {
         // an early error return must not free buffers a chunked copy is still writing
         if (piped_ && c_->copy_stream) cudaStreamSynchronize(c_->copy_stream);
         for (cudaEvent_t e : events_) cudaEventDestroy(e);
+        // scratch that held secret material (signing keys, witnesses) is cleared before it goes back to the
+        // stream-ordered pool: the pool keeps freed blocks resident (release threshold = max) and would hand the
+        // bytes to the next allocation of this process
+        for (auto& s : secret_) cudaMemsetAsync(s.first, 0, s.second, c_->stream);
         for (void* p : owned_) cudaFreeAsync(p, c_->stream);
     }
-    cudaError_t alloc(void** out, size_t bytes) {
+    cudaError_t alloc(void** out, size_t bytes, bool secret = false) {
         *out = nullptr;
         if (bytes == 0) bytes = 16;
         cudaError_t e = cudaMallocAsync(out, bytes, c_->stream);
-        if (e == cudaSuccess) owned_.push_back(*out);
+        if (e == cudaSuccess) {
+            owned_.push_back(*out);
+            if (secret) secret_.push_back({*out, bytes});
+        }
         return e;
     }
     // polynomial data (16-bit elements) is moved with 128-bit loads / cp.async: caller-owned DEVICE
@@ -162,12 +171,12 @@ class Staging {
     template <typename T>
     static bool misaligned(const T* p) { return sizeof(T) == 2 && (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
     template <typename T>
-    cudaError_t in(const T** dev, const T* p, size_t count) {
+    cudaError_t in(const T** dev, const T* p, size_t count, bool secret = false) {
         *dev = p;
         if (p == nullptr || count == 0) return cudaSuccess;
         if (on_device(p)) return misaligned(p) ? cudaErrorMisalignedAddress : cudaSuccess;
         void* d = nullptr;
-        cudaError_t e = alloc(&d, count * sizeof(T));
+        cudaError_t e = alloc(&d, count * sizeof(T), secret);
         if (e != cudaSuccess) return e;
         host_touched_ = true;
         *dev = static_cast<const T*>(d);
@@ -212,12 +221,12 @@ class Staging {
         return cudaEventRecord(*done, c_->copy_stream);
     }
     template <typename T>
-    cudaError_t out(T** dev, T* p, size_t count) {
+    cudaError_t out(T** dev, T* p, size_t count, bool secret = false) {
         *dev = p;
         if (p == nullptr || count == 0) return cudaSuccess;
         if (on_device(p)) return misaligned(p) ? cudaErrorMisalignedAddress : cudaSuccess;
         void* d = nullptr;
-        cudaError_t e = alloc(&d, count * sizeof(T));
+        cudaError_t e = alloc(&d, count * sizeof(T), secret);
         if (e != cudaSuccess) return e;
         host_touched_ = true;
         *dev = static_cast<T*>(d);
@@ -238,6 +247,7 @@ class Staging {
     struct Back { void* host; void* dev; size_t bytes; };
     lcb_ctx* c_;
     std::vector<void*> owned_;
+    std::vector<std::pair<void*, size_t>> secret_;
     std::vector<Back> back_;
     std::vector<cudaEvent_t> events_;
     bool host_touched_ = false;
@@ -281,6 +291,8 @@ int fill_sampler(lcb_ctx* c, SamplerArgs& a, const char* salt, const char* suffi
     a.out_dense = nullptr;
     a.dense_stride = 0;
     a.out_pairs = nullptr;
+    a.il_msg = nullptr;
+    a.il_stride = 0;
     return LCB_OK;
 }
 
@@ -316,7 +328,22 @@ int run_agg_coefs(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* d_agmsg, int
     a.shared_len = agmsg_len;
     a.index_first = first;
     a.out_pairs = d_pairs;
-    CK(c, timed(c, K_AGG_COEFS, [&] { return launch_agg_coefs(a, c->stream); }));
+    if (agg_coefs_two_lane(count, c->ring.num_sms)) {
+        // few long streams: two lanes per sponge over the pre-split message (sampler.cu, k_agg_coefs_il)
+        const size_t need = agg_il_bytes(agmsg_len);
+        if (need > c->il_scratch_bytes) {
+            CK(c, cudaStreamSynchronize(c->stream));
+            if (c->il_scratch) cudaFree(c->il_scratch);
+            c->il_scratch = nullptr;
+            c->il_scratch_bytes = 0;
+            CK(c, cudaMalloc(&c->il_scratch, need));
+            c->il_scratch_bytes = need;
+        }
+        a.il_msg = c->il_scratch;
+        a.il_stride = agg_il_stride(agmsg_len);
+        c->launches += 1;                                  // the pre-split kernel
+    }
+    CK(c, timed(c, K_AGG_COEFS, [&] { return launch_agg_coefs(a, c->ring.num_sms, c->stream); }));
     return LCB_OK;
 }
 
@@ -455,6 +482,7 @@ int lcb_ctx_destroy(lcb_ctx* c) {
     if (c->d_tab) cudaFree(c->d_tab);
     if (c->d_a_hat) cudaFree(c->d_a_hat);
     if (c->idx_scratch) cudaFree(c->idx_scratch);
+    if (c->il_scratch) cudaFree(c->il_scratch);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);
@@ -668,8 +696,8 @@ int lcb_lm_keygen_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* seeds,
     uint16_t *d_sk_ntt, *d_vk_ntt;
     CK(c, sg.in(&d_seeds, seeds, (size_t)total));
     CK(c, sg.in(&d_off, seed_off, (size_t)n + 1));
-    CK(c, sg.out(&d_sk_coef, sk_coef, (size_t)n * 2 * l * D));
-    CK(c, sg.out(&d_sk_ntt, sk_ntt, (size_t)n * 2 * l * D));
+    CK(c, sg.out(&d_sk_coef, sk_coef, (size_t)n * 2 * l * D, true));
+    CK(c, sg.out(&d_sk_ntt, sk_ntt, (size_t)n * 2 * l * D, true));
     CK(c, sg.out(&d_vk_ntt, vk_ntt, (size_t)n * 2 * D));
     CK(c, sg.out(&d_vk_coef, vk_coef, (size_t)n * 2 * D));
     // Signing keys pass through HBM in coefficient form between the sampler and the row-vector
@@ -689,7 +717,7 @@ int lcb_lm_keygen_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* seeds,
         if (v > 0 && !d_sk_coef) chunk = v < n ? v : n;
     }
     int16_t* scratch = nullptr;
-    if (!d_sk_coef) CK(c, sg.alloc((void**)&scratch, (size_t)chunk * 2 * l * D * sizeof(int16_t)));
+    if (!d_sk_coef) CK(c, sg.alloc((void**)&scratch, (size_t)chunk * 2 * l * D * sizeof(int16_t), true));
     for (int64_t start = 0; start < n; start += chunk) {
         const int64_t cnt = (n - start < chunk) ? n - start : chunk;
         int16_t* skc = d_sk_coef ? d_sk_coef + start * 2 * l * D : scratch;
@@ -744,7 +772,7 @@ int lcb_lm_sign_batch(lcb_ctx* c, const lcb_scheme* sch, const uint16_t* sk_ntt,
     const uint8_t* d_msg;
     const int64_t* d_off;
     int16_t *d_sig, *d_pairs;
-    CK(c, sg.in(&d_sk, sk_ntt, (size_t)n * 2 * l * D));
+    CK(c, sg.in(&d_sk, sk_ntt, (size_t)n * 2 * l * D, true));
     CK(c, sg.in(&d_msg, chmsg, (size_t)total));
     CK(c, sg.in(&d_off, chmsg_off, (size_t)n + 1));
     CK(c, sg.out(&d_sig, sig, (size_t)n * l * D));
@@ -875,7 +903,12 @@ int lcb_lm_verify_packed_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t*
     const int64_t chunk = n < 2 * kPipeChunk ? n : 2 * kPipeChunk;
     // The two shipped packings (11/14 and 13/16 bits) are expanded inside k_verify; any other width is unpacked
     // into scratch first.
-    const bool fused = (sig_bits == 11 && vk_bits == 14) || (sig_bits == 13 && vk_bits == 16);
+    // The fused route streams packed signature rows with 16-byte cp.async and reads 16-bit key slots with 128-bit
+    // loads, so it needs 16-byte aligned buffers (staged host buffers always are); a caller-owned device buffer that
+    // is only 4-byte aligned takes the unpack-first route instead of raising a sticky misaligned-address fault.
+    const bool aligned16 = (reinterpret_cast<uintptr_t>(d_sigp) & 15u) == 0 &&
+                           (vk_bits == 14 || (reinterpret_cast<uintptr_t>(d_vkp) & 15u) == 0);
+    const bool fused = aligned16 && ((sig_bits == 11 && vk_bits == 14) || (sig_bits == 13 && vk_bits == 16));
     uint16_t* d_vk = nullptr;
     int16_t *d_sig = nullptr, *d_pairs;
     if (!fused) {
@@ -1060,10 +1093,10 @@ int lcb_adaptor_witgen_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* s
     uint16_t* d_st_ntt;
     CK(c, sg.in(&a.msgs, seeds, (size_t)total));
     CK(c, sg.in(&a.off, seed_off, (size_t)n + 1));
-    CK(c, sg.out(&d_wit, wit_coef, (size_t)n * l * D));
+    CK(c, sg.out(&d_wit, wit_coef, (size_t)n * l * D, true));
     CK(c, sg.out(&d_st_ntt, st_ntt, (size_t)n * D));
     CK(c, sg.out(&d_st_coef, st_coef, (size_t)n * D));
-    if (!d_wit) CK(c, sg.alloc((void**)&d_wit, (size_t)n * l * D * sizeof(int16_t)));
+    if (!d_wit) CK(c, sg.alloc((void**)&d_wit, (size_t)n * l * D * sizeof(int16_t), true));
     if (sch->wit_wt < D) CK(c, cudaMemsetAsync(d_wit, 0, (size_t)n * l * D * sizeof(int16_t), c->stream));
     a.n = n;
     a.out_dense = d_wit;

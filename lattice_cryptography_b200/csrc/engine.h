@@ -31,6 +31,11 @@ struct SamplerArgs {
     int16_t* out_pairs;        // or nullptr; [n][vec_len][wt][2]
     uint8_t* idx_scratch;      // device scratch, sampler_scratch_bytes(n, wt) bytes
     int64_t idx_stride;        // streams rounded up to whole blocks
+    // shared_msg, two lanes per sponge: the message split into (even, odd) bit halves per 64-bit word, one copy per
+    // byte phase delta = 0..7 (il_msg[delta * il_stride + t] <-> message bytes 8t + delta ..); nullptr = one thread
+    // per sponge
+    uint2* il_msg;
+    int64_t il_stride;
 };
 
 cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st);
@@ -38,7 +43,11 @@ inline int64_t sampler_stride(int64_t n) { return (n + 127) / 128 * 128; }
 inline size_t sampler_scratch_bytes(int64_t n, int wt) { return (size_t)sampler_stride(n) * (size_t)wt; }
 cudaError_t launch_shake256(const uint8_t* in, const int64_t* off, int64_t n, uint8_t* out, int64_t out_len,
                             cudaStream_t st);
-cudaError_t launch_agg_coefs(const SamplerArgs& a, cudaStream_t st);   // shared-message fast path, wt == 1
+// shared-message fast path, wt == 1; two lanes per sponge when a.il_msg is set (see agg_coefs_two_lane)
+cudaError_t launch_agg_coefs(const SamplerArgs& a, int num_sms, cudaStream_t st);
+bool agg_coefs_two_lane(int64_t n, int num_sms);
+inline int64_t agg_il_stride(int64_t msg_len) { return msg_len / 8 + 1; }
+inline size_t agg_il_bytes(int64_t msg_len) { return (size_t)8 * (size_t)agg_il_stride(msg_len) * sizeof(uint2); }
 
 struct RingCtx {
     ModQ m;

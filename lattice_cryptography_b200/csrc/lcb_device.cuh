@@ -17,6 +17,17 @@
 
 #include <cuda_runtime.h>
 
+// Checked build (make CHECKED=1 -> liblcb200_checked.so): every hand-rolled guard of a global access asserts the
+// range it is about to touch.  compute-sanitizer is not available on the GPU pool (profiles/sanitizer_r2.txt), so
+// this build plus tests/test_gpu_checked.py stands in for memcheck.  A failed check traps the kernel: the call
+// returns LCB_ERR_CUDA ("device-side assert").
+#ifdef LCB_CHECKED
+#include <cassert>
+#define LCB_CHECK(cond) assert(cond)
+#else
+#define LCB_CHECK(cond) ((void)0)
+#endif
+
 namespace lcb {
 
 constexpr int D = 256;            // ring degree handled by the fast path
@@ -459,6 +470,98 @@ __device__ __forceinline__ void keccak_f1600(KeccakState& s, const uint64_t* __r
         const uint64_t c = rc[round];
         s.lo[0] ^= (uint32_t)c;
         s.hi[0] ^= (uint32_t)(c >> 32);
+    }
+}
+
+// ---- Keccak-f[1600] on TWO adjacent lanes per sponge (bit-interleaved halves) ---------------------
+// A kernel with few, long SHAKE streams (BKLM aggregation coefficients on 8 GPUs: 8,192 streams of 59,754
+// permutations each; a single key generation) leaves most of the 592 warp schedulers without a warp when a
+// sponge is one thread.  Here lane 2i holds the EVEN bits and lane 2i+1 the ODD bits of each of the 25 state
+// words (32 bits of every 64-bit word): theta's parities, chi and iota act on bit positions independently, so
+// they stay lane-local; a rotation by an even amount 2a is a 32-bit rotation by a of the own half, a rotation by
+// an odd amount 2a+1 takes the PARTNER's half rotated by a (odd lane) or a+1 (even lane) - one SHFL.  Per round
+// and lane: 61 LOP3 + 29 SHF (exactly half of the one-thread form's 122 + 58, so the ALU-pipe roofline per
+// permutation is unchanged) + 17 SHFL (12 odd rho offsets + 5 for theta's rotl(C,1)).
+struct KeccakHalf {
+    uint32_t a[25];
+};
+
+// (even, odd) bit halves of a 64-bit word
+__host__ __device__ __forceinline__ uint32_t keccak_even_bits(uint64_t x) {
+    x &= 0x5555555555555555ULL;
+    x = (x | (x >> 1)) & 0x3333333333333333ULL;
+    x = (x | (x >> 2)) & 0x0F0F0F0F0F0F0F0FULL;
+    x = (x | (x >> 4)) & 0x00FF00FF00FF00FFULL;
+    x = (x | (x >> 8)) & 0x0000FFFF0000FFFFULL;
+    x = (x | (x >> 16)) & 0x00000000FFFFFFFFULL;
+    return (uint32_t)x;
+}
+__host__ __device__ __forceinline__ uint32_t keccak_half_of(uint64_t x, unsigned odd) { return keccak_even_bits(x >> odd); }
+
+// Rotation amounts of the odd rho offsets (and of theta's rotl 1) differ by one between the two lanes of a pair:
+// a + 1 on the even lane, a on the odd lane, a = offset >> 1.  The twelve distinct values are pinned in registers
+// by keccak_half_rot_init (volatile asm: ptxas otherwise re-derives each one from SR_TID at every use - S2R + LOP3
+// + IADD3, 15 % more ALU instructions per round).
+struct KeccakHalfRot {
+    uint32_t s[12];
+};
+__host__ __device__ constexpr int keccak_half_rot_slot(int a) {
+    constexpr int A[12] = {0, 1, 7, 10, 12, 13, 19, 20, 21, 22, 27, 30};
+    for (int i = 0; i < 12; ++i)
+        if (A[i] == a) return i;
+    return -1;
+}
+__device__ __forceinline__ void keccak_half_rot_init(KeccakHalfRot& r, unsigned odd) {
+    constexpr int A[12] = {0, 1, 7, 10, 12, 13, 19, 20, 21, 22, 27, 30};
+    const uint32_t up = 1u - odd;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) asm volatile("add.u32 %0, %1, %2;" : "=r"(r.s[i]) : "r"(up), "r"((uint32_t)A[i]));
+}
+
+template <int I>
+struct KeccakHalfRhoPi {
+    __device__ static __forceinline__ void run(const KeccakHalf& s, const uint32_t (&c)[5], const uint32_t (&r1)[5],
+                                               const KeccakHalfRot& rot, KeccakHalf& b) {
+        constexpr int R[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+        constexpr int x = I % 5;
+        const uint32_t t = lop_xor3(s.a[I], c[(x + 4) % 5], r1[(x + 1) % 5]);
+        if (R[I] == 0) b.a[keccak_pi(I)] = t;
+        else if (R[I] % 2 == 0) b.a[keccak_pi(I)] = __funnelshift_l(t, t, R[I] / 2);
+        else {
+            static_assert(R[I] % 2 == 0 || keccak_half_rot_slot(R[I] / 2) >= 0, "rotation table");
+            const uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, t, 1);
+            b.a[keccak_pi(I)] = __funnelshift_l(o, o, rot.s[keccak_half_rot_slot(R[I] / 2)]);
+        }
+        KeccakHalfRhoPi<I + 1>::run(s, c, r1, rot, b);
+    }
+};
+template <>
+struct KeccakHalfRhoPi<25> {
+    __device__ static __forceinline__ void run(const KeccakHalf&, const uint32_t (&)[5], const uint32_t (&)[5],
+                                               const KeccakHalfRot&, KeccakHalf&) {}
+};
+
+// rc = this lane's halves of the 24 round constants (even-bit halves on even lanes, odd-bit halves on odd lanes).
+// All 32 lanes of the warp must be active and converged.
+__device__ __forceinline__ void keccak_f1600_half(KeccakHalf& s, const uint32_t* __restrict__ rc, const KeccakHalfRot& rot) {
+#pragma unroll 2
+    for (int round = 0; round < 24; ++round) {
+        uint32_t c[5], r1[5];
+#pragma unroll
+        for (int x = 0; x < 5; ++x) c[x] = lop_xor3(lop_xor3(s.a[x], s.a[x + 5], s.a[x + 10]), s.a[x + 15], s.a[x + 20]);
+#pragma unroll
+        for (int x = 0; x < 5; ++x) {                      // rotl64(C, 1): partner's half, rotated by 1 on even lanes
+            const uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, c[x], 1);
+            r1[x] = __funnelshift_l(o, o, rot.s[0]);
+        }
+        KeccakHalf b;
+        KeccakHalfRhoPi<0>::run(s, c, r1, rot, b);
+#pragma unroll
+        for (int y = 0; y < 5; ++y)
+#pragma unroll
+            for (int x = 0; x < 5; ++x)
+                s.a[x + 5 * y] = lop_chi(b.a[x + 5 * y], b.a[(x + 1) % 5 + 5 * y], b.a[(x + 2) % 5 + 5 * y]);
+        s.a[0] ^= rc[round];
     }
 }
 

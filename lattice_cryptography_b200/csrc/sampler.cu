@@ -193,6 +193,144 @@ __global__ void __launch_bounds__(ABS) k_agg_coefs(SamplerArgs a) {
     reinterpret_cast<uint32_t*>(a.out_pairs)[inst] = k | ((uint32_t)(uint16_t)(int16_t)sgn << 16);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// The same derivation with TWO lanes per sponge (keccak_f1600_half, lcb_device.cuh), for launches that would
+// otherwise leave warp schedulers empty: on 8 GPUs a 2^16-signature aggregate is 8,192 streams per GPU = 256
+// one-thread-per-sponge warps on 592 schedulers (0.39 of the Keccak roofline); as lane pairs it is 512 warps of
+// half the length.  The message is common to all streams, so its 64-bit words are split into (even, odd) halves
+// ONCE per salt-length phase by k_msg_interleave - a stream whose salt has slen bytes sees message byte
+// 8 t + delta, delta = (-slen) mod 8, at the start of its word g0 + t - and an interior rate block is then 17
+// aligned 32-bit loads and 17 XORs per lane (no funnel shifts at all; warp-uniform addresses wherever the
+// decimal index has the same number of digits).
+struct Rc2Table {
+    uint32_t v[2][24];      // [even-bit halves | odd-bit halves] of the round constants
+};
+constexpr uint32_t cx_even_bits(uint64_t x) {
+    uint32_t r = 0;
+    for (int i = 0; i < 32; ++i) r |= (uint32_t)((x >> (2 * i)) & 1u) << i;
+    return r;
+}
+constexpr Rc2Table make_rc2() {
+    constexpr uint64_t rc[24] = LCB_KECCAK_RC_INIT;
+    Rc2Table t{};
+    for (int i = 0; i < 24; ++i) { t.v[0][i] = cx_even_bits(rc[i]); t.v[1][i] = cx_even_bits(rc[i] >> 1); }
+    return t;
+}
+static __constant__ Rc2Table c_keccak_rc2 = make_rc2();
+
+// il[delta][t] = (even, odd) halves of the little-endian 64-bit word msg[8 t + delta .. 8 t + delta + 8), for every t
+// whose 8 bytes lie inside the message; grid.y = delta.
+__global__ void __launch_bounds__(256) k_msg_interleave(const uint8_t* __restrict__ msg, int64_t len, uint2* __restrict__ il,
+                                                        int64_t il_stride, unsigned delta_mask) {
+    const int delta = blockIdx.y;
+    if (!((delta_mask >> delta) & 1u)) return;
+    const int64_t words = len >= delta ? (len - delta) / 8 : 0;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < words; t += (int64_t)gridDim.x * blockDim.x) {
+        const uint8_t* p = msg + 8 * t + delta;
+        const uint64_t x = (uint64_t)load_u32_unaligned(p) | ((uint64_t)load_u32_unaligned(p + 4) << 32);
+        il[delta * il_stride + t] = make_uint2(keccak_half_of(x, 0), keccak_half_of(x, 1));
+    }
+}
+
+constexpr int ABS2 = 64;   // threads per block = 32 sponges
+
+__global__ void __launch_bounds__(ABS2) k_agg_coefs_il(SamplerArgs a) {
+    __shared__ uint32_t rc_sh[2][24];
+    if (threadIdx.x < 48) rc_sh[threadIdx.x / 24][threadIdx.x % 24] = c_keccak_rc2.v[threadIdx.x / 24][threadIdx.x % 24];
+    __syncthreads();
+    const unsigned odd = threadIdx.x & 1u;
+    const int64_t raw = ((int64_t)blockIdx.x * ABS2 + threadIdx.x) >> 1;
+    const bool live = raw < a.n;
+    const int64_t inst = live ? raw : a.n - 1;          // every lane stays in the shuffles
+    const uint64_t index = (uint64_t)(a.index_first + inst);
+    uint32_t sw[8];
+    const uint32_t* salt_w = reinterpret_cast<const uint32_t*>(a.salt);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sw[i] = i < (SALT_BYTES / 4) ? salt_w[i] : 0;
+    int ndig = 1;
+    for (uint64_t v = index; v >= 10; v /= 10) ++ndig;
+    const int slen = a.salt_len + ndig;
+    {
+        uint64_t v = index;
+        for (int dpos = slen - 1; dpos >= a.salt_len; --dpos, v /= 10) {
+            const uint32_t ch = (uint32_t)('0' + (v % 10));
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if ((dpos >> 2) == i) sw[i] |= ch << (8 * (dpos & 3));
+        }
+    }
+    const int64_t tot = (int64_t)slen + a.shared_len;
+    const int64_t nblocks = tot / 136 + 1;
+    const int64_t last = nblocks * 136 - 1;
+    const uint8_t* msg = a.msgs;
+    auto salt_byte = [&](int p) -> uint32_t {
+        uint32_t w = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if ((p >> 2) == i) w = sw[i];
+        return (w >> (8 * (p & 3))) & 0xFFu;
+    };
+    auto word_at = [&](int64_t k) -> uint32_t {        // stream word k (bytes 4k .. 4k+3), SHAKE padding applied
+        const int64_t p = 4 * k;
+        if (p >= slen && p + 4 <= tot) return load_u32_unaligned(msg + (p - slen));
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int64_t q = p + b;
+            uint32_t byte = q < slen ? salt_byte((int)q) : (q < tot ? (uint32_t)__ldg(msg + (q - slen)) : (q == tot ? 0x1Fu : 0u));
+            if (q == last) byte ^= 0x80u;
+            v |= byte << (8 * b);
+        }
+        return v;
+    };
+    // stream word (64-bit) g is a plain message word iff g0 <= g < g0 + nl; it is then il[delta][g - g0]
+    const int64_t g0 = (slen + 7) >> 3;
+    const int delta = (int)(8 * g0 - slen);
+    const int64_t nl = a.shared_len >= delta ? (a.shared_len - delta) / 8 : 0;
+    const uint32_t* il = reinterpret_cast<const uint32_t*>(a.il_msg + delta * a.il_stride) + odd;
+    const uint32_t* rc = rc_sh[odd];
+    KeccakHalfRot rot;
+    keccak_half_rot_init(rot, odd);
+    KeccakHalf s;
+#pragma unroll
+    for (int i = 0; i < 25; ++i) s.a[i] = 0;
+    // The lanes of a warp shuffle in lock-step, so the trip count is the warp's maximum (streams whose index has
+    // one digit more may need one block more); a stream that is done keeps permuting, its result is taken on the way.
+    const unsigned nb = (unsigned)(nblocks > 0xFFFFFFFFll ? 0xFFFFFFFFll : nblocks);
+    const unsigned max_nb = __reduce_max_sync(0xFFFFFFFFu, nb);
+    uint32_t result = 0;
+    for (unsigned blk = 0; blk < max_nb; ++blk) {
+        const int64_t g = (int64_t)blk * 17;
+        if (g >= g0 && g + 17 <= g0 + nl) {
+            const uint32_t* w = il + 2 * (g - g0);
+            LCB_CHECK(g - g0 >= 0 && g - g0 + 17 <= nl);
+#pragma unroll
+            for (int i = 0; i < 17; ++i) s.a[i] ^= __ldg(w + 2 * i);
+        } else {
+            // first / last blocks (salt, tail, padding): assembled from bytes, split on the fly
+#pragma unroll 1
+            for (int i = 0; i < 17; ++i) {
+                const uint64_t x = (uint64_t)word_at(2 * (g + i)) | ((uint64_t)word_at(2 * (g + i) + 1) << 32);
+                const uint32_t h = keccak_half_of(x, odd);
+#pragma unroll
+                for (int j = 0; j < 17; ++j)
+                    if (j == i) s.a[j] ^= h;
+            }
+        }
+        keccak_f1600_half(s, rc, rot);
+        if (blk + 1 == nb) result = s.a[0];
+    }
+    // digest bits 0..7 (position) and 15 (sign) of word 0: even lane has bits 0,2,..,14, odd lane 1,3,..,15
+    const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, result, 1);
+    const uint32_t ev = odd ? other : result, od = odd ? result : other;
+    uint32_t k = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) k |= ((ev >> i) & 1u) << (2 * i) | ((od >> i) & 1u) << (2 * i + 1);
+    const int sgn = (od >> 7) & 1u ? 1 : -1;
+    if (live && !odd) reinterpret_cast<uint32_t*>(a.out_pairs)[inst] = k | ((uint32_t)(uint16_t)(int16_t)sgn << 16);
+}
+
 }  // namespace
 
 cudaError_t launch_shake256(const uint8_t* in, const int64_t* off, int64_t n, uint8_t* out, int64_t out_len,
@@ -228,8 +366,38 @@ cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_agg_coefs(const SamplerArgs& a, cudaStream_t st) {
+// Which digit counts occur among the decimal indices [first, first + count)?  -> mask of the message phases
+// delta = (-(salt_len + digits)) mod 8 the two-lane kernel will read.
+unsigned agg_delta_mask(int salt_len, int64_t first, int64_t count) {
+    auto digits = [](uint64_t v) { int n = 1; while (v >= 10) { v /= 10; ++n; } return n; };
+    unsigned mask = 0;
+    for (int d = digits((uint64_t)first); d <= digits((uint64_t)(first + count - 1)); ++d)
+        mask |= 1u << ((8 - ((salt_len + d) & 7)) & 7);
+    return mask;
+}
+
+bool agg_coefs_two_lane(int64_t n, int num_sms) {
+    if (const char* env = getenv("LCB_AGG_LANES")) return atoi(env) == 2;       // tuning knob
+    // one thread per sponge fills the machine only from about two warps per scheduler upwards
+    return n <= (int64_t)num_sms * 4 * 32;
+}
+
+cudaError_t launch_agg_coefs(const SamplerArgs& a, int num_sms, cudaStream_t st) {
     if (a.n <= 0) return cudaSuccess;
+    if (a.il_msg) {
+        const unsigned mask = agg_delta_mask(a.salt_len, a.index_first, a.n);
+        const int64_t words = a.shared_len / 8;
+        if (words > 0) {
+            int64_t need = (words + 255) / 256;
+            dim3 grid((unsigned)(need < 4 * num_sms ? need : 4 * num_sms), 8);
+            k_msg_interleave<<<grid, 256, 0, st>>>(a.msgs, a.shared_len, a.il_msg, a.il_stride, mask);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+        }
+        int64_t blocks = (2 * a.n + ABS2 - 1) / ABS2;
+        k_agg_coefs_il<<<(unsigned)blocks, ABS2, 0, st>>>(a);
+        return cudaGetLastError();
+    }
     int64_t blocks = (a.n + ABS - 1) / ABS;
     k_agg_coefs<<<(unsigned)blocks, ABS, 0, st>>>(a);
     return cudaGetLastError();

@@ -4,6 +4,9 @@ Every method takes host (numpy) or device (torch.cuda) arrays; the library detec
 Outputs are numpy arrays unless ``device=True`` (then torch CUDA tensors on the engine's
 GPU, left on its stream).  Layouts are the ones documented in include/lcb200.h.
 """
+import functools
+import hashlib
+import threading
 from ctypes import byref, c_void_p
 from typing import List, Optional, Sequence, Tuple, Union
 
@@ -42,6 +45,41 @@ def _addr(x):
     return c_void_p(x.ctypes.data)
 
 
+_NP_OF_TORCH = {'torch.int16': np.int16, 'torch.uint16': np.uint16, 'torch.uint8': np.uint8, 'torch.int32': np.int32,
+                'torch.int64': np.int64}
+
+
+def _want(x, name: str, dtypes, shape):
+    """Raise ValueError unless `x` (numpy array or torch tensor) has one of `dtypes` and exactly `shape`
+    (None entries match any extent).  The C side trusts the extents it is given and reads n*l*d elements from
+    every pointer, so a short or mistyped buffer must stop here (out-of-bounds read on a short signature)."""
+    if x is None:
+        raise ValueError(f'{name} is required')
+    if _is_torch(x):
+        dt = _NP_OF_TORCH.get(str(x.dtype))
+        shp = tuple(x.shape)
+    elif isinstance(x, np.ndarray):
+        dt, shp = x.dtype.type, x.shape
+    else:
+        raise ValueError(f'{name} must be a numpy array or a torch tensor, not {type(x).__name__}')
+    if not isinstance(dtypes, tuple):
+        dtypes = (dtypes,)
+    if dt not in dtypes:
+        raise ValueError(f'{name} must have dtype {" or ".join(np.dtype(d).name for d in dtypes)}, not {x.dtype}')
+    if len(shp) != len(shape) or any(w is not None and int(g) != int(w) for g, w in zip(shp, shape)):
+        raise ValueError(f'{name} must have shape {tuple("*" if w is None else int(w) for w in shape)}, not {tuple(shp)}')
+    return x
+
+
+def _lead(x, name: str, dtypes, last: int):
+    """Like _want for arrays of shape (..., last); returns the number of rows."""
+    shp = tuple(x.shape) if hasattr(x, 'shape') else ()
+    if len(shp) < 1:
+        raise ValueError(f'{name} must have shape (..., {last})')
+    _want(x, name, dtypes, (None,) * (len(shp) - 1) + (last,))
+    return int(np.prod(shp[:-1])) if len(shp) > 1 else 1
+
+
 def make_scheme(sk_bd=1, sk_wt=1, ch_bd=1, ch_wt=1, ag_bd=1, ag_wt=1, wit_bd=1, wit_wt=1, sk_salt='SK_SALT',
                 ch_salt='CH_SALT', ag_salt='AG_SALT', wit_salt='WIT_SALT') -> LcbScheme:
     s = LcbScheme()
@@ -55,10 +93,31 @@ def make_scheme(sk_bd=1, sk_wt=1, ch_bd=1, ch_wt=1, ag_bd=1, ag_wt=1, wit_bd=1, 
     return s
 
 
+def _locked(cls):
+    """Serialise every public method of an Engine on its own re-entrant lock: one context = one stream, one key_ch
+    row and one set of scratch buffers, and ctypes releases the GIL inside a call (include/lcb200.h: "a ctx is not
+    re-entrant")."""
+    for name, fn in list(vars(cls).items()):
+        if callable(fn) and not name.startswith('_') and not isinstance(fn, (staticmethod, classmethod, property)):
+            def wrap(f):
+                @functools.wraps(f)
+                def inner(self, *a, **k):
+                    with self.lock:
+                        return f(self, *a, **k)
+                return inner
+            setattr(cls, name, wrap(fn))
+    return cls
+
+
+@_locked
 class Engine(object):
-    """One GPU context: LatticeParameters (q, d, l) + secpar + the NTT-resident public row key_ch."""
+    """One GPU context: LatticeParameters (q, d, l) + secpar + the NTT-resident public row key_ch.
+    Thread-safe at the granularity of one call (see `lock`); callers that must pair a particular key_ch with a call
+    hold `lock` around ensure_key_ch() + the call (lattice_algebra.BoundEngine does)."""
 
     def __init__(self, secpar: int, modulus: int, degree: int, length: int, device: int = 0):
+        self.lock = threading.RLock()
+        self._key_ch_token = None
         self._lib = _ffi.load()
         self._ctx = c_void_p()
         st = self._lib.lcb_ctx_create(byref(self._ctx), device, secpar, modulus, degree, length)
@@ -124,7 +183,15 @@ class Engine(object):
     @staticmethod
     def _rag(items):
         if isinstance(items, tuple) and len(items) == 2:
-            return items            # already (blob, offsets); host or device
+            blob, off = items       # already (blob, offsets); host or device
+            _want(blob, 'ragged blob', np.uint8, (None,))
+            _want(off, 'ragged offsets', np.int64, (None,))
+            if int(off.shape[0]) < 1:
+                raise ValueError('ragged offsets need n + 1 entries')
+            if isinstance(off, np.ndarray) and (int(off[0]) != 0 or int(off[-1]) > int(blob.shape[0]) or
+                                                (off.shape[0] > 1 and bool((np.diff(off) < 0).any()))):
+                raise ValueError('ragged offsets must start at 0, ascend and end inside the blob')
+            return items
         return ragged(items)
 
     @staticmethod
@@ -133,7 +200,16 @@ class Engine(object):
 
     # ------------------------------------------------------------------ K1 / K2
     def set_key_ch(self, key_ch_coef):
+        _want(key_ch_coef, 'key_ch', np.int16, (self.l, self.d))
+        self._key_ch_token = None
         self._ck(self._lib.lcb_set_key_ch(self._ctx, _addr(key_ch_coef)))
+        if isinstance(key_ch_coef, np.ndarray):
+            self._key_ch_token = hashlib.blake2b(key_ch_coef.tobytes(), digest_size=16).digest()
+
+    def ensure_key_ch(self, key_ch_coef: np.ndarray):
+        """Upload `key_ch_coef` unless it already is this context's resident public row."""
+        if self._key_ch_token != hashlib.blake2b(np.ascontiguousarray(key_ch_coef).tobytes(), digest_size=16).digest():
+            self.set_key_ch(np.ascontiguousarray(key_ch_coef))
 
     def shake256(self, items, out_len: int, device: bool = False):
         blob, off = self._rag(items)
@@ -146,7 +222,7 @@ class Engine(object):
                      want_pairs: bool = False, device: bool = False):
         blob, off = self._rag(msgs)
         n = self._count(off)
-        dense = self._out((n, vec_len, D), np.int16, device) if want_dense else None
+        dense = self._out((n, vec_len, self.d), np.int16, device) if want_dense else None
         pairs = self._out((n, vec_len, wt, 2), np.int16, device) if want_pairs else None
         self._ck(self._lib.lcb_hash2polyvec_batch(self._ctx, salt.encode(), _addr(blob), _addr(off), n, bd, wt,
                                                   vec_len, _addr(dense), _addr(pairs)))
@@ -154,26 +230,27 @@ class Engine(object):
 
     # ------------------------------------------------------------------ K3 / K4 / K6
     def ntt_fwd(self, coef, device: bool = False):
-        npoly = int(np.prod(coef.shape[:-1]))
+        npoly = _lead(coef, 'coef', np.int16, self.d)
         out = self._out(tuple(coef.shape), np.uint16, device)
         self._ck(self._lib.lcb_ntt_fwd_batch(self._ctx, _addr(coef), npoly, _addr(out)))
         return out
 
     def ntt_inv(self, ntt, device: bool = False):
-        npoly = int(np.prod(ntt.shape[:-1]))
+        npoly = _lead(ntt, 'ntt', np.uint16, self.d)
         out = self._out(tuple(ntt.shape), np.int16, device)
         self._ck(self._lib.lcb_ntt_inv_batch(self._ctx, _addr(ntt), npoly, _addr(out)))
         return out
 
     def ntt_reference_repr(self, coef, device: bool = False):
         """lattice_algebra's Polynomial.ntt_representation: int16[..., 2d], rep[k] = a(rou^k), centred."""
-        npoly = int(np.prod(coef.shape[:-1]))
-        out = self._out(tuple(coef.shape[:-1]) + (2 * D,), np.int16, device)
+        npoly = _lead(coef, 'coef', np.int16, self.d)
+        out = self._out(tuple(coef.shape[:-1]) + (2 * self.d,), np.int16, device)
         self._ck(self._lib.lcb_ntt_reference_repr_batch(self._ctx, _addr(coef), npoly, _addr(out)))
         return out
 
     def poly_mul(self, a, b, device: bool = False):
-        npoly = int(np.prod(a.shape[:-1]))
+        npoly = _lead(a, 'a', np.int16, self.d)
+        _want(b, 'b', np.int16, tuple(a.shape))
         out = self._out(tuple(a.shape), np.int16, device)
         self._ck(self._lib.lcb_poly_mul_batch(self._ctx, _addr(a), _addr(b), npoly, _addr(out)))
         return out
@@ -183,10 +260,10 @@ class Engine(object):
                   want_vk_ntt: bool = True, want_vk_coef: bool = True, device: bool = False):
         blob, off = self._rag(seeds)
         n = self._count(off)
-        sk_coef = self._out((n, 2, self.l, D), np.int16, device) if want_sk_coef else None
-        sk_ntt = self._out((n, 2, self.l, D), np.uint16, device) if want_sk_ntt else None
-        vk_ntt = self._out((n, 2, D), np.uint16, device) if want_vk_ntt else None
-        vk_coef = self._out((n, 2, D), np.int16, device) if want_vk_coef else None
+        sk_coef = self._out((n, 2, self.l, self.d), np.int16, device) if want_sk_coef else None
+        sk_ntt = self._out((n, 2, self.l, self.d), np.uint16, device) if want_sk_ntt else None
+        vk_ntt = self._out((n, 2, self.d), np.uint16, device) if want_vk_ntt else None
+        vk_coef = self._out((n, 2, self.d), np.int16, device) if want_vk_coef else None
         self._ck(self._lib.lcb_lm_keygen_batch(self._ctx, byref(sch), _addr(blob), _addr(off), n, _addr(sk_coef),
                                                _addr(sk_ntt), _addr(vk_ntt), _addr(vk_coef)))
         return sk_coef, sk_ntt, vk_ntt, vk_coef
@@ -201,7 +278,8 @@ class Engine(object):
     def lm_sign(self, sch: LcbScheme, sk_ntt, chmsgs, device: bool = False):
         blob, off = self._rag(chmsgs)
         n = self._count(off)
-        sig = self._out((n, self.l, D), np.int16, device)
+        _want(sk_ntt, 'sk_ntt', np.uint16, (n, 2, self.l, self.d))
+        sig = self._out((n, self.l, self.d), np.int16, device)
         self._ck(self._lib.lcb_lm_sign_batch(self._ctx, byref(sch), _addr(sk_ntt), _addr(blob), _addr(off), n,
                                              _addr(sig)))
         return sig
@@ -210,7 +288,11 @@ class Engine(object):
                   out=None):
         blob, off = self._rag(chmsgs)
         n = self._count(off)
-        verdict = out if out is not None else self._out((n,), np.uint8, device)
+        _want(vk_ntt, 'vk_ntt', np.uint16, (n, 2, self.d))
+        _want(sig, 'sig', np.int16, (n, self.l, self.d))
+        if st_ntt is not None:
+            _want(st_ntt, 'st_ntt', np.uint16, (n, self.d))
+        verdict = _want(out, 'out', np.uint8, (n,)) if out is not None else self._out((n,), np.uint8, device)
         self._ck(self._lib.lcb_lm_verify_batch(self._ctx, byref(sch), _addr(vk_ntt), _addr(blob), _addr(off),
                                                _addr(sig), _addr(st_ntt), n, bd, wt, _addr(verdict)))
         return verdict
@@ -218,17 +300,17 @@ class Engine(object):
     # ------------------------------------------------------------------ packed wire format
     def pack(self, values, bits: int, bias: int, device: bool = False, want_range: bool = False):
         """values int16/uint16 [..., 256] -> uint8 [..., 32*bits] (include/lcb200.h, lcb_pack_batch)."""
+        npoly = _lead(values, 'values', (np.int16, np.uint16), self.d)
         lead = tuple(values.shape[:-1])
-        npoly = int(np.prod(lead)) if lead else 1
-        packed = self._out(lead + (32 * bits,), np.uint8, device)
+        packed = self._out(lead + (self.d * bits // 8,), np.uint8, device)
         ok = self._out(lead, np.uint8, device) if want_range else None
         self._ck(self._lib.lcb_pack_batch(self._ctx, _addr(values), npoly, bits, bias, _addr(packed), _addr(ok)))
         return (packed, ok) if want_range else packed
 
     def unpack(self, packed, bits: int, bias: int, dtype=np.int16, device: bool = False):
+        npoly = _lead(packed, 'packed', np.uint8, self.d * bits // 8)
         lead = tuple(packed.shape[:-1])
-        npoly = int(np.prod(lead)) if lead else 1
-        out = self._out(lead + (D,), dtype, device)
+        out = self._out(lead + (self.d,), dtype, device)
         self._ck(self._lib.lcb_unpack_batch(self._ctx, _addr(packed), npoly, bits, bias, _addr(out)))
         return out
 
@@ -236,7 +318,9 @@ class Engine(object):
                          sig_bias: int, bd: int, wt: int, device: bool = False, out=None):
         blob, off = self._rag(chmsgs)
         n = self._count(off)
-        verdict = out if out is not None else self._out((n,), np.uint8, device)
+        _want(vk_packed, 'vk_packed', np.uint8, (n, 2, self.d * vk_bits // 8))
+        _want(sig_packed, 'sig_packed', np.uint8, (n, self.l, self.d * sig_bits // 8))
+        verdict = _want(out, 'out', np.uint8, (n,)) if out is not None else self._out((n,), np.uint8, device)
         self._ck(self._lib.lcb_lm_verify_packed_batch(self._ctx, byref(sch), _addr(vk_packed), vk_bits, _addr(blob),
                                                       _addr(off), _addr(sig_packed), sig_bits, sig_bias, n, bd, wt,
                                                       _addr(verdict)))
@@ -246,6 +330,7 @@ class Engine(object):
     def agg_coefs(self, sch: LcbScheme, agmsg, first: int, count: int, device: bool = False):
         if isinstance(agmsg, (str, bytes, bytearray)):
             agmsg = np.frombuffer(agmsg.encode() if isinstance(agmsg, str) else bytes(agmsg), dtype=np.uint8)
+        _want(agmsg, 'agmsg', np.uint8, (None,))
         pairs = self._out((count, sch.ag_wt, 2), np.int16, device)
         self._ck(self._lib.lcb_bklm_agg_coefs(self._ctx, byref(sch), _addr(agmsg), int(agmsg.shape[0]), first,
                                               count, _addr(pairs)))
@@ -253,26 +338,33 @@ class Engine(object):
 
     def aggregate_partial(self, sch: LcbScheme, sig_sorted, ag_pairs, device: bool = False):
         count = int(sig_sorted.shape[0])
-        partial = self._out((self.l, D), np.int32, device)
+        _want(sig_sorted, 'sig_sorted', np.int16, (count, self.l, self.d))
+        _want(ag_pairs, 'ag_pairs', np.int16, (count, sch.ag_wt, 2))
+        partial = self._out((self.l, self.d), np.int32, device)
         self._ck(self._lib.lcb_bklm_aggregate_partial(self._ctx, byref(sch), _addr(sig_sorted), _addr(ag_pairs),
                                                       None, 0, 0, count, _addr(partial)))
         return partial
 
     def aggregate_finish(self, partial_sum, device: bool = False):
-        out = self._out((self.l, D), np.int16, device)
+        _want(partial_sum, 'partial_sum', np.int32, (self.l, self.d))
+        out = self._out((self.l, self.d), np.int16, device)
         self._ck(self._lib.lcb_bklm_aggregate_finish(self._ctx, _addr(partial_sum), _addr(out)))
         return out
 
     def aggverify_partial(self, sch: LcbScheme, vk_ntt_sorted, chmsgs_sorted, ag_pairs, device: bool = False):
         blob, off = self._rag(chmsgs_sorted)
         count = self._count(off)
-        partial = self._out((D,), np.int32, device)
+        _want(vk_ntt_sorted, 'vk_ntt_sorted', np.uint16, (count, 2, self.d))
+        _want(ag_pairs, 'ag_pairs', np.int16, (count, sch.ag_wt, 2))
+        partial = self._out((self.d,), np.int32, device)
         self._ck(self._lib.lcb_bklm_aggverify_partial(self._ctx, byref(sch), _addr(vk_ntt_sorted), _addr(blob),
                                                       _addr(off), _addr(ag_pairs), None, 0, 0, count,
                                                       _addr(partial)))
         return partial
 
     def aggverify_finish(self, partial_sum, ag_sig, total: int, ag_cap: int, avf_bd: int, avf_wt: int) -> bool:
+        _want(partial_sum, 'partial_sum', np.int32, (self.d,))
+        _want(ag_sig, 'ag_sig', np.int16, (self.l, self.d))
         verdict = np.zeros(1, dtype=np.uint8)
         self._ck(self._lib.lcb_bklm_aggverify_finish(self._ctx, _addr(partial_sum), _addr(ag_sig), total, ag_cap,
                                                      avf_bd, avf_wt, _addr(verdict)))
@@ -283,27 +375,31 @@ class Engine(object):
                want_st_coef: bool = True, device: bool = False):
         blob, off = self._rag(seeds)
         n = self._count(off)
-        wit = self._out((n, self.l, D), np.int16, device) if want_wit else None
-        st_ntt = self._out((n, D), np.uint16, device) if want_st_ntt else None
-        st_coef = self._out((n, D), np.int16, device) if want_st_coef else None
+        wit = self._out((n, self.l, self.d), np.int16, device) if want_wit else None
+        st_ntt = self._out((n, self.d), np.uint16, device) if want_st_ntt else None
+        st_coef = self._out((n, self.d), np.int16, device) if want_st_coef else None
         self._ck(self._lib.lcb_adaptor_witgen_batch(self._ctx, byref(sch), _addr(blob), _addr(off), n, _addr(wit),
                                                     _addr(st_ntt), _addr(st_coef)))
         return wit, st_ntt, st_coef
 
     def vec_add(self, a, b, device: bool = False):
-        npoly = int(np.prod(a.shape[:-1]))
+        npoly = _lead(a, 'a', np.int16, self.d)
+        _want(b, 'b', np.int16, tuple(a.shape))
         out = self._out(tuple(a.shape), np.int16, device)
         self._ck(self._lib.lcb_vec_add_batch(self._ctx, _addr(a), _addr(b), npoly, _addr(out)))
         return out
 
     def vec_sub(self, a, b, device: bool = False):
-        npoly = int(np.prod(a.shape[:-1]))
+        npoly = _lead(a, 'a', np.int16, self.d)
+        _want(b, 'b', np.int16, tuple(a.shape))
         out = self._out(tuple(a.shape), np.int16, device)
         self._ck(self._lib.lcb_vec_sub_batch(self._ctx, _addr(a), _addr(b), npoly, _addr(out)))
         return out
 
     def witness_verify(self, wit_coef, st_ntt, bd: int, wt: int, device: bool = False):
         n = int(wit_coef.shape[0])
+        _want(wit_coef, 'wit_coef', np.int16, (n, self.l, self.d))
+        _want(st_ntt, 'st_ntt', np.uint16, (n, self.d))
         verdict = self._out((n,), np.uint8, device)
         self._ck(self._lib.lcb_adaptor_witness_verify_batch(self._ctx, _addr(wit_coef), _addr(st_ntt), n, bd, wt,
                                                             _addr(verdict)))

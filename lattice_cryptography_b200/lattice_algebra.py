@@ -97,17 +97,33 @@ def engine_for(lp: LatticeParameters, secpar: Optional[int] = None, device: Opti
     key = (secpar, lp.modulus, lp.degree, lp.length, dev)
     if key not in _ENGINES:
         _ENGINES[key] = Engine(secpar, lp.modulus, lp.degree, lp.length, device=dev)
-        _ENGINES[key]._key_ch_token = None
     return _ENGINES[key]
 
 
 def ensure_key_ch(eng: Engine, key_ch: 'PolynomialVector'):
     """Make `key_ch` the NTT-resident public row of the context (uploaded once per distinct row)."""
-    coef = key_ch.coef
-    token = coef.tobytes()
-    if getattr(eng, '_key_ch_token', None) != token:
-        eng.set_key_ch(coef)
-        eng._key_ch_token = token
+    eng.ensure_key_ch(key_ch.coef)
+
+
+class BoundEngine(object):
+    """An Engine paired with one public row: every method call takes the engine's lock, makes `key_ch` the resident
+    row if another pp (or another thread) replaced it, and then runs - so two parameter sets that share a cached
+    context, or two threads, cannot hand each other's key_ch to a keygen / verify call."""
+
+    def __init__(self, eng: Engine, key_ch_coef: np.ndarray):
+        self._eng, self._coef = eng, key_ch_coef
+
+    def __getattr__(self, name):
+        attr = getattr(self._eng, name)
+        if not callable(attr):
+            return attr
+        eng, coef = self._eng, self._coef
+
+        def call(*a, **k):
+            with eng.lock:
+                eng.ensure_key_ch(coef)
+                return attr(*a, **k)
+        return call
 
 
 # ------------------------------------------------------------------------------- ring elements

@@ -16,7 +16,7 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from .engine import make_scheme
-from .lattice_algebra import (LatticeParameters, Polynomial, PolynomialVector, engine_for, ensure_key_ch,
+from .lattice_algebra import (BoundEngine, LatticeParameters, Polynomial, PolynomialVector, engine_for, ensure_key_ch,
                               hash2polynomial, hash2polynomialvector)
 from .one_time_keys import (ALLOWABLE_SECPARS, OneTimeSigningKey, OneTimeVerificationKey, SchemeParameters,
                             SecretSeed, UNIFORM_INFINITY_WEIGHT, bits_to_decode, bits_to_indices)
@@ -51,10 +51,10 @@ def make_setup_parameters(secpar: SecurityParameter) -> PublicParameters:
 
 # ------------------------------------------------------------------------------- engine plumbing
 def _ctx(pp: PublicParameters):
-    """(engine, lcb_scheme) for a pp dict; uploads key_ch if this context holds a different row."""
+    """(engine bound to pp's key_ch, lcb_scheme) for a pp dict; the row is (re)uploaded inside each call whenever the
+    cached context holds a different one."""
     sp = pp['scheme_parameters']
-    eng = engine_for(sp.lp, sp.secpar)
-    ensure_key_ch(eng, sp.key_ch)
+    eng = BoundEngine(engine_for(sp.lp, sp.secpar), sp.key_ch.coef)
     sch = make_scheme(sk_bd=pp.get('sk_bd', 1), sk_wt=pp.get('sk_wt', 1), ch_bd=pp.get('ch_bd', 1),
                       ch_wt=pp.get('ch_wt', 1), ag_bd=pp.get('ag_bd', 1), ag_wt=pp.get('ag_wt', 1),
                       wit_bd=pp.get('wit_bd', 1), wit_wt=pp.get('wit_wt', 1), sk_salt=pp.get('sk_salt', 'SK_SALT'),
@@ -148,9 +148,18 @@ def keygen_core(pp: PublicParameters, num_keys_to_gen: int = 1, seeds: List[Secr
 
 def keygen(pp: PublicParameters, num_keys_to_gen: int = 1, seeds: List[SecretSeed] = None,
            multiprocessing: bool = None) -> List[OneTimeKeyTuple]:
-    """Same contract as the reference's Pool wrapper (order preserved, exactly num_keys_to_gen tuples);
-    the batch is sharded over GPU threads instead of worker processes."""
-    return keygen_core(pp=pp, num_keys_to_gen=num_keys_to_gen, seeds=seeds if seeds else None)
+    """Same contract as the reference's Pool wrapper (lm_one_time_sigs.py:100-123), order preserved; the batch is
+    one pass of the sampler + row-vector-product kernels instead of a process pool.  The observable corner
+    cases of the wrapper are kept: without "multiprocessing" (fewer than 16 keys by default) the arguments go to
+    keygen_core unchanged, so an empty seed list raises; with it, a falsy seed list means "no seeds" and a seed
+    list of another length yields min(len(seeds), num_keys_to_gen) keys."""
+    if multiprocessing is None:
+        multiprocessing = num_keys_to_gen >= 16
+    if (not multiprocessing) or num_keys_to_gen == 1:
+        return keygen_core(pp=pp, num_keys_to_gen=num_keys_to_gen, seeds=seeds)
+    if not seeds:
+        return keygen_core(pp=pp, num_keys_to_gen=num_keys_to_gen, seeds=None)
+    return keygen_core(pp=pp, num_keys_to_gen=len(seeds), seeds=seeds)[:num_keys_to_gen]
 
 
 def make_signature_challenge(pp: PublicParameters, otvk: OneTimeVerificationKey, msg: Message) -> Challenge:
@@ -169,9 +178,18 @@ def sign(pp: PublicParameters, otk: OneTimeKeyTuple, msg: Message) -> Signature:
     return PolynomialVector(sp.lp, const_time_flag=False, _coef=sig[0])
 
 
+def well_formed(lp: LatticeParameters, vec) -> bool:
+    """True iff `vec` is a PolynomialVector over `lp` with exactly lp.length entries of lp.degree coefficients.
+    The reference's verify functions pair entries with zip() and so tolerate a short vector; the engine reads
+    l*d coefficients from the buffer it is given, so a malformed signature is rejected here (verdict False)."""
+    return isinstance(vec, PolynomialVector) and vec.lp == lp and tuple(vec.coef.shape) == (lp.length, lp.degree)
+
+
 def verify(pp: PublicParameters, otvk: OneTimeVerificationKey, msg: Message, sig: Signature) -> bool:
-    sig.const_time_flag = False
     sp = pp['scheme_parameters']
+    if not well_formed(sp.lp, sig):
+        return False
+    sig.const_time_flag = False
     sp.key_ch.const_time_flag = False
     otvk.left_key.const_time_flag = False
     otvk.right_key.const_time_flag = False
