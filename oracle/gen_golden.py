@@ -21,9 +21,10 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
+import ref_loader  # noqa: E402
 from ref_loader import load_reference  # noqa: E402
 
-otk_mod, lm, bklm, ad = load_reference()
+otk_mod, lm, bklm, ad = load_reference()      # real lattice_algebra underneath if reachable (oracle/l1.py)
 import lattice_algebra as la  # noqa: E402  (the restatement; ref_loader put it on sys.path)
 import schemes  # noqa: E402
 
@@ -63,7 +64,10 @@ def fix_key_ch(pp, secpar):
 
 
 def main():
-    arrays, meta = {}, {'key_ch_seed': KEY_CH_SEED, 'cases': {}}
+    # "l1": which lattice_algebra the reference's modules ran on when these vectors were made.  Anything but
+    # "lattice_algebra==0.1.1" means PARITY UNPINNED: the vectors then pin the engine to the
+    # restatement only.
+    arrays, meta = {}, {'key_ch_seed': KEY_CH_SEED, 'l1': ref_loader.L1_LABEL, 'cases': {}}
     for secpar in (128, 256):
         tag = f's{secpar}'
         # ---------------------------------------------------------------- LM-OTS
