@@ -543,6 +543,10 @@ struct KeccakHalfRhoPi<25> {
 
 // rc = this lane's halves of the 24 round constants (even-bit halves on even lanes, odd-bit halves on odd lanes).
 // All 32 lanes of the warp must be active and converged.
+// Measured dead end (tools/agg_coefs_timing.py, round 2): fetching the partner's raw odd-rho words and parities up front
+// and forming its theta-applied word locally (one dependent exchange per round instead of two, 5 more SHF) changes
+// nothing at one warp per scheduler (173 vs 174 ms) - a lone warp issues one instruction every two cycles whatever
+// the pipe, so the 17 SHFL count as much as the 90 ALU instructions and only the instruction total matters.
 __device__ __forceinline__ void keccak_f1600_half(KeccakHalf& s, const uint32_t* __restrict__ rc, const KeccakHalfRot& rot) {
 #pragma unroll 2
     for (int round = 0; round < 24; ++round) {

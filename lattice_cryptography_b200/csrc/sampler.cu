@@ -235,6 +235,7 @@ __global__ void __launch_bounds__(256) k_msg_interleave(const uint8_t* __restric
 
 constexpr int ABS2 = 64;   // threads per block = 32 sponges
 
+template <bool PREFETCH>
 __global__ void __launch_bounds__(ABS2) k_agg_coefs_il(SamplerArgs a) {
     __shared__ uint32_t rc_sh[2][24];
     if (threadIdx.x < 48) rc_sh[threadIdx.x / 24][threadIdx.x % 24] = c_keccak_rc2.v[threadIdx.x / 24][threadIdx.x % 24];
@@ -300,13 +301,24 @@ __global__ void __launch_bounds__(ABS2) k_agg_coefs_il(SamplerArgs a) {
     const unsigned nb = (unsigned)(nblocks > 0xFFFFFFFFll ? 0xFFFFFFFFll : nblocks);
     const unsigned max_nb = __reduce_max_sync(0xFFFFFFFFu, nb);
     uint32_t result = 0;
+    // The 17 message words of an interior block are requested one block AHEAD (before the permutation of the
+    // previous block, volatile so that ptxas keeps them there): with one warp per scheduler nothing else would
+    // cover the L2 round trip of a load issued at the top of the block.
+    uint32_t pre[17];
+    bool have = false;
+    auto interior = [&](int64_t g) { return g >= g0 && g + 17 <= g0 + nl; };
+    auto request = [&](int64_t g) {
+        const uint32_t* w = il + 2 * (g - g0);
+        LCB_CHECK(g - g0 >= 0 && g - g0 + 17 <= nl);
+#pragma unroll
+        for (int i = 0; i < 17; ++i) asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(pre[i]) : "l"(w + 2 * i));
+    };
     for (unsigned blk = 0; blk < max_nb; ++blk) {
         const int64_t g = (int64_t)blk * 17;
-        if (g >= g0 && g + 17 <= g0 + nl) {
-            const uint32_t* w = il + 2 * (g - g0);
-            LCB_CHECK(g - g0 >= 0 && g - g0 + 17 <= nl);
+        if (interior(g)) {
+            if (!have) request(g);
 #pragma unroll
-            for (int i = 0; i < 17; ++i) s.a[i] ^= __ldg(w + 2 * i);
+            for (int i = 0; i < 17; ++i) s.a[i] ^= pre[i];
         } else {
             // first / last blocks (salt, tail, padding): assembled from bytes, split on the fly
 #pragma unroll 1
@@ -318,6 +330,8 @@ __global__ void __launch_bounds__(ABS2) k_agg_coefs_il(SamplerArgs a) {
                     if (j == i) s.a[j] ^= h;
             }
         }
+        have = PREFETCH && interior(g + 17);
+        if (have) request(g + 17);
         keccak_f1600_half(s, rc, rot);
         if (blk + 1 == nb) result = s.a[0];
     }
@@ -378,8 +392,13 @@ unsigned agg_delta_mask(int salt_len, int64_t first, int64_t count) {
 
 bool agg_coefs_two_lane(int64_t n, int num_sms) {
     if (const char* env = getenv("LCB_AGG_LANES")) return atoi(env) == 2;       // tuning knob
-    // one thread per sponge fills the machine only from about two warps per scheduler upwards
-    return n <= (int64_t)num_sms * 4 * 32;
+    // Measured on B200 (tools/agg_coefs_timing.py, 59,754 permutations per stream): 8,192 streams 297 -> 164 ms,
+    // 16,384 streams 297 vs 302 ms, 65,536 streams 1,104 -> 1,000 ms.  Two lanes win while the lane pairs still fit
+    // one warp per scheduler (the one-thread form then leaves half the schedulers empty) and again once there are
+    // enough warps for the finer grain to balance (7 instead of 3.5 warps per scheduler); in between both forms put
+    // two warps on the busiest scheduler and tie.
+    const int64_t schedulers = (int64_t)num_sms * 4;
+    return n <= schedulers * 16 || n >= schedulers * 64;
 }
 
 cudaError_t launch_agg_coefs(const SamplerArgs& a, int num_sms, cudaStream_t st) {
@@ -395,7 +414,12 @@ cudaError_t launch_agg_coefs(const SamplerArgs& a, int num_sms, cudaStream_t st)
             if (e != cudaSuccess) return e;
         }
         int64_t blocks = (2 * a.n + ABS2 - 1) / ABS2;
-        k_agg_coefs_il<<<(unsigned)blocks, ABS2, 0, st>>>(a);
+        // few warps (at most about one per scheduler): nothing hides a load, so request a block ahead (80 registers);
+        // many warps: stay at 64 registers so that 2^16 streams (4,096 warps) are resident at once
+        bool prefetch = 2 * a.n <= (int64_t)num_sms * 4 * 32 * 2;
+        if (const char* env = getenv("LCB_AGG_PREFETCH")) prefetch = atoi(env) != 0;
+        auto kern = prefetch ? k_agg_coefs_il<true> : k_agg_coefs_il<false>;
+        kern<<<(unsigned)blocks, ABS2, 0, st>>>(a);
         return cudaGetLastError();
     }
     int64_t blocks = (a.n + ABS - 1) / ABS;

@@ -328,11 +328,18 @@ def test_bklm_golden(engines, golden, secpar):
         assert not e.aggverify_finish(vp, np.zeros_like(ag_sig), cap, cap, case['avf_bd'], case['avf_wt'])
 
 
-@pytest.mark.parametrize('n,first,msg_len', [(1, 0, 0), (130, 0, 5), (257, 95, 1000), (1500, 9990, 33000), (64, 99999990, 271)])
-def test_agg_coefs_vs_hashlib(engines, n, first, msg_len):
+@pytest.mark.parametrize('lanes', [1, 2])
+@pytest.mark.parametrize('n,first,msg_len', [(1, 0, 0), (130, 0, 5), (257, 95, 1000), (1500, 9990, 33000), (64, 99999990, 271),
+                                             (40, 0, 7), (40, 0, 8), (33, 90, 121), (33, 90, 128), (33, 90, 129),
+                                             (19, 9_999_999_990, 4000), (70, 999_999_999_999_999_980, 300)])
+def test_agg_coefs_vs_hashlib(engines, monkeypatch, n, first, msg_len, lanes):
     """make_agg_coefs (bklm_one_time_agg_sigs.py:78-81) for many indices over one shared message:
     ag_i = +-X^k with k = first digest byte, sign = next bit of SHAKE256('AG_SALT' + str(i) + msg).
-    Covers every salt-length class (1..8 digits), unaligned messages and sharded index ranges."""
+    Covers every salt-length class (1..18 digits, i.e. every byte phase of the message against the 64-bit words of
+    the sponge), digit-count changes inside a warp (streams of one warp then need different numbers of rate blocks),
+    messages shorter than a word / a block, unaligned messages and sharded index ranges - for both kernels: one
+    thread per sponge (k_agg_coefs) and two lanes per sponge over the pre-split message (k_agg_coefs_il)."""
+    monkeypatch.setenv('LCB_AGG_LANES', str(lanes))
     e = engines[128]
     sch = scheme(128)
     rng = np.random.default_rng(n + msg_len)

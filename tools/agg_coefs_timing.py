@@ -20,8 +20,10 @@ agmsg = ('[' + ', '.join(f"(<lattice_cryptography.one_time_keys.OneTimeVerificat
                          f"'{bytes(r).decode()}')" for i, r in enumerate(bits)) + ']').encode()
 d_msg = torch.from_numpy(np.frombuffer(agmsg, dtype=np.uint8).copy()).cuda()
 perms = count * ((len(agmsg) + 12) // 136 + 1)
-for lanes in (1, 2):
+variants = [(1, 0, 0), (2, 0, 0), (2, 0, 1)]
+for lanes, early, prefetch in variants:
     os.environ['LCB_AGG_LANES'] = str(lanes)
+    os.environ['LCB_AGG_PREFETCH'] = str(prefetch)
     eng = Engine(128, 11777, 256, 13)
     eng.use_torch_stream()
     sch = make_scheme()
@@ -31,10 +33,10 @@ for lanes in (1, 2):
         pairs = eng.agg_coefs(sch, d_msg, first, count, device=True)
         torch.cuda.synchronize()
         ms, _ = eng.profile_read('agg_coefs')
-        print(f'lanes={lanes} N=2^{log2n} count={count} first={first}: {ms:.2f} ms, {perms / ms / 1e6:.3f} Gperm/s', flush=True)
+        print(f'lanes={lanes} early={early} prefetch={prefetch} N=2^{log2n} count={count} first={first}: {ms:.2f} ms, {perms / ms / 1e6:.3f} Gperm/s', flush=True)
     got = pairs.cpu().numpy()[:, 0, :]
     for i in sorted(set([0, 1, count // 3, count - 2, count - 1] + list(rng.integers(0, count, 6)))):
         dg = hashlib.shake_256(b'AG_SALT' + str(first + i).encode() + agmsg).digest(2)
         assert (int(got[i, 0]), int(got[i, 1])) == (dg[0], 1 if dg[1] & 0x80 else -1), (lanes, i)
-    print(f'lanes={lanes}: hashlib subsample ok')
+    print(f'lanes={lanes} early={early} prefetch={prefetch}: hashlib subsample ok')
     eng.close()
