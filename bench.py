@@ -39,6 +39,9 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-secondary', action='store_true', help='skip the keygen+sign / BKLM / adaptor measurements')
     ap.add_argument('--bklm-log2n', type=int, default=16, help='log2 of signatures per aggregate (whole job)')
+    ap.add_argument('--keygen-log2n', type=int, default=20, help='configs[2]: log2 of seeds, whole job (split over the GPUs)')
+    ap.add_argument('--adaptor-log2n', type=int, default=18, help='configs[4]: log2 of instances, whole job')
+    ap.add_argument('--cpu-bklm-log2n', type=int, default=8, help='CPU baseline: largest BKLM aggregate actually run')
     return ap.parse_args()
 
 
@@ -46,17 +49,35 @@ def workload_name(a):
     return f'lm_ots_verify_batch secpar={a.secpar} n=2^{a.log2n} triples per GPU'
 
 
+def engine_config(a):
+    p = SHIPPED[a.secpar]
+    n = 1 << a.log2n
+    gb = (n * p['l'] * D * 2 + n * 2 * D * 2 + n * (86 + a.secpar)) / 1e9
+    return {'workload': workload_name(a), 'secpar': a.secpar, 'q': p['q'], 'd': D, 'l': p['l'], 'triples_per_gpu': n,
+            'tampered_every': 64, 'l2': f'inputs {gb:.2f} GB per pass >> 126 MB L2, no flush needed'}
+
+
 # ---------------------------------------------------------------------------------------------------
-def cpu_leg(secpar, per_core):
-    """The oracle port on every host core, bounded sample (see oracle/cpu_baseline.py)."""
+def cpu_leg(secpar, per_core, extras=None):
+    """The oracle port on every host core, bounded sample (see oracle/cpu_baseline.py).  `extras` = args: also time
+    the other halves of the metric (keygen / sign phases, BKLM with the a*N^2 + b*N extrapolation of BASELINE.md
+    section 3, the adaptor flow) for the `also` / `secondary` figures of the line."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import cpu_baseline
     cores = os.cpu_count() or 1
     sample = per_core * cores
     r = cpu_baseline.lm_verify_throughput(secpar, sample, cores)
-    return {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
-            'sample': f'{sample} honest LM-OTS triples at secpar {secpar} ({per_core} per core), verify() only timed, '
-                      f'pure-Python port of lattice_algebra (oracle/), slowest worker {r["elapsed_s"]:.2f} s'}
+    leg = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
+           'sample': f'{sample} honest LM-OTS triples at secpar {secpar} ({per_core} per core), verify() only timed, '
+                     f'pure-Python port of lattice_algebra (oracle/), slowest worker {r["elapsed_s"]:.2f} s'}
+    if extras is not None:
+        t0 = time.perf_counter()
+        ns = tuple(n for n in (2, 16, 64, 256, 1024) if n <= (1 << extras.cpu_bklm_log2n))
+        leg['phases_secpar256'] = cpu_baseline.lm_phase_throughput(256, max(cores, 8), cores)
+        leg['bklm'] = cpu_baseline.bklm_extrapolation(128, ns=ns, target=1 << extras.bklm_log2n, nproc=cores)
+        leg['adaptor'] = cpu_baseline.adaptor_throughput(128, 64, cores)
+        leg['extras_wall_s'] = time.perf_counter() - t0
+    return leg
 
 
 def reference_arm(a):
@@ -74,7 +95,8 @@ def reference_arm(a):
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps,
             'warmup': a.warmup, 'ms_per_step': 1e3 * (time.perf_counter() - t0) / (a.warmup + a.steps),
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'python-int', 'data': 'synthetic',
-            'config': {'workload': workload_name(a), 'l2': 'n/a (CPU)'},
+            # the engine arm's config, key for key (each step here is a bounded sample of that workload, see cpu_baseline.sample)
+            'config': engine_config(a),
             'cpu_baseline': leg,
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
@@ -207,6 +229,50 @@ def _timed(torch, dist, world, dev, fn, reps=3):
     return float(ms.item())
 
 
+def _peaks():
+    """Roofline denominators: measured HBM copy bandwidth (driver-written MEASURED_PEAKS.json, else the profiling
+    recipe's fallback) and the integer issue limit 148 SMs x 4 schedulers x 32 lanes x max SM clock."""
+    peaks, src = {}, 'fallback (B200_PROFILING.md)'
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            peaks, src = json.load(f), 'MEASURED_PEAKS.json'
+    except OSError:
+        pass
+    mhz = peaks.get('sm_max_mhz', 1965.0)
+    return {'hbm_gbs': peaks.get('hbm_gbs', 6650.0), 'source': src, 'sm_max_mhz': mhz,
+            'int_tinstr_s': 148 * 128 * mhz * 1e6 / 1e12}
+
+
+def _ncu_summary(kernel):
+    """Figures of the newest committed ncu --set full digest of `kernel` (profiles/prof_r*_<kernel>.summary.txt), or
+    None.  Only a digest that names its capture batch and commit (tools/digest_profiles.sh writes a `# capture:`
+    line) is used: numbers of an older build must not ride along silently."""
+    import glob
+    import re
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', f'prof_r*_{kernel}.summary.txt'))):
+        txt = open(path).read()
+        cap = re.search(r'# capture: units=(\d+) commit=(\w+)', txt)
+        if not cap:
+            continue
+        num = lambda key: (lambda m: float(m.group(1).replace(',', '')) if m else None)(re.search(re.escape(key) + r'\s+([\d.,]+)', txt))
+        unit = lambda key: (lambda m: m.group(1) if m else '')(re.search(re.escape(key) + r'\s+[\d.,]+\s+(\w+)', txt))
+        scale = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}
+        rd, wr = num('dram__bytes_read.sum'), num('dram__bytes_write.sum')
+        if rd is None or wr is None:
+            continue
+        units = int(cap.group(1))
+        best = {'source': os.path.relpath(path, ROOT), 'commit': cap.group(2), 'units_per_captured_launch': units,
+                'dram_bytes_per_unit': (rd * scale.get(unit('dram__bytes_read.sum'), 1.0) +
+                                        wr * scale.get(unit('dram__bytes_write.sum'), 1.0)) / units,
+                'warp_instr_per_unit': (num('smsp__inst_executed.sum') or 0) / units,
+                'issue_active_pct': num('smsp__issue_active.avg.pct_of_peak_sustained_active'),
+                'pipe_alu_pct': num('sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active'),
+                'pipe_fma_pct': num('sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active'),
+                'pipe_lsu_pct': num('sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active')}
+    return best
+
+
 def _engine(secpar, local, np):
     from lattice_cryptography_b200 import Engine, make_scheme
     p = SHIPPED[secpar]
@@ -218,10 +284,21 @@ def _engine(secpar, local, np):
     return eng, sch, p
 
 
+def _c_oracle():
+    """oracle/lcb_oracle.c through ctypes: the CHECKER of the secondary legs (never timed, never on the product path)."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import c_oracle
+    return c_oracle
+
+
+def _chmsg_str(ch_row):
+    return bytes(ch_row.tolist())
+
+
 def secondary_keygen_sign(a, rank, local, world, torch, np, dist):
-    """configs[2]: keygen + sign from synthetic seeds at secpar 256; 2^17 seeds per GPU (the config's 2^20
-    seeds over 8 GPUs)."""
-    class A: secpar, log2n = 256, 17
+    """configs[2]: keygen + sign from 2^20 synthetic seeds at secpar 256, split over the GPUs (2^20 on one GPU at
+    N = 1); a random subsample of keys and signatures is compared coefficient by coefficient with the C oracle."""
+    class A: secpar, log2n = 256, max(0, a.keygen_log2n - (world.bit_length() - 1))
     eng, sch, p = _engine(256, local, np)
     dev = f'cuda:{local}'
     n = 1 << A.log2n
@@ -231,14 +308,30 @@ def secondary_keygen_sign(a, rank, local, world, torch, np, dist):
     out = {}
 
     def run():
+        out.clear()
         _, sk_ntt, vk_ntt, _ = eng.lm_keygen(sch, d_seeds, want_sk_coef=False, want_vk_coef=False, device=True)
         out['sig'] = eng.lm_sign(sch, sk_ntt, d_ch, device=True)
         out['vk'] = vk_ntt
     ms = _timed(torch, dist, world, dev, run, reps=3)
     ok = bool(eng.lm_verify(sch, out['vk'], d_ch, out['sig'], p['vf_bd'], p['vf_wt'], device=True).all().item())
+    # ---- checker: 12 random instances against the C oracle (keys from the seed, signature from the hash input)
+    orc = _c_oracle()
+    op = orc.params(256, p['q'], p['l'], p['sk_bd'], p['ch_wt'])
+    key_ch, _ = eng.hash2polyvec('KEY_CH_SEED', [KEY_CH_SEED], p['q'] // 2, D, p['l'])
+    pick = np.sort(np.random.default_rng(99 + rank).choice(n, 12, replace=False))
+    d_pick = torch.from_numpy(pick).to(dev)
+    vk_coef = eng.ntt_inv(out['vk'].view(torch.int16)[d_pick].contiguous().view(torch.uint16))
+    sig_pick = out['sig'][d_pick].cpu().numpy()
+    matches = 0
+    for j, i in enumerate(pick):
+        skl, skr, vkl, vkr = orc.lm_keygen(op, np.ascontiguousarray(key_ch[0]), bytes(seeds[i * 256:(i + 1) * 256].tolist()))
+        osig = orc.lm_sign(op, skl, skr, _chmsg_str(ch[i]))
+        matches += int(np.array_equal(vkl, vk_coef[j, 0]) and np.array_equal(vkr, vk_coef[j, 1]) and
+                       np.array_equal(osig, sig_pick[j]))
     eng.close()
     perms = 2 * 2853 + 26
-    return {'keys_per_s': world * n / (ms * 1e-3), 'ms': ms, 'n_per_gpu': n, 'all_verify': ok,
+    return {'keys_per_s': world * n / (ms * 1e-3), 'ms': ms, 'n_per_gpu': n, 'n_total': world * n, 'all_verify': ok,
+            'oracle_subsample': {'checked': len(pick), 'bit_exact': matches, 'checker': 'oracle/lcb_oracle.c'},
             'keccak_gperm_s_per_gpu': n * perms / (ms * 1e-3) / 1e9, 'keccak_roofline_gperm_s': 4.28}
 
 
@@ -278,7 +371,12 @@ def secondary_verify_secpar256(a, rank, local, world, torch, np, dist):
 
 def secondary_bklm(a, rank, local, world, torch, np, dist):
     """configs[3]: aggregate + aggregate-verify of 2^k signatures per aggregate (secpar 128), the sorted list
-    sharded over the ranks, ONE reduce of int32 partial sums each."""
+    sharded over the ranks, ONE reduce of int32 partial sums each.  Two rows:
+      (i)  exact reference semantics, including the O(N^2) aggregation-coefficient hashing (Keccak-bound);
+      (ii) the algebra alone with the coefficients supplied: k_agg_partial (a pure HBM stream, 6,656 B per
+           signature) and challenge sampler + k_aggv_partial, on 2^k signatures PER GPU.
+    A hashlib subsample checks the coefficients and the aggregate is compared with a numpy statement of the sum."""
+    import hashlib
     from lattice_cryptography_b200.distributed import reduce_partial, shard_range
     class A: secpar, log2n = 128, a.bklm_log2n
     eng, sch, p = _engine(128, local, np)
@@ -290,7 +388,8 @@ def secondary_bklm(a, rank, local, world, torch, np, dist):
     bits = rng.integers(0, 2, (total, 32), dtype=np.uint8) + ord('0')
     msgs = [bytes(r).decode() for r in bits]
     ident = [f'<lattice_cryptography.one_time_keys.OneTimeVerificationKey object at 0x7f{16 * i:010x}>' for i in range(total)]
-    agmsg = np.frombuffer(('[' + ', '.join(f"({k}, '{m}')" for k, m in zip(ident, msgs)) + ']').encode(), dtype=np.uint8)
+    agmsg_b = ('[' + ', '.join(f"({k}, '{m}')" for k, m in zip(ident, msgs)) + ']').encode()
+    agmsg = np.frombuffer(agmsg_b, dtype=np.uint8)
     d_agmsg = torch.from_numpy(agmsg.copy()).to(dev)
     seeds = [bin((0x9E3779B97F4A7C15 * (i + 1)) % (1 << 128))[2:].zfill(128) for i in range(start, start + count)]
     chm = [k + ', ' + m for k, m in zip(ident[start:start + count], msgs[start:start + count])]
@@ -299,12 +398,15 @@ def secondary_bklm(a, rank, local, world, torch, np, dist):
     d_chm = (torch.from_numpy(cb.copy()).to(dev), torch.from_numpy(co).to(dev))
     _, sk_ntt, vk_ntt, _ = eng.lm_keygen(sch, seeds, want_sk_coef=False, want_vk_coef=False, device=True)
     sigs = eng.lm_sign(sch, sk_ntt, d_chm, device=True)
+    del sk_ntt
     res = {}
 
+    # ---- row (i): exact
     def agg():
         ag = eng.agg_coefs(sch, d_agmsg, start, count, device=True)
         part = eng.aggregate_partial(sch, sigs, ag, device=True)
         part = reduce_partial(part)
+        res['ag'] = ag
         if rank == 0:
             res['ag_sig'] = eng.aggregate_finish(part, device=True)
     ms_agg = _timed(torch, dist, world, dev, agg, reps=1)
@@ -327,13 +429,74 @@ def secondary_bklm(a, rank, local, world, torch, np, dist):
     eng.agg_coefs(sch, d_agmsg, start, count, device=True)
     coef_ms, _ = eng.profile_read('agg_coefs')
     eng.profile(False)
+
+    # ---- checker (untimed): coefficients against hashlib on this rank's shard, the aggregate against numpy
+    coefs = res['ag'].cpu().numpy()
+    pick = sorted({0, 1, count // 2, count - 1} | set(int(i) for i in rng.integers(0, count, 8)))
+    h0 = hashlib.shake_256(b'AG_SALT')
+    coef_ok = 0
+    for i in pick:
+        h = h0.copy()
+        h.update(str(start + i).encode() + agmsg_b)
+        dg = h.digest(2)
+        coef_ok += int((int(coefs[i, 0, 0]), int(coefs[i, 0, 1])) == (dg[0], 1 if dg[1] & 0x80 else -1))
+    sum_ok = None
+    if world == 1 and total <= (1 << 16):
+        h_sig = sigs.cpu().numpy()
+        acc = np.zeros((p['l'], D), dtype=np.int64)
+        pp_ = np.arange(D)
+        for a0 in range(0, total, 2048):
+            k = coefs[a0:a0 + 2048, 0, 0].astype(np.int64)[:, None]
+            src = (pp_[None, :] - k) & (D - 1)
+            sign = np.where(pp_[None, :] < k, -1, 1) * coefs[a0:a0 + 2048, 0, 1].astype(np.int64)[:, None]
+            rot = np.take_along_axis(h_sig[a0:a0 + 2048].astype(np.int64),
+                                     np.broadcast_to(src[:, None, :], (src.shape[0], p['l'], D)), axis=2)
+            acc += (rot * sign[:, None, :]).sum(axis=0)
+        want = acc % p['q']
+        want = np.where(want > (p['q'] - 1) // 2, want - p['q'], want).astype(np.int16)
+        sum_ok = bool(np.array_equal(want, ag_sig.cpu().numpy()))
+        del h_sig
+
+    # ---- row (ii): coefficients supplied, 2^k signatures per GPU
+    reps_ = total // count
+    sig_ii = sigs if reps_ == 1 else sigs.repeat(reps_, 1, 1)
+    vk_ii = vk_ntt if reps_ == 1 else vk_ntt.view(torch.int16).repeat(reps_, 1, 1).view(torch.uint16)
+    ag_ii = res['ag'] if reps_ == 1 else res['ag'].repeat(reps_, 1, 1)
+    chm_ii = d_chm if reps_ == 1 else (d_chm[0].repeat(reps_), torch.arange(total + 1, device=dev, dtype=torch.int64) * (cb.shape[0] // count))
+    n_ii = int(sig_ii.shape[0])
+    eng.profile(True)
+    ii = {}
+    for name, fn, kern in (('aggregate', lambda: eng.aggregate_partial(sch, sig_ii, ag_ii, device=True), 'agg_partial'),
+                           ('aggregate_verify', lambda: eng.aggverify_partial(sch, vk_ii, chm_ii, ag_ii, device=True), 'aggv_partial')):
+        fn()
+        eng.profile_reset()
+        ms = _timed(torch, dist, world, dev, fn, reps=3)
+        k_ms, k_n = eng.profile_read(kern)
+        ii[name] = {'ms': ms, 'sigs_per_s_per_gpu': n_ii / (ms * 1e-3), 'kernel': 'k_' + kern,
+                    'kernel_ms_per_launch': k_ms / max(k_n, 1)}
+    eng.profile(False)
+    peaks = _peaks()
+    sig_bytes = p['l'] * D * 2
+    k = ii['aggregate']
+    k['roofline'] = {'bound': 'hbm', 'algorithmic_bytes_per_unit': sig_bytes + 4,
+                     'achieved': (sig_bytes + 4) * n_ii / (k['kernel_ms_per_launch'] * 1e-3) / 1e9, 'peak': peaks['hbm_gbs'],
+                     'unit': 'GB/s'}
+    k['roofline']['frac'] = k['roofline']['achieved'] / k['roofline']['peak']
+    k = ii['aggregate_verify']
+    instr = 8192 + 3 * 256 * 6          # one NTT-256 + three pointwise passes per signature (Keccak is the sampler's)
+    k['roofline'] = {'bound': 'int_issue', 'algorithmic_instr_per_unit': instr,
+                     'achieved': instr * n_ii / (k['kernel_ms_per_launch'] * 1e-3) / 1e12, 'peak': peaks['int_tinstr_s'],
+                     'unit': 'Tinstr/s'}
+    k['roofline']['frac'] = k['roofline']['achieved'] / k['roofline']['peak']
     eng.close()
     perms = count * ((len(agmsg) + 12) // 136 + 1)
     return {'sigs_per_aggregate': total, 'aggregate_sigs_per_s': total / (ms_agg * 1e-3),
             'aggregate_verify_sigs_per_s': total / (ms_aggv * 1e-3), 'aggregate_ms': ms_agg,
             'aggregate_verify_ms': ms_aggv, 'verdict': res.get('ok') if rank == 0 else None,
-            'agmsg_bytes': int(len(agmsg)), 'agg_coefs_ms_rank0': coef_ms,
-            'agg_coefs_gperm_s_per_gpu': perms / (coef_ms * 1e-3) / 1e9, 'keccak_roofline_gperm_s': 4.28}
+            'checker': {'coefficients_vs_hashlib': f'{coef_ok}/{len(pick)}', 'aggregate_vs_numpy_sum': sum_ok},
+            'agmsg_bytes': int(len(agmsg)), 'agg_coefs_ms_rank0': coef_ms, 'streams_per_gpu': count,
+            'agg_coefs_gperm_s_per_gpu': perms / (coef_ms * 1e-3) / 1e9, 'keccak_roofline_gperm_s': 4.28,
+            'row_ii_coefficients_supplied': dict(ii, signatures_per_gpu=n_ii)}
 
 
 def secondary_single_ops(a, rank, local, world, torch, np, dist):
@@ -371,8 +534,10 @@ def secondary_single_ops(a, rank, local, world, torch, np, dist):
 
 
 def secondary_adaptor(a, rank, local, world, torch, np, dist):
-    """configs[4]: adaptor pre-sign / pre-verify / adapt / verify / extract / witness-verify, 2^15 instances per GPU."""
-    class A: secpar, log2n = 128, 15
+    """configs[4]: adaptor pre-sign / pre-verify / adapt / verify / extract / witness-verify over 2^18 instances, split
+    over the GPUs (2^18 on one GPU at N = 1); a random subsample of every object and verdict is compared with the
+    C oracle."""
+    class A: secpar, log2n = 128, max(0, a.adaptor_log2n - (world.bit_length() - 1))
     eng, sch, p = _engine(128, local, np)
     dev = f'cuda:{local}'
     n = 1 << A.log2n
@@ -391,8 +556,35 @@ def secondary_adaptor(a, rank, local, world, torch, np, dist):
     t['extract'] = _timed(torch, dist, world, dev, lambda: st.__setitem__('ext', eng.vec_sub(st['sig'], st['presig'], device=True)))
     t['witness_verify'] = _timed(torch, dist, world, dev, lambda: st.__setitem__('wv', eng.witness_verify(st['ext'], st['st_ntt'], ext_bd, 256, device=True)))
     ok = bool(st['pv'].all().item() and st['vv'].all().item() and st['wv'].all().item())
+    # ---- checker: 12 random instances end to end against the C oracle (adaptor_sigs.py:80-101,191-266)
+    orc = _c_oracle()
+    op = orc.params(128, p['q'], p['l'], p['sk_bd'], p['ch_wt'])
+    key_ch, _ = eng.hash2polyvec('KEY_CH_SEED', [KEY_CH_SEED], p['q'] // 2, D, p['l'])
+    key_ch = np.ascontiguousarray(key_ch[0])
+    pick = np.sort(np.random.default_rng(7 + rank).choice(n, 12, replace=False))
+    d_pick = torch.from_numpy(pick).to(dev)
+    got = {k: st[k][d_pick].cpu().numpy() for k in ('wit', 'st_coef', 'presig', 'sig', 'ext')}
+    q = p['q']
+    centre = lambda x: ((x.astype(np.int64) + q // 2) % q - q // 2).astype(np.int16)
+    matches = 0
+    for j, i in enumerate(pick):
+        seed = bytes(seeds[i * 128:(i + 1) * 128].tolist())
+        skl, skr, vkl, vkr = orc.lm_keygen(op, key_ch, seed)
+        wit, _ = orc.hash2polyvec(128, D, 'WIT_SALT', seed, 1, 20, p['l'])
+        stc = orc.dot(q, key_ch, wit)
+        m = _chmsg_str(ch[i])
+        presig = orc.lm_sign(op, skl, skr, m)
+        sig = centre(presig.astype(np.int64) + wit)
+        good = (np.array_equal(wit, got['wit'][j]) and np.array_equal(stc, got['st_coef'][j]) and
+                np.array_equal(presig, got['presig'][j]) and np.array_equal(sig, got['sig'][j]) and
+                np.array_equal(centre(sig.astype(np.int64) - presig), got['ext'][j]) and
+                orc.lm_verify(op, key_ch, vkl, vkr, m, presig, pvf_bd, 256) and
+                orc.lm_verify(op, key_ch, vkl, vkr, m, sig, vf_bd, 256, st=stc) and
+                not orc.lm_verify(op, key_ch, vkl, vkr, m, presig, vf_bd, 256, st=stc))
+        matches += int(good)
     eng.close()
-    return {'n_per_gpu': n, 'all_verdicts_true': ok,
+    return {'n_per_gpu': n, 'n_total': world * n, 'all_verdicts_true': ok,
+            'oracle_subsample': {'checked': len(pick), 'bit_exact': matches, 'checker': 'oracle/lcb_oracle.c'},
             'ops_per_s': {k: world * n / (v * 1e-3) for k, v in t.items()}, 'ms': t}
 
 
@@ -404,7 +596,7 @@ def engine_arm(a):
 
     cpu = None
     if rank == 0 and a.gpus == 1 and not a.no_cpu_baseline:
-        cpu = cpu_leg(a.secpar, a.cpu_per_core)       # before CUDA is initialised (forks workers)
+        cpu = cpu_leg(a.secpar, a.cpu_per_core, None if a.no_secondary else a)   # before CUDA is initialised (forks workers)
 
     import numpy as np
     import torch
@@ -565,44 +757,56 @@ def engine_arm(a):
                   'h2d_bytes_per_step': np_sig_p.nbytes + np_vk_p.nbytes + np_ch.nbytes + np_off.nbytes,
                   'd2h_bytes_per_step': d2h, 'steps': a.e2e_steps, 'sig_bits': sbits, 'key_bits': kbits,
                   'resident_ms_per_step': packed_resident_ms,
-                  'note': 'lcb_lm_verify_packed_batch on pinned host buffers; opt-in wire format, not the headline e2e'}
+                  'h2d_gbs_per_rank': (np_sig_p.nbytes + np_vk_p.nbytes + np_ch.nbytes + np_off.nbytes) * a.e2e_steps /
+                                      float(e2e_p_s.item()) / 1e9,
+                  'note': 'lcb_lm_verify_packed_batch on pinned host buffers: the documented route for host-resident '
+                          'callers (INTEGRATION.md); the contract e2e above keeps the unpacked int16 format'}
     del h_sig_p, h_vk_p, np_sig_p, np_vk_p
 
     if rank == 0:
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
-                peaks = json.load(f)
-        except OSError:
-            pass
-        peak = peaks.get('hbm_gbs', 6650.0)
+        peaks = _peaks()
+        k_ms = v_ms / max(v_n, 1)
+        # ---- primary roofline: integer instruction issue.  Algorithmic work of ONE verify
+        # inside k_verify at secpar 128 / 256 by the survey's work model: (l + 1) negacyclic NTT-256 of 8,192
+        # int32 instructions (1,024 butterflies x 8), (l + 1) x 256 multiply-accumulates of 6, bounds 2 per coefficient,
+        # comparison 2 per slot.  (The Keccak share of a verify, 6 / 26 permutations, is the sampler kernel's.)
+        ntts = p['l'] + 1
+        unit_instr = ntts * 8192 + ntts * D * 6 + p['l'] * D * 2 + D * 2
+        step_instr = unit_instr + {128: 6, 256: 26}[a.secpar] * 4560 + p['ch_wt'] * 40
+        achieved_t = unit_instr * n / (k_ms * 1e-3) / 1e12
         # algorithmic bytes of one verify inside k_verify: signature + vk + challenge pairs + verdict
         unit_bytes = p['l'] * D * 2 + 2 * D * 2 + p['ch_wt'] * 4 + 1
-        k_ms = v_ms / max(v_n, 1)
-        achieved = unit_bytes * n / (k_ms * 1e-3) / 1e9
+        hbm_achieved = unit_bytes * n / (k_ms * 1e-3) / 1e9
+        ncu = _ncu_summary('verify') if a.secpar == 128 else None
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': total_ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'u32 (mod-q integer arithmetic, q < 2^16)', 'data': 'synthetic',
-            'config': {'workload': workload_name(a), 'secpar': a.secpar, 'q': p['q'], 'd': D, 'l': p['l'],
-                       'triples_per_gpu': n, 'tampered_every': 64,
-                       'l2': f'inputs {(sig.numel() * 2 + vk_ntt.numel() * 2 + d_ch.numel()) / 1e9:.2f} GB per pass '
-                             f'>> 126 MB L2, no flush needed'},
-            'roofline': {'bound': 'hbm', 'kernel': 'k_verify', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak,
-                         # DRAM bytes per launch from the ncu --set full capture of this kernel
-                         # (profiles/prof_r1_verify.summary.txt: 2.0344 GB read + 5.0 MB written for 2^18
-                         # verifies = 7,780 B per verify), scaled to this launch's batch
-                         'traffic': 7780 * n if a.secpar == 128 else None,
-                         'algorithmic_bytes_per_launch': unit_bytes * n,
-                         'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback',
-                         'algorithmic_bytes_per_unit': unit_bytes,
+            'config': engine_config(a),
+            'roofline': {'bound': 'int_issue', 'kernel': 'k_verify', 'achieved': achieved_t, 'peak': peaks['int_tinstr_s'],
+                         'unit': 'Tinstr/s', 'frac': achieved_t / peaks['int_tinstr_s'],
+                         # DRAM bytes per launch of this kernel from its ncu --set full capture, scaled from the
+                         # capture's batch to this launch's (None when no capture of this build's kernel is committed)
+                         'traffic': ncu['dram_bytes_per_unit'] * n if ncu else None,
+                         'algorithmic_instr_per_unit': unit_instr,
+                         'work_model': f'{ntts} NTT-256 x 8192 + {ntts} x 256 x 6 (multiply-accumulate) + '
+                                       f'{p["l"]} x 256 x 2 (bounds) + 512 (compare) int32 instructions per verify '
+                                       f'(SURVEY.md 8d); peak = 148 SMs x 128 lanes x {peaks["sm_max_mhz"]:.0f} MHz',
+                         'peak_source': peaks['source'] + ' sm_max_mhz',
                          'kernel_ms_per_launch': k_ms, 'kernel_share_of_step': v_ms / total_ms,
                          'sampler_ms_per_launch': s_ms / max(s_n, 1),
-                         'note': 'k_verify is integer-issue bound by design (see DESIGN.md); HBM fraction is the '
-                                 'contract figure, int-pipe figures are in int_pipe'},
+                         'whole_step': {'algorithmic_instr_per_unit': step_instr,
+                                        'frac': step_instr * (value / world) / 1e12 / peaks['int_tinstr_s']},
+                         'hbm': {'bound': 'hbm', 'achieved': hbm_achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                                 'frac': hbm_achieved / peaks['hbm_gbs'], 'algorithmic_bytes_per_unit': unit_bytes,
+                                 'algorithmic_bytes_per_launch': unit_bytes * n, 'peak_source': peaks['source'] + ' hbm_gbs',
+                                 'note': 'secondary figure: the kernel needs 7.8 KB per ~140 k instructions, HBM does not bind'},
+                         'ncu': ncu},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'steps': a.e2e_steps, 'host_cpus_bound_per_rank': numa_cpus},
+                    'steps': a.e2e_steps, 'host_cpus_bound_per_rank': numa_cpus,
+                    'h2d_gbs_per_rank': h2d * a.e2e_steps / float(e2e_s.item()) / 1e9,
+                    'note': 'host-resident int16 signatures: bound by the host link (PCIe / host memory), see '
+                            'h2d_gbs_per_rank; e2e_packed moves 28 % fewer bytes for the same verdicts'},
             'e2e_packed': e2e_packed,
             'gpu_launches': launches,
             'clocks': clk,
@@ -611,20 +815,6 @@ def engine_arm(a):
                       'note': 'cold first calls of this process (memory-pool growth and output allocation inside); '
                               'warm rates are in secondary and profiles/README.md'},
         }
-        # instruction-issue view of the same kernel: warp-instructions per verify from the ncu count of this
-        # build (profiles/prof_r1_verify.summary.txt: 1,004.7 M for 2^18 verifies), against the issue limit of
-        # 4 schedulers x 148 SMs x 1 warp-instruction per clock at the max clock
-        instr_per_unit = 32 * 3833 if a.secpar == 128 else None
-        clk_hz = ((clk or {}).get('sm_max_mhz') or 1965.0) * 1e6
-        if instr_per_unit:
-            achieved_t = instr_per_unit * n / (k_ms * 1e-3) / 1e12
-            issue_peak = 148 * 128 * clk_hz / 1e12
-            line['roofline']['int_pipe'] = {
-                'thread_instr_per_unit': instr_per_unit, 'achieved_tinstr_s': achieved_t,
-                'issue_peak_tinstr_s': issue_peak, 'issue_frac': achieved_t / issue_peak,
-                'ncu_pipe_utilisation': {'issue_active': 0.751, 'alu': 0.523, 'fma': 0.355, 'lsu': 0.342},
-                'note': 'k_verify is bound by instruction issue: 5-instruction FP32-assisted butterflies spread '
-                        'over the ALU, FMA-heavy and FMA-lite pipes (DESIGN.md 3.3)'}
         if cpu is not None:
             line['cpu_baseline'] = cpu
     del sig, sig_v, vk_ntt, d_ch, h_sig, h_vk, h_ch, np_sig, np_vk, np_ch
@@ -647,7 +837,21 @@ def engine_arm(a):
                             'config': {'workload': f"bklm aggregate-verify, N = {bk['sigs_per_aggregate']} signatures per "
                                                    f"aggregate sharded over {world} GPU(s), secpar 128, exact reference "
                                                    f"semantics incl. the O(N^2) aggregation-coefficient hashing"},
-                            'aggregate_sigs_per_s': bk.get('aggregate_sigs_per_s')}
+                            'aggregate_sigs_per_s': bk.get('aggregate_sigs_per_s'),
+                            'agg_coefs_gperm_s_per_gpu': bk.get('agg_coefs_gperm_s_per_gpu'),
+                            'roofline': {'bound': 'alu_pipe (Keccak LOP3/SHF)', 'kernel': 'k_agg_coefs / k_agg_coefs_il',
+                                         'achieved': bk.get('agg_coefs_gperm_s_per_gpu'), 'peak': 4.28, 'unit': 'Gperm/s',
+                                         'frac': (bk.get('agg_coefs_gperm_s_per_gpu') or 0) / 4.28,
+                                         'peak_source': 'tools/keccak_bench2.cu (measured, 100 % ALU pipe)'},
+                            'row_ii_coefficients_supplied': bk.get('row_ii_coefficients_supplied')}
+            if cpu is not None and 'bklm' in cpu:
+                cb = cpu['bklm']
+                line['also']['cpu_baseline'] = {
+                    'value': cb['aggregate_verify']['sigs_per_s'], 'unit': 'signatures/s', 'cores': cb['cores'], 'kind': 'port',
+                    'aggregate_sigs_per_s': cb['aggregate']['sigs_per_s'],
+                    'sample': f"aggregate + aggregate-verify timed at N in {[q_['n'] for q_ in cb['points']]} on {cb['cores']} cores, "
+                              f"t(N) = a N^2 + b N extrapolated to N = {cb['target_n']} (BASELINE.md section 3): b fitted, "
+                              f"a = 124 B / (hashlib SHAKE256 rate measured on a {124 * cb['target_n']}-byte message on all cores)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

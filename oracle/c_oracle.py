@@ -63,6 +63,13 @@ def poly_mul(q, a, b):
     return out
 
 
+def dot(q, row, vec):
+    """sum_i row[i] * vec[i] (PolynomialVector.__mul__), int16[l][d] x int16[l][d] -> int16[d]"""
+    out = np.empty(row.shape[-1], dtype=np.int16)
+    lib().orc_dot(q, row.shape[-1], row.shape[0], _p(np.ascontiguousarray(row)), _p(np.ascontiguousarray(vec)), _p(out))
+    return out
+
+
 def lm_keygen(p: OrcParams, key_ch, seed: bytes):
     skl = np.empty((p.l, p.d), dtype=np.int16)
     skr = np.empty((p.l, p.d), dtype=np.int16)

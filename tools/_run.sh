@@ -1,6 +1,4 @@
 set -x
-python -m pytest tests/test_gpu_parity.py -q -x -k "agg_coefs" 2>&1 | tail -5
-LCB_AGG_EARLY=1 python -m pytest tests/test_gpu_parity.py -q -x -k "agg_coefs" 2>&1 | tail -5
-timeout 600 python tools/agg_coefs_timing.py 16 8192 57344 2>&1 | grep -v subsample
-timeout 900 python tools/agg_coefs_timing.py 16 65536 0 2>&1 | grep -v subsample
-timeout 900 python -m pytest tests/test_gpu_bklm_full.py -q -x 2>&1 | tail -15
+python -m pytest tests -q -x -m gpu 2>&1 | tail -8
+python bench.py --steps 3 --warmup 3 --log2n 16 --bklm-log2n 12 --keygen-log2n 14 --adaptor-log2n 12 --cpu-per-core 2 --cpu-bklm-log2n 4 > gpurun_out/bench_small.json 2> gpurun_out/bench_small.err; echo rc=$?; tail -5 gpurun_out/bench_small.err
+python bench.py > gpurun_out/bench_r2_a.json 2> gpurun_out/bench_r2_a.err; echo rc=$?; tail -5 gpurun_out/bench_r2_a.err

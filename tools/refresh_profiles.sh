@@ -3,7 +3,7 @@
 # launch list and one --set full capture per kernel, all into gpurun_out/ (digests are made afterwards
 # with profiles/ncu_summary.py and copied into profiles/).
 set -u
-R=${ROUND:-r1}
+R=${ROUND:-r2}
 O=gpurun_out
 mkdir -p $O
 python -m pytest tests -m gpu -x -q 2>&1 | tail -1 | tee $O/pytest_gpu_${R}.txt
