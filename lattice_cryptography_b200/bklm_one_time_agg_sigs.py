@@ -9,7 +9,9 @@ Sharded: aggregate_shard / aggregate_finish, aggregate_verify_shard / aggregate_
 
 Sorting by str(otvk) and building the hash-input strings stay on the host: they depend on CPython
 object identity.  The shipped parameters have ag_wt = ag_bd = 1, i.e. every
-aggregation coefficient is a signed monomial; that is the only case the engine supports.
+aggregation coefficient is a signed monomial (a signed rotation of the signature: the HBM-bound fast kernels);
+other values of the module tables BDs / WTs (the reference leaves them editable, :15-19) take the general
+NTT-domain product kernels.
 """
 from typing import Dict, List, Tuple
 
@@ -71,7 +73,8 @@ def prepare_hash2polyinput(pp: PublicParameters, otvks: List[OneTimeVerification
 
 
 def _monomials(lp, pairs: np.ndarray) -> List[AggCoef]:
-    return [Polynomial(lp, {int(k): int(s)}, const_time_flag=False) for k, s in pairs[:, 0, :]]
+    """(index, value) pairs int16[n][ag_wt][2] -> the n aggregation coefficients as Polynomials."""
+    return [Polynomial(lp, {int(k): int(v) for k, v in row}, const_time_flag=False) for row in pairs]
 
 
 def make_agg_coefs(pp: PublicParameters, otvks: List[OneTimeVerificationKey], msgs: List[Message]) -> List[AggCoef]:

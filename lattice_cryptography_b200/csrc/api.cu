@@ -20,6 +20,10 @@ struct lcb_ctx {
     cudaStream_t copy_stream = nullptr;  // H2D of large host inputs, chunk by chunk, under the kernels (lazy)
     int secpar = 0, q = 0, d = 0, l = 0, rou = 0;
     RingCtx ring{};
+    bool generic = false;                // d != 256 or q >= 2^16: ring_generic.cu / k_sampler_g instead of the fast kernels
+    bool wide = false;                   // q >= 2^16: int32 / uint32 element formats
+    GenCtx gen{};
+    uint32_t* d_gen_tab = nullptr;       // generic twiddle tables: w, ws, iw, iws [d] each, pw [2d]
     NttTables* d_tab = nullptr;
     uint32_t* d_a_hat = nullptr;
     bool has_key_ch = false;
@@ -85,7 +89,7 @@ cudaError_t timed(lcb_ctx* c, int id, F&& launch) {
 
 // Point a sampler launch at the ctx's index scratch, growing it when the batch needs more.
 cudaError_t sampler_scratch(lcb_ctx* c, SamplerArgs& a) {
-    const size_t need = sampler_scratch_bytes(a.n, a.wt);
+    const size_t need = sampler_scratch_bytes(a.n, a.wt, true);   // sized for 16-bit indices: either kernel may run
     if (need > c->idx_scratch_bytes) {
         cudaError_t e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) return e;
@@ -125,6 +129,15 @@ uint32_t bitrev8(uint32_t v) {
 }
 
 uint32_t shoup(uint32_t w, uint32_t q) { return (uint32_t)(((uint64_t)w << 32) / q); }
+
+uint32_t bitrev(uint32_t v, int bits) {
+    uint32_t r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((v >> i) & 1u) << (bits - 1 - i);
+    return r;
+}
+
+// element counts below are in 16-bit units of the narrow formats; a wide context (q >= 2^16) moves 32-bit elements
+inline size_t ew(const lcb_ctx* c) { return c->wide ? 2 : 1; }
 
 int ceil_log2(int v) {
     int c = 0;
@@ -268,7 +281,7 @@ cudaError_t last_offset(lcb_ctx* c, const void* blob, const int64_t* off, int64_
 }
 
 int fill_sampler(lcb_ctx* c, SamplerArgs& a, const char* salt, const char* suffix, int bd, int wt, int vec_len) {
-    if (bd < 1 || bd > 32767 || wt < 1 || wt > D || vec_len < 1) return LCB_ERR_INVALID;
+    if (bd < 1 || (!c->wide && bd > 32767) || wt < 1 || wt > c->d || vec_len < 1) return LCB_ERR_INVALID;
     std::string s = std::string(salt ? salt : "") + (suffix ? suffix : "");
     if ((int)s.size() > SALT_BYTES) return LCB_ERR_INVALID;
     std::memset(a.salt, 0, sizeof(a.salt));
@@ -278,10 +291,16 @@ int fill_sampler(lcb_ctx* c, SamplerArgs& a, const char* salt, const char* suffi
     a.bd = bd;
     a.wt = wt;
     a.vec_len = vec_len;
-    a.idx_bits = LOGD + c->secpar;
+    const int logd = ceil_log2(c->d);
+    a.d = c->d;
+    a.logd = logd;
+    a.wide = c->wide ? 1 : 0;
+    a.stream_salts = nullptr;
+    a.stream_salt_len = nullptr;
+    a.idx_bits = logd + c->secpar;
     const int btd = ceil_log2(bd) + 1 + c->secpar;
     a.mag_bits = btd - 1;
-    const int64_t bits = (int64_t)LOGD + (int64_t)(wt - 1) * a.idx_bits + (int64_t)wt * btd;
+    const int64_t bits = (int64_t)logd + (int64_t)(wt - 1) * a.idx_bits + (int64_t)wt * btd;
     a.pad_bits = (int)(8 * ((bits + 7) / 8) - bits);
     a.paired = 0;
     a.salt2_len = 0;
@@ -315,8 +334,6 @@ int run_challenge(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* d_msg, const
 
 int run_agg_coefs(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* d_agmsg, int64_t agmsg_len, int64_t first,
                   int64_t count, int16_t* d_pairs) {
-    if (sch->ag_wt != 1 || sch->ag_bd != 1)
-        return fail(c, LCB_ERR_INVALID, "only ag_wt == ag_bd == 1 (signed monomial aggregation coefficients) is supported");
     SamplerArgs a{};
     int st = fill_sampler(c, a, salt_of(sch->ag_salt).c_str(), nullptr, sch->ag_bd, sch->ag_wt, 1);
     if (st != LCB_OK) return fail(c, st, "bad aggregation parameters");
@@ -328,6 +345,25 @@ int run_agg_coefs(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* d_agmsg, int
     a.shared_len = agmsg_len;
     a.index_first = first;
     a.out_pairs = d_pairs;
+    if (c->generic || sch->ag_wt != 1 || sch->ag_bd != 1) {
+        // General aggregation coefficients (ag_wt > 1 or ag_bd > 1: bklm_one_time_agg_sigs.py:15-19 leaves both as
+        // editable tables) and generic degrees: the full sampler over the shared message, one salt
+        // ag_salt || str(index) per stream.
+        uint8_t* salts = nullptr;
+        int32_t* lens = nullptr;
+        CK(c, cudaMallocAsync((void**)&salts, (size_t)count * SALT_BYTES, c->stream));
+        CK(c, cudaMallocAsync((void**)&lens, (size_t)count * sizeof(int32_t), c->stream));
+        cudaError_t e = launch_index_salts(a, salts, lens, c->stream);
+        a.stream_salts = salts;
+        a.stream_salt_len = lens;
+        if (e == cudaSuccess) e = sampler_scratch(c, a);
+        if (e == cudaSuccess) e = timed(c, K_AGG_COEFS, [&] { return launch_sampler(a, c->stream); });
+        cudaFreeAsync(salts, c->stream);
+        cudaFreeAsync(lens, c->stream);
+        c->launches += 1;
+        if (e != cudaSuccess) return fail_cuda(c, e, "general aggregation coefficients");
+        return LCB_OK;
+    }
     if (agg_coefs_two_lane(count, c->ring.num_sms)) {
         // few long streams: two lanes per sponge over the pre-split message (sampler.cu, k_agg_coefs_il)
         const size_t need = agg_il_bytes(agmsg_len);
@@ -371,9 +407,11 @@ int lcb_ctx_create(lcb_ctx** out, int device, int secpar, int q, int d, int l) {
     if (!out) return LCB_ERR_INVALID;
     *out = nullptr;
     g_create_error.clear();
-    if (d != D || l < 1 || l > 64 || secpar < 1 || secpar > 512 ||   /* fields of 8+secpar / 16+secpar bits must fit the sampler window */ q < 3 || q >= 65536 || !is_prime(q) ||
+    // fields of logd + secpar / 32 + secpar bits must fit the sampler window (MAX_FIELD_BITS)
+    if (d < 32 || d > 1024 || (d & (d - 1)) != 0 || l < 1 || l > 64 || secpar < 1 || secpar > 512 || q < 3 || !is_prime(q) ||
         q % (2 * d) != 1) {
-        g_create_error = "supported: d == 256, prime q < 65536 with q % 512 == 1, 1 <= l <= 64, 1 <= secpar <= 512";
+        g_create_error = "supported: power-of-two 32 <= d <= 1024, prime q < 2^31 with q % (2 d) == 1, 1 <= l <= 64, "
+                         "1 <= secpar <= 512";
         return LCB_ERR_INVALID;
     }
     int ndev = 0;
@@ -395,6 +433,8 @@ int lcb_ctx_create(lcb_ctx** out, int device, int secpar, int q, int d, int l) {
     c->q = q;
     c->d = d;
     c->l = l;
+    c->wide = q >= 65536;
+    c->generic = d != D || c->wide;
     auto bail = [&](cudaError_t e, const char* what) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
         lcb_ctx_destroy(c);
@@ -417,6 +457,50 @@ int lcb_ctx_create(lcb_ctx** out, int device, int secpar, int q, int d, int l) {
     uint32_t psi = 2;
     while (!(powmod(psi, 2 * d, uq) == 1 && powmod(psi, d, uq) != 1)) ++psi;
     c->rou = (int)psi;
+    {
+        // Tables of the generic kernels (ring_generic.cu): zetas in bit-reversed order, their inverses, Shoup
+        // companions, psi^e.  Built for EVERY context: the shipped geometry uses them for the operations that have no
+        // fast kernel (aggregation with non-monomial coefficients).
+        int logd = 0;
+        while ((1 << logd) < d) ++logd;
+        std::vector<uint32_t> tab((size_t)6 * d);
+        uint32_t *w = tab.data(), *ws = w + d, *iw = ws + d, *iws = iw + d, *pw = iws + d;
+        for (uint32_t k = 0; k < (uint32_t)d; ++k) {
+            w[k] = (uint32_t)powmod(psi, bitrev(k, logd), uq);
+            iw[k] = (uint32_t)powmod(w[k], uq - 2, uq);
+            ws[k] = shoup(w[k], uq);
+            iws[k] = shoup(iw[k], uq);
+        }
+        for (uint32_t e2 = 0; e2 < 2 * (uint32_t)d; ++e2) pw[e2] = (uint32_t)powmod(psi, e2, uq);
+        if ((e = cudaMalloc(&c->d_gen_tab, tab.size() * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc tables");
+        if ((e = cudaMemcpy(c->d_gen_tab, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess)
+            return bail(e, "cudaMemcpy tables");
+        if (c->generic && (e = cudaMalloc(&c->d_a_hat, (size_t)l * d * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc key_ch");
+        GenRing& r = c->gen.r;
+        r.q = uq;
+        r.half = (uq - 1) / 2;
+        r.d = d;
+        r.logd = logd;
+        r.mu64 = (uint64_t)((((unsigned __int128)1) << 64) / uq);
+        r.pos_off = (((1ull << 31) + uq - 1) / uq) * uq;
+        r.dinv = (uint32_t)powmod((uint32_t)d, uq - 2, uq);
+        r.dinv_s = shoup(r.dinv, uq);
+        r.w = c->d_gen_tab;
+        r.ws = r.w + d;
+        r.iw = r.ws + d;
+        r.iws = r.iw + d;
+        r.pw = r.iws + d;
+        c->gen.a_hat = c->d_a_hat;
+        c->gen.l = l;
+        c->gen.num_sms = prop.multiProcessorCount;
+        c->gen.wide = c->wide;
+        c->ring.l = l;
+        c->ring.num_sms = prop.multiProcessorCount;
+    }
+    if (c->generic) {
+        *out = c;
+        return LCB_OK;
+    }
     std::vector<NttTables> host(1);
     NttTables& t = host[0];
     for (uint32_t k = 0; k < 256; ++k) {
@@ -469,6 +553,7 @@ int lcb_ctx_create(lcb_ctx** out, int device, int secpar, int q, int d, int l) {
     if ((e = cudaMalloc(&c->d_a_hat, (size_t)l * D * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc key_ch");
     c->ring.tab = c->d_tab;
     c->ring.a_hat = c->d_a_hat;
+    c->gen.a_hat = c->d_a_hat;
     c->ring.l = l;
     c->ring.num_sms = prop.multiProcessorCount;
     *out = c;
@@ -480,6 +565,7 @@ int lcb_ctx_destroy(lcb_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->d_tab) cudaFree(c->d_tab);
+    if (c->d_gen_tab) cudaFree(c->d_gen_tab);
     if (c->d_a_hat) cudaFree(c->d_a_hat);
     if (c->idx_scratch) cudaFree(c->idx_scratch);
     if (c->il_scratch) cudaFree(c->il_scratch);
@@ -563,18 +649,25 @@ int lcb_set_key_ch(lcb_ctx* c, const int16_t* key_ch_coef) {
     if (!c || !key_ch_coef) return LCB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     Staging sg(c);
+    const size_t cnt = (size_t)c->l * c->d;
     const int16_t* d_in;
-    CK(c, sg.in(&d_in, key_ch_coef, (size_t)c->l * D));
+    CK(c, sg.in(&d_in, key_ch_coef, cnt * ew(c)));
     uint16_t* d_ntt;
-    CK(c, sg.alloc((void**)&d_ntt, (size_t)c->l * D * sizeof(uint16_t)));
-    CK(c, timed(c, K_NTT_FWD, [&] { return launch_ntt_fwd(c->ring, d_in, c->l, d_ntt, c->stream); }));
-    // widen to uint32 on the host side of the stream (tiny: l*256 values, once per parameter set)
-    std::vector<uint16_t> h16((size_t)c->l * D);
-    CK(c, cudaMemcpyAsync(h16.data(), d_ntt, h16.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaStreamSynchronize(c->stream));
-    std::vector<uint32_t> h32(h16.begin(), h16.end());
-    CK(c, cudaMemcpyAsync(c->d_a_hat, h32.data(), h32.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, sg.alloc((void**)&d_ntt, cnt * ew(c) * sizeof(uint16_t)));
+    if (c->generic) CK(c, timed(c, K_NTT_FWD, [&] { return g_launch_ntt_fwd(c->gen, d_in, c->l, d_ntt, c->stream); }));
+    else CK(c, timed(c, K_NTT_FWD, [&] { return launch_ntt_fwd(c->ring, d_in, c->l, d_ntt, c->stream); }));
+    if (c->wide) {
+        CK(c, cudaMemcpyAsync(c->d_a_hat, d_ntt, cnt * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+    } else {
+        // widen to uint32 on the host side of the stream (tiny: l*d values, once per parameter set)
+        std::vector<uint16_t> h16(cnt);
+        CK(c, cudaMemcpyAsync(h16.data(), d_ntt, h16.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        std::vector<uint32_t> h32(h16.begin(), h16.end());
+        CK(c, cudaMemcpyAsync(c->d_a_hat, h32.data(), h32.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+    }
     c->has_key_ch = true;
     CK(c, sg.finish());
     return LCB_OK;
@@ -612,11 +705,12 @@ int lcb_hash2polyvec_batch(lcb_ctx* c, const char* salt, const uint8_t* msgs, co
     Staging sg(c);
     CK(c, sg.in(&a.msgs, msgs, (size_t)total));
     CK(c, sg.in(&a.off, msg_off, (size_t)n + 1));
-    CK(c, sg.out(&a.out_dense, out_dense, (size_t)n * vec_len * D));
-    CK(c, sg.out(&a.out_pairs, out_pairs, (size_t)n * vec_len * wt * 2));
+    CK(c, sg.out(&a.out_dense, out_dense, (size_t)n * vec_len * c->d * ew(c)));
+    CK(c, sg.out(&a.out_pairs, out_pairs, (size_t)n * vec_len * wt * 2 * ew(c)));
     a.n = n;
-    a.dense_stride = (int64_t)vec_len * D;
-    if (a.out_dense && wt < D) CK(c, cudaMemsetAsync(a.out_dense, 0, (size_t)n * vec_len * D * sizeof(int16_t), c->stream));
+    a.dense_stride = (int64_t)vec_len * c->d;
+    if (a.out_dense && wt < c->d)
+        CK(c, cudaMemsetAsync(a.out_dense, 0, (size_t)n * vec_len * c->d * ew(c) * sizeof(int16_t), c->stream));
     CK(c, sampler_scratch(c, a));
     CK(c, timed(c, K_SAMPLER, [&] { return launch_sampler(a, c->stream); }));
     CK(c, sg.finish());
@@ -629,9 +723,11 @@ int lcb_ntt_fwd_batch(lcb_ctx* c, const int16_t* coef, int64_t npoly, uint16_t* 
     Staging sg(c);
     const int16_t* d_in;
     uint16_t* d_out;
-    CK(c, sg.in(&d_in, coef, (size_t)npoly * D));
-    CK(c, sg.out(&d_out, ntt, (size_t)npoly * D));
-    CK(c, timed(c, K_NTT_FWD, [&] { return launch_ntt_fwd(c->ring, d_in, npoly, d_out, c->stream); }));
+    CK(c, sg.in(&d_in, coef, (size_t)npoly * c->d * ew(c)));
+    CK(c, sg.out(&d_out, ntt, (size_t)npoly * c->d * ew(c)));
+    CK(c, timed(c, K_NTT_FWD, [&] {
+        return c->generic ? g_launch_ntt_fwd(c->gen, d_in, npoly, d_out, c->stream) : launch_ntt_fwd(c->ring, d_in, npoly, d_out, c->stream);
+    }));
     CK(c, sg.finish());
     return LCB_OK;
 }
@@ -642,9 +738,11 @@ int lcb_ntt_reference_repr_batch(lcb_ctx* c, const int16_t* coef, int64_t npoly,
     Staging sg(c);
     const int16_t* d_in;
     int16_t* d_out;
-    CK(c, sg.in(&d_in, coef, (size_t)npoly * D));
-    CK(c, sg.out(&d_out, rep, (size_t)npoly * 2 * D));
-    CK(c, timed(c, K_NTT_FWD, [&] { return launch_ntt_ref_repr(c->ring, d_in, npoly, d_out, c->stream); }));
+    CK(c, sg.in(&d_in, coef, (size_t)npoly * c->d * ew(c)));
+    CK(c, sg.out(&d_out, rep, (size_t)npoly * 2 * c->d * ew(c)));
+    CK(c, timed(c, K_NTT_FWD, [&] {
+        return c->generic ? g_launch_ref_repr(c->gen, d_in, npoly, d_out, c->stream) : launch_ntt_ref_repr(c->ring, d_in, npoly, d_out, c->stream);
+    }));
     CK(c, sg.finish());
     return LCB_OK;
 }
@@ -655,9 +753,11 @@ int lcb_ntt_inv_batch(lcb_ctx* c, const uint16_t* ntt, int64_t npoly, int16_t* c
     Staging sg(c);
     const uint16_t* d_in;
     int16_t* d_out;
-    CK(c, sg.in(&d_in, ntt, (size_t)npoly * D));
-    CK(c, sg.out(&d_out, coef, (size_t)npoly * D));
-    CK(c, timed(c, K_NTT_INV, [&] { return launch_ntt_inv(c->ring, d_in, npoly, d_out, c->stream); }));
+    CK(c, sg.in(&d_in, ntt, (size_t)npoly * c->d * ew(c)));
+    CK(c, sg.out(&d_out, coef, (size_t)npoly * c->d * ew(c)));
+    CK(c, timed(c, K_NTT_INV, [&] {
+        return c->generic ? g_launch_ntt_inv(c->gen, d_in, npoly, d_out, c->stream) : launch_ntt_inv(c->ring, d_in, npoly, d_out, c->stream);
+    }));
     CK(c, sg.finish());
     return LCB_OK;
 }
@@ -668,10 +768,12 @@ int lcb_poly_mul_batch(lcb_ctx* c, const int16_t* a, const int16_t* b, int64_t n
     Staging sg(c);
     const int16_t *d_a, *d_b;
     int16_t* d_out;
-    CK(c, sg.in(&d_a, a, (size_t)npoly * D));
-    CK(c, sg.in(&d_b, b, (size_t)npoly * D));
-    CK(c, sg.out(&d_out, out, (size_t)npoly * D));
-    CK(c, timed(c, K_POLY_MUL, [&] { return launch_poly_mul(c->ring, d_a, d_b, npoly, d_out, c->stream); }));
+    CK(c, sg.in(&d_a, a, (size_t)npoly * c->d * ew(c)));
+    CK(c, sg.in(&d_b, b, (size_t)npoly * c->d * ew(c)));
+    CK(c, sg.out(&d_out, out, (size_t)npoly * c->d * ew(c)));
+    CK(c, timed(c, K_POLY_MUL, [&] {
+        return c->generic ? g_launch_poly_mul(c->gen, d_a, d_b, npoly, d_out, c->stream) : launch_poly_mul(c->ring, d_a, d_b, npoly, d_out, c->stream);
+    }));
     CK(c, sg.finish());
     return LCB_OK;
 }
@@ -696,10 +798,11 @@ int lcb_lm_keygen_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* seeds,
     uint16_t *d_sk_ntt, *d_vk_ntt;
     CK(c, sg.in(&d_seeds, seeds, (size_t)total));
     CK(c, sg.in(&d_off, seed_off, (size_t)n + 1));
-    CK(c, sg.out(&d_sk_coef, sk_coef, (size_t)n * 2 * l * D, true));
-    CK(c, sg.out(&d_sk_ntt, sk_ntt, (size_t)n * 2 * l * D, true));
-    CK(c, sg.out(&d_vk_ntt, vk_ntt, (size_t)n * 2 * D));
-    CK(c, sg.out(&d_vk_coef, vk_coef, (size_t)n * 2 * D));
+    const size_t D_ = (size_t)c->d * ew(c);       // 16-bit units per polynomial (twice the degree in a wide context)
+    CK(c, sg.out(&d_sk_coef, sk_coef, (size_t)n * 2 * l * D_, true));
+    CK(c, sg.out(&d_sk_ntt, sk_ntt, (size_t)n * 2 * l * D_, true));
+    CK(c, sg.out(&d_vk_ntt, vk_ntt, (size_t)n * 2 * D_));
+    CK(c, sg.out(&d_vk_coef, vk_coef, (size_t)n * 2 * D_));
     // Signing keys pass through HBM in coefficient form between the sampler and the row-vector
     // product; when the caller does not want them, a bounded scratch chunk is reused.
     // Both halves of a key come from ONE paired sampler launch (stream 2i = left, 2i+1 = right: twice the
@@ -717,22 +820,24 @@ int lcb_lm_keygen_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* seeds,
         if (v > 0 && !d_sk_coef) chunk = v < n ? v : n;
     }
     int16_t* scratch = nullptr;
-    if (!d_sk_coef) CK(c, sg.alloc((void**)&scratch, (size_t)chunk * 2 * l * D * sizeof(int16_t), true));
+    if (!d_sk_coef) CK(c, sg.alloc((void**)&scratch, (size_t)chunk * 2 * l * D_ * sizeof(int16_t), true));
     for (int64_t start = 0; start < n; start += chunk) {
         const int64_t cnt = (n - start < chunk) ? n - start : chunk;
-        int16_t* skc = d_sk_coef ? d_sk_coef + start * 2 * l * D : scratch;
-        if (sch->sk_wt < D) CK(c, cudaMemsetAsync(skc, 0, (size_t)cnt * 2 * l * D * sizeof(int16_t), c->stream));
+        int16_t* skc = d_sk_coef ? d_sk_coef + start * 2 * l * D_ : scratch;
+        if (sch->sk_wt < c->d) CK(c, cudaMemsetAsync(skc, 0, (size_t)cnt * 2 * l * D_ * sizeof(int16_t), c->stream));
         left.msgs = d_seeds;
         left.off = d_off + start;
         left.n = 2 * cnt;
-        left.dense_stride = (int64_t)l * D;
+        left.dense_stride = (int64_t)l * c->d;
         left.out_dense = skc;
         CK(c, sampler_scratch(c, left));
         CK(c, timed(c, K_SAMPLER, [&] { return launch_sampler(left, c->stream); }));
+        uint16_t* o_sk = d_sk_ntt ? d_sk_ntt + start * 2 * l * D_ : nullptr;
+        uint16_t* o_vk = d_vk_ntt ? d_vk_ntt + start * 2 * D_ : nullptr;
+        int16_t* o_vkc = d_vk_coef ? d_vk_coef + start * 2 * D_ : nullptr;
         CK(c, timed(c, K_MATVEC, [&] {
-            return launch_matvec(c->ring, skc, cnt * 2, d_sk_ntt ? d_sk_ntt + start * 2 * l * D : nullptr,
-                                 d_vk_ntt ? d_vk_ntt + start * 2 * D : nullptr,
-                                 d_vk_coef ? d_vk_coef + start * 2 * D : nullptr, c->stream);
+            return c->generic ? g_launch_matvec(c->gen, skc, cnt * 2, o_sk, o_vk, o_vkc, c->stream)
+                              : launch_matvec(c->ring, skc, cnt * 2, o_sk, o_vk, o_vkc, c->stream);
         }));
     }
     CK(c, sg.finish());
@@ -752,7 +857,7 @@ int lcb_challenge_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* chmsg,
     int16_t* d_pairs;
     CK(c, sg.in(&d_msg, chmsg, (size_t)total));
     CK(c, sg.in(&d_off, chmsg_off, (size_t)n + 1));
-    CK(c, sg.out(&d_pairs, out_pairs, (size_t)n * sch->ch_wt * 2));
+    CK(c, sg.out(&d_pairs, out_pairs, (size_t)n * sch->ch_wt * 2 * ew(c)));
     int st = run_challenge(c, sch, d_msg, d_off, n, d_pairs);
     if (st != LCB_OK) return st;
     CK(c, sg.finish());
@@ -772,14 +877,18 @@ int lcb_lm_sign_batch(lcb_ctx* c, const lcb_scheme* sch, const uint16_t* sk_ntt,
     const uint8_t* d_msg;
     const int64_t* d_off;
     int16_t *d_sig, *d_pairs;
-    CK(c, sg.in(&d_sk, sk_ntt, (size_t)n * 2 * l * D, true));
+    const size_t D_ = (size_t)c->d * ew(c);
+    CK(c, sg.in(&d_sk, sk_ntt, (size_t)n * 2 * l * D_, true));
     CK(c, sg.in(&d_msg, chmsg, (size_t)total));
     CK(c, sg.in(&d_off, chmsg_off, (size_t)n + 1));
-    CK(c, sg.out(&d_sig, sig, (size_t)n * l * D));
-    CK(c, sg.alloc((void**)&d_pairs, (size_t)n * sch->ch_wt * 2 * sizeof(int16_t)));
+    CK(c, sg.out(&d_sig, sig, (size_t)n * l * D_));
+    CK(c, sg.alloc((void**)&d_pairs, (size_t)n * sch->ch_wt * 2 * ew(c) * sizeof(int16_t)));
     int st = run_challenge(c, sch, d_msg, d_off, n, d_pairs);
     if (st != LCB_OK) return st;
-    CK(c, timed(c, K_SIGN, [&] { return launch_sign(c->ring, d_sk, d_pairs, sch->ch_wt, n, d_sig, c->stream); }));
+    CK(c, timed(c, K_SIGN, [&] {
+        return c->generic ? g_launch_sign(c->gen, d_sk, d_pairs, sch->ch_wt, n, d_sig, c->stream)
+                          : launch_sign(c->ring, d_sk, d_pairs, sch->ch_wt, n, d_sig, c->stream);
+    }));
     CK(c, sg.finish());
     return LCB_OK;
 }
@@ -801,14 +910,15 @@ int lcb_lm_verify_batch(lcb_ctx* c, const lcb_scheme* sch, const uint16_t* vk_nt
     const int16_t* d_sig;
     int16_t* d_pairs;
     uint8_t* d_verdict;
-    CK(c, sg.in(&d_vk, vk_ntt, (size_t)n * 2 * D));
+    const size_t D_ = (size_t)c->d * ew(c);
+    CK(c, sg.in(&d_vk, vk_ntt, (size_t)n * 2 * D_));
     CK(c, sg.in(&d_msg, chmsg, (size_t)total));
     CK(c, sg.in(&d_off, chmsg_off, (size_t)n + 1));
     bool piped = false;
-    CK(c, sg.in_piped(&d_sig, sig, (size_t)n * l * D, &piped));
-    CK(c, sg.in(&d_st, st_ntt, (size_t)n * D));
+    CK(c, sg.in_piped(&d_sig, sig, (size_t)n * l * D_, &piped));
+    CK(c, sg.in(&d_st, st_ntt, (size_t)n * D_));
     CK(c, sg.out(&d_verdict, verdict, (size_t)n));
-    CK(c, sg.alloc((void**)&d_pairs, (size_t)n * sch->ch_wt * 2 * sizeof(int16_t)));
+    CK(c, sg.alloc((void**)&d_pairs, (size_t)n * sch->ch_wt * 2 * ew(c) * sizeof(int16_t)));
     const int vbd = bd > 32767 ? 32767 : bd;
     // Signatures in HOST memory (the bulk of the bytes) cross PCIe in chunks on the copy stream while the
     // sampler and verify kernels of the previous chunk run; everything else is one launch over the batch.
@@ -819,20 +929,23 @@ int lcb_lm_verify_batch(lcb_ctx* c, const lcb_scheme* sch, const uint16_t* vk_nt
         for (int64_t first = 0; first < n; first += chunk) {
             const int64_t m = n - first < chunk ? n - first : chunk;
             cudaEvent_t ev;
-            CK(c, sg.pipe_chunk(d_sig + (size_t)first * l * D, sig + (size_t)first * l * D,
-                                (size_t)m * l * D * sizeof(int16_t), &ev));
+            CK(c, sg.pipe_chunk(d_sig + (size_t)first * l * D_, sig + (size_t)first * l * D_,
+                                (size_t)m * l * D_ * sizeof(int16_t), &ev));
             arrived.push_back(ev);
         }
     }
     for (int64_t first = 0, k = 0; first < n; first += chunk, ++k) {
         const int64_t m = n - first < chunk ? n - first : chunk;
-        int16_t* pairs = d_pairs + (size_t)first * sch->ch_wt * 2;
+        int16_t* pairs = d_pairs + (size_t)first * sch->ch_wt * 2 * ew(c);
         int st = run_challenge(c, sch, d_msg, d_off + first, m, pairs);
         if (st != LCB_OK) return st;
         if (piped) CK(c, cudaStreamWaitEvent(c->stream, arrived[k], 0));
         CK(c, timed(c, K_VERIFY, [&] {
-            return launch_verify(c->ring, d_sig + (size_t)first * l * D, d_vk + (size_t)first * 2 * D, pairs, sch->ch_wt,
-                                 nullptr, d_st ? d_st + (size_t)first * D : nullptr, m, vbd, wt, d_verdict + first,
+            if (c->generic)
+                return g_launch_verify(c->gen, d_sig + (size_t)first * l * D_, d_vk + (size_t)first * 2 * D_, pairs, sch->ch_wt,
+                                       nullptr, d_st ? d_st + (size_t)first * D_ : nullptr, m, bd, wt, d_verdict + first, c->stream);
+            return launch_verify(c->ring, d_sig + (size_t)first * l * D_, d_vk + (size_t)first * 2 * D_, pairs, sch->ch_wt,
+                                 nullptr, d_st ? d_st + (size_t)first * D_ : nullptr, m, vbd, wt, d_verdict + first,
                                  c->stream);
         }));
     }
@@ -844,6 +957,7 @@ int lcb_lm_verify_batch(lcb_ctx* c, const lcb_scheme* sch, const uint16_t* vk_nt
 int lcb_pack_batch(lcb_ctx* c, const void* values, int64_t npoly, int bits, int bias, uint8_t* packed,
                    uint8_t* in_range) {
     if (!c || !values || !packed || npoly < 0 || bits < 1 || bits > 16 || bias < 0 || bias > 65535) return LCB_ERR_INVALID;
+    if (c->generic) return fail(c, LCB_ERR_INVALID, "the packed wire format is defined for d == 256, q < 2^16 contexts only");
     if (npoly == 0) return LCB_OK;
     CK(c, cudaSetDevice(c->device));
     Staging sg(c);
@@ -860,6 +974,7 @@ int lcb_pack_batch(lcb_ctx* c, const void* values, int64_t npoly, int bits, int 
 
 int lcb_unpack_batch(lcb_ctx* c, const uint8_t* packed, int64_t npoly, int bits, int bias, void* values) {
     if (!c || !values || !packed || npoly < 0 || bits < 1 || bits > 16 || bias < 0 || bias > 65535) return LCB_ERR_INVALID;
+    if (c->generic) return fail(c, LCB_ERR_INVALID, "the packed wire format is defined for d == 256, q < 2^16 contexts only");
     if (npoly == 0) return LCB_OK;
     CK(c, cudaSetDevice(c->device));
     Staging sg(c);
@@ -882,6 +997,7 @@ int lcb_lm_verify_packed_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t*
     if (!c || !sch || !vk_packed || !chmsg_off || !sig_packed || !verdict || n < 0 || bd < 0 || wt < 0 ||
         vk_bits < 1 || vk_bits > 16 || sig_bits < 1 || sig_bits > 16 || sig_bias < 0 || sig_bias > 32767)
         return LCB_ERR_INVALID;
+    if (c->generic) return fail(c, LCB_ERR_INVALID, "the packed wire format is defined for d == 256, q < 2^16 contexts only");
     if (!c->has_key_ch) return fail(c, LCB_ERR_NO_KEY_CH, "lcb_lm_verify_packed_batch before lcb_set_key_ch");
     if (n == 0) return LCB_OK;
     CK(c, cudaSetDevice(c->device));
@@ -970,7 +1086,7 @@ int lcb_bklm_agg_coefs(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* agmsg, 
     const uint8_t* d_msg;
     int16_t* d_pairs;
     CK(c, sg.in(&d_msg, agmsg, (size_t)agmsg_len));
-    CK(c, sg.out(&d_pairs, out_pairs, (size_t)count * sch->ag_wt * 2));
+    CK(c, sg.out(&d_pairs, out_pairs, (size_t)count * sch->ag_wt * 2 * ew(c)));
     int st = run_agg_coefs(c, sch, d_msg, agmsg_len, first, count, d_pairs);
     if (st != LCB_OK) return st;
     CK(c, sg.finish());
@@ -987,20 +1103,28 @@ int lcb_bklm_aggregate_partial(lcb_ctx* c, const lcb_scheme* sch, const int16_t*
     const int16_t *d_sig, *d_pairs_in;
     const uint8_t* d_msg;
     int32_t* d_partial;
-    CK(c, sg.in(&d_sig, sig_sorted, (size_t)count * l * D));
-    CK(c, sg.in(&d_pairs_in, ag_pairs, (size_t)count * 2));
-    CK(c, sg.out(&d_partial, partial, (size_t)l * D));
-    CK(c, cudaMemsetAsync(d_partial, 0, (size_t)l * D * sizeof(int32_t), c->stream));
+    const size_t D_ = (size_t)c->d * ew(c);
+    const size_t pair_len = (size_t)sch->ag_wt * 2 * ew(c);
+    const bool monomial = sch->ag_wt == 1 && sch->ag_bd == 1;
+    if (sch->ag_wt < 1 || sch->ag_wt > c->d || sch->ag_bd < 1) return fail(c, LCB_ERR_INVALID, "bad aggregation parameters");
+    CK(c, sg.in(&d_sig, sig_sorted, (size_t)count * l * D_));
+    CK(c, sg.in(&d_pairs_in, ag_pairs, (size_t)count * pair_len));
+    CK(c, sg.out(&d_partial, partial, (size_t)l * c->d * ew(c)));
+    CK(c, cudaMemsetAsync(d_partial, 0, (size_t)l * c->d * ew(c) * sizeof(int32_t), c->stream));
     if (count > 0) {
         if (!d_pairs_in) {
             int16_t* d_pairs;
             CK(c, sg.in(&d_msg, agmsg, (size_t)agmsg_len));
-            CK(c, sg.alloc((void**)&d_pairs, (size_t)count * 2 * sizeof(int16_t)));
+            CK(c, sg.alloc((void**)&d_pairs, (size_t)count * pair_len * sizeof(int16_t)));
             int st = run_agg_coefs(c, sch, d_msg, agmsg_len, first, count, d_pairs);
             if (st != LCB_OK) return st;
             d_pairs_in = d_pairs;
         }
-        CK(c, timed(c, K_AGG_PARTIAL, [&] { return launch_agg_partial(c->ring, d_sig, d_pairs_in, count, d_partial, c->stream); }));
+        CK(c, timed(c, K_AGG_PARTIAL, [&] {
+            if (!monomial) return g_launch_agg_partial_poly(c->gen, d_sig, d_pairs_in, sch->ag_wt, count, d_partial, c->stream);
+            return c->generic ? g_launch_agg_partial(c->gen, d_sig, d_pairs_in, count, d_partial, c->stream)
+                              : launch_agg_partial(c->ring, d_sig, d_pairs_in, count, d_partial, c->stream);
+        }));
     }
     CK(c, sg.finish());
     return LCB_OK;
@@ -1012,9 +1136,11 @@ int lcb_bklm_aggregate_finish(lcb_ctx* c, const int32_t* partial_sum, int16_t* a
     Staging sg(c);
     const int32_t* d_partial;
     int16_t* d_out;
-    CK(c, sg.in(&d_partial, partial_sum, (size_t)c->l * D));
-    CK(c, sg.out(&d_out, ag_sig, (size_t)c->l * D));
-    CK(c, timed(c, K_AGG_FINISH, [&] { return launch_agg_finish(c->ring, d_partial, d_out, c->stream); }));
+    CK(c, sg.in(&d_partial, partial_sum, (size_t)c->l * c->d * ew(c)));
+    CK(c, sg.out(&d_out, ag_sig, (size_t)c->l * c->d * ew(c)));
+    CK(c, timed(c, K_AGG_FINISH, [&] {
+        return c->generic ? g_launch_agg_finish(c->gen, d_partial, d_out, c->stream) : launch_agg_finish(c->ring, d_partial, d_out, c->stream);
+    }));
     CK(c, sg.finish());
     return LCB_OK;
 }
@@ -1028,8 +1154,12 @@ int lcb_bklm_aggverify_partial(lcb_ctx* c, const lcb_scheme* sch, const uint16_t
     CK(c, cudaSetDevice(c->device));
     Staging sg(c);
     int32_t* d_partial;
-    CK(c, sg.out(&d_partial, partial, (size_t)D));
-    CK(c, cudaMemsetAsync(d_partial, 0, (size_t)D * sizeof(int32_t), c->stream));
+    const size_t D_ = (size_t)c->d * ew(c);
+    const size_t pair_len = (size_t)sch->ag_wt * 2 * ew(c);
+    const bool monomial = sch->ag_wt == 1 && sch->ag_bd == 1;
+    if (sch->ag_wt < 1 || sch->ag_wt > c->d || sch->ag_bd < 1) return fail(c, LCB_ERR_INVALID, "bad aggregation parameters");
+    CK(c, sg.out(&d_partial, partial, (size_t)c->d * ew(c)));
+    CK(c, cudaMemsetAsync(d_partial, 0, (size_t)c->d * ew(c) * sizeof(int32_t), c->stream));
     if (count > 0) {
         int64_t total = 0;
         CK(c, last_offset(c, chmsg_sorted, chmsg_off, count, &total));
@@ -1038,22 +1168,26 @@ int lcb_bklm_aggverify_partial(lcb_ctx* c, const lcb_scheme* sch, const uint16_t
         const int64_t* d_off;
         const int16_t* d_ag;
         int16_t* d_ch;
-        CK(c, sg.in(&d_vk, vk_ntt_sorted, (size_t)count * 2 * D));
+        CK(c, sg.in(&d_vk, vk_ntt_sorted, (size_t)count * 2 * D_));
         CK(c, sg.in(&d_chmsg, chmsg_sorted, (size_t)total));
         CK(c, sg.in(&d_off, chmsg_off, (size_t)count + 1));
-        CK(c, sg.in(&d_ag, ag_pairs, (size_t)count * 2));
-        CK(c, sg.alloc((void**)&d_ch, (size_t)count * sch->ch_wt * 2 * sizeof(int16_t)));
+        CK(c, sg.in(&d_ag, ag_pairs, (size_t)count * pair_len));
+        CK(c, sg.alloc((void**)&d_ch, (size_t)count * sch->ch_wt * 2 * ew(c) * sizeof(int16_t)));
         int st = run_challenge(c, sch, d_chmsg, d_off, count, d_ch);
         if (st != LCB_OK) return st;
         if (!d_ag) {
             int16_t* d_pairs;
             CK(c, sg.in(&d_agmsg, agmsg, (size_t)agmsg_len));
-            CK(c, sg.alloc((void**)&d_pairs, (size_t)count * 2 * sizeof(int16_t)));
+            CK(c, sg.alloc((void**)&d_pairs, (size_t)count * pair_len * sizeof(int16_t)));
             st = run_agg_coefs(c, sch, d_agmsg, agmsg_len, first, count, d_pairs);
             if (st != LCB_OK) return st;
             d_ag = d_pairs;
         }
-        CK(c, timed(c, K_AGGV_PARTIAL, [&] { return launch_aggv_partial(c->ring, d_vk, d_ch, sch->ch_wt, d_ag, count, d_partial, c->stream); }));
+        CK(c, timed(c, K_AGGV_PARTIAL, [&] {
+            if (!monomial) return g_launch_aggv_partial_poly(c->gen, d_vk, d_ch, sch->ch_wt, d_ag, sch->ag_wt, count, d_partial, c->stream);
+            return c->generic ? g_launch_aggv_partial(c->gen, d_vk, d_ch, sch->ch_wt, d_ag, count, d_partial, c->stream)
+                              : launch_aggv_partial(c->ring, d_vk, d_ch, sch->ch_wt, d_ag, count, d_partial, c->stream);
+        }));
     }
     CK(c, sg.finish());
     return LCB_OK;
@@ -1068,10 +1202,13 @@ int lcb_bklm_aggverify_finish(lcb_ctx* c, const int32_t* partial_sum, const int1
     const int32_t* d_partial;
     const int16_t* d_sig;
     uint8_t* d_verdict;
-    CK(c, sg.in(&d_partial, partial_sum, (size_t)D));
-    CK(c, sg.in(&d_sig, ag_sig, (size_t)c->l * D));
+    CK(c, sg.in(&d_partial, partial_sum, (size_t)c->d * ew(c)));
+    CK(c, sg.in(&d_sig, ag_sig, (size_t)c->l * c->d * ew(c)));
     CK(c, sg.out(&d_verdict, verdict, 1));
-    CK(c, timed(c, K_AGGV_FINISH, [&] { return launch_aggv_finish(c->ring, d_partial, d_sig, total, ag_cap, avf_bd, avf_wt, d_verdict, c->stream); }));
+    CK(c, timed(c, K_AGGV_FINISH, [&] {
+        return c->generic ? g_launch_aggv_finish(c->gen, d_partial, d_sig, total, ag_cap, avf_bd, avf_wt, d_verdict, c->stream)
+                          : launch_aggv_finish(c->ring, d_partial, d_sig, total, ag_cap, avf_bd, avf_wt, d_verdict, c->stream);
+    }));
     CK(c, sg.finish());
     return LCB_OK;
 }
@@ -1093,17 +1230,21 @@ int lcb_adaptor_witgen_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* s
     uint16_t* d_st_ntt;
     CK(c, sg.in(&a.msgs, seeds, (size_t)total));
     CK(c, sg.in(&a.off, seed_off, (size_t)n + 1));
-    CK(c, sg.out(&d_wit, wit_coef, (size_t)n * l * D, true));
-    CK(c, sg.out(&d_st_ntt, st_ntt, (size_t)n * D));
-    CK(c, sg.out(&d_st_coef, st_coef, (size_t)n * D));
-    if (!d_wit) CK(c, sg.alloc((void**)&d_wit, (size_t)n * l * D * sizeof(int16_t), true));
-    if (sch->wit_wt < D) CK(c, cudaMemsetAsync(d_wit, 0, (size_t)n * l * D * sizeof(int16_t), c->stream));
+    const size_t D_ = (size_t)c->d * ew(c);
+    CK(c, sg.out(&d_wit, wit_coef, (size_t)n * l * D_, true));
+    CK(c, sg.out(&d_st_ntt, st_ntt, (size_t)n * D_));
+    CK(c, sg.out(&d_st_coef, st_coef, (size_t)n * D_));
+    if (!d_wit) CK(c, sg.alloc((void**)&d_wit, (size_t)n * l * D_ * sizeof(int16_t), true));
+    if (sch->wit_wt < c->d) CK(c, cudaMemsetAsync(d_wit, 0, (size_t)n * l * D_ * sizeof(int16_t), c->stream));
     a.n = n;
     a.out_dense = d_wit;
-    a.dense_stride = (int64_t)l * D;
+    a.dense_stride = (int64_t)l * c->d;
     CK(c, sampler_scratch(c, a));
     CK(c, timed(c, K_SAMPLER, [&] { return launch_sampler(a, c->stream); }));
-    CK(c, timed(c, K_MATVEC, [&] { return launch_matvec(c->ring, d_wit, n, nullptr, d_st_ntt, d_st_coef, c->stream); }));
+    CK(c, timed(c, K_MATVEC, [&] {
+        return c->generic ? g_launch_matvec(c->gen, d_wit, n, nullptr, d_st_ntt, d_st_coef, c->stream)
+                          : launch_matvec(c->ring, d_wit, n, nullptr, d_st_ntt, d_st_coef, c->stream);
+    }));
     CK(c, sg.finish());
     return LCB_OK;
 }
@@ -1114,10 +1255,13 @@ static int vec_addsub(lcb_ctx* c, const int16_t* a, const int16_t* b, int64_t np
     Staging sg(c);
     const int16_t *d_a, *d_b;
     int16_t* d_out;
-    CK(c, sg.in(&d_a, a, (size_t)npoly * D));
-    CK(c, sg.in(&d_b, b, (size_t)npoly * D));
-    CK(c, sg.out(&d_out, out, (size_t)npoly * D));
-    CK(c, timed(c, K_ADDSUB, [&] { return launch_vec_addsub(c->ring, d_a, d_b, npoly * D, sub, d_out, c->stream); }));
+    CK(c, sg.in(&d_a, a, (size_t)npoly * c->d * ew(c)));
+    CK(c, sg.in(&d_b, b, (size_t)npoly * c->d * ew(c)));
+    CK(c, sg.out(&d_out, out, (size_t)npoly * c->d * ew(c)));
+    CK(c, timed(c, K_ADDSUB, [&] {
+        return c->generic ? g_launch_vec_addsub(c->gen, d_a, d_b, npoly * c->d, sub, d_out, c->stream)
+                          : launch_vec_addsub(c->ring, d_a, d_b, npoly * D, sub, d_out, c->stream);
+    }));
     CK(c, sg.finish());
     return LCB_OK;
 }
@@ -1140,11 +1284,14 @@ int lcb_adaptor_witness_verify_batch(lcb_ctx* c, const int16_t* wit_coef, const 
     const int16_t* d_wit;
     const uint16_t* d_st;
     uint8_t* d_verdict;
-    CK(c, sg.in(&d_wit, wit_coef, (size_t)n * c->l * D));
-    CK(c, sg.in(&d_st, st_ntt, (size_t)n * D));
+    CK(c, sg.in(&d_wit, wit_coef, (size_t)n * c->l * c->d * ew(c)));
+    CK(c, sg.in(&d_st, st_ntt, (size_t)n * c->d * ew(c)));
     CK(c, sg.out(&d_verdict, verdict, (size_t)n));
-    CK(c, timed(c, K_VERIFY, [&] { return launch_verify(c->ring, d_wit, nullptr, nullptr, 0, d_st, nullptr, n, bd > 32767 ? 32767 : bd, wt, d_verdict,
-                        c->stream); }));
+    CK(c, timed(c, K_VERIFY, [&] {
+        return c->generic ? g_launch_verify(c->gen, d_wit, nullptr, nullptr, 0, d_st, nullptr, n, bd, wt, d_verdict, c->stream)
+                          : launch_verify(c->ring, d_wit, nullptr, nullptr, 0, d_st, nullptr, n, bd > 32767 ? 32767 : bd, wt, d_verdict,
+                                          c->stream);
+    }));
     CK(c, sg.finish());
     return LCB_OK;
 }

@@ -36,11 +36,21 @@ struct SamplerArgs {
     // per sponge
     uint2* il_msg;
     int64_t il_stride;
+    // ring geometry (d = 256 and 16-bit outputs take the fast kernel, anything else k_sampler_g)
+    int d, logd;
+    int wide;                  // outputs are int32 (moduli q >= 2^16) instead of int16
+    // per-stream salts (aggregation coefficients with ag_wt > 1): [n][SALT_BYTES] bytes + [n] lengths, or nullptr
+    const uint8_t* stream_salts;
+    const int32_t* stream_salt_len;
 };
 
 cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st);
+cudaError_t launch_index_salts(const SamplerArgs& a, uint8_t* salts, int32_t* lens, cudaStream_t st);
 inline int64_t sampler_stride(int64_t n) { return (n + 127) / 128 * 128; }
-inline size_t sampler_scratch_bytes(int64_t n, int wt) { return (size_t)sampler_stride(n) * (size_t)wt; }
+// parked indices: one byte each for d = 256, two bytes on the generic path
+inline size_t sampler_scratch_bytes(int64_t n, int wt, bool generic = false) {
+    return (size_t)sampler_stride(n) * (size_t)wt * (generic ? 2 : 1);
+}
 cudaError_t launch_shake256(const uint8_t* in, const int64_t* off, int64_t n, uint8_t* out, int64_t out_len,
                             cudaStream_t st);
 // shared-message fast path, wt == 1; two lanes per sponge when a.il_msg is set (see agg_coefs_two_lane)
@@ -48,6 +58,50 @@ cudaError_t launch_agg_coefs(const SamplerArgs& a, int num_sms, cudaStream_t st)
 bool agg_coefs_two_lane(int64_t n, int num_sms);
 inline int64_t agg_il_stride(int64_t msg_len) { return msg_len / 8 + 1; }
 inline size_t agg_il_bytes(int64_t msg_len) { return (size_t)8 * (size_t)agg_il_stride(msg_len) * sizeof(uint2); }
+
+// ---- generic degree / modulus (ring_generic.cu) -------------------------------------------------------------
+struct GenRing {
+    uint32_t q, half;          // modulus (< 2^31), (q - 1) / 2
+    int d, logd;               // power-of-two degree 32..1024
+    uint64_t mu64;             // floor(2^64 / q): 64-bit Barrett constant
+    uint64_t pos_off;          // least multiple of q >= 2^31: makes any int32 coefficient non-negative
+    uint32_t dinv, dinv_s;     // d^-1 mod q and its Shoup companion
+    const uint32_t *w, *ws, *iw, *iws;   // device, [d]: zetas[k] = psi^bitrev_logd(k), inverses, Shoup companions
+    const uint32_t* pw;        // device, [2d]: psi^e
+};
+
+struct GenCtx {
+    GenRing r;
+    const uint32_t* a_hat;     // device, uint32[l][d]: NTT(key_ch)
+    int l, num_sms;
+    bool wide;                 // int32 / uint32 element formats (q >= 2^16)
+};
+
+cudaError_t g_launch_ntt_fwd(const GenCtx& c, const void* coef, int64_t npoly, void* out, cudaStream_t st);
+cudaError_t g_launch_ntt_inv(const GenCtx& c, const void* in, int64_t npoly, void* coef, cudaStream_t st);
+cudaError_t g_launch_poly_mul(const GenCtx& c, const void* a, const void* b, int64_t npoly, void* out, cudaStream_t st);
+cudaError_t g_launch_ref_repr(const GenCtx& c, const void* coef, int64_t npoly, void* out, cudaStream_t st);
+cudaError_t g_launch_matvec(const GenCtx& c, const void* vec_coef, int64_t nvec, void* vec_ntt, void* y_ntt, void* y_coef,
+                            cudaStream_t st);
+cudaError_t g_launch_sign(const GenCtx& c, const void* sk_ntt, const void* ch_pairs, int ch_wt, int64_t n, void* sig,
+                          cudaStream_t st);
+cudaError_t g_launch_verify(const GenCtx& c, const void* vec_coef, const void* vk_ntt, const void* ch_pairs, int ch_wt,
+                            const void* rhs_only, const void* extra_rhs, int64_t n, int64_t bd, int wt, uint8_t* verdict,
+                            cudaStream_t st);
+cudaError_t g_launch_vec_addsub(const GenCtx& c, const void* a, const void* b, int64_t nelem, int sub, void* out,
+                                cudaStream_t st);
+cudaError_t g_launch_agg_partial(const GenCtx& c, const void* sigs, const void* ag_pairs, int64_t count, void* partial,
+                                 cudaStream_t st);
+// general (non-monomial) aggregation coefficients: ag_pairs [count][ag_wt][2]
+cudaError_t g_launch_agg_partial_poly(const GenCtx& c, const void* sigs, const void* ag_pairs, int ag_wt, int64_t count,
+                                      void* partial, cudaStream_t st);
+cudaError_t g_launch_aggv_partial_poly(const GenCtx& c, const void* vk_ntt, const void* ch_pairs, int ch_wt, const void* ag_pairs,
+                                       int ag_wt, int64_t count, void* partial, cudaStream_t st);
+cudaError_t g_launch_agg_finish(const GenCtx& c, const void* partial, void* ag_sig, cudaStream_t st);
+cudaError_t g_launch_aggv_partial(const GenCtx& c, const void* vk_ntt, const void* ch_pairs, int ch_wt, const void* ag_pairs,
+                                  int64_t count, void* partial, cudaStream_t st);
+cudaError_t g_launch_aggv_finish(const GenCtx& c, const void* partial, const void* ag_sig, int64_t total, int64_t ag_cap,
+                                 int64_t avf_bd, int avf_wt, uint8_t* verdict, cudaStream_t st);
 
 struct RingCtx {
     ModQ m;

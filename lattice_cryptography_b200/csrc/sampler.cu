@@ -102,6 +102,61 @@ __global__ void __launch_bounds__(P, 640 / P) k_sampler(SamplerArgs a) {   // 5 
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same sampler for any power-of-two degree 32 <= d <= 1024 (run-time geometry, 16-bit parked indices, Horner
+// field reduction) and, with CT = int32_t, for coefficient bounds beyond int16 (moduli q >= 2^16).  Shared memory
+// per block: ring [54][P], bmap [d/32][P], mutab [d + 1].
+template <int P, typename CT>
+__global__ void __launch_bounds__(P) k_sampler_g(SamplerArgs a) {
+    extern __shared__ uint32_t smem[];
+    const GeoAny geo{a.d, a.logd};
+    uint32_t* ring = smem;                       // [RING_WORDS][P]
+    uint32_t* bmap = ring + RING_WORDS * P;      // [d / 32][P]
+    uint32_t* mutab = bmap + geo.words() * P;    // [d + 1]
+    const int tid = threadIdx.x;
+    const int64_t inst_raw = (int64_t)blockIdx.x * P + tid;
+    const bool live = inst_raw < a.n;
+    const int64_t inst = live ? inst_raw : a.n - 1;
+    const int64_t item = a.paired ? inst >> 1 : inst;
+    const bool second = a.paired && (inst & 1);
+    const int64_t msg_begin = a.shared_msg ? 0 : __ldg(a.off + item), msg_end = a.shared_msg ? a.shared_len : __ldg(a.off + item + 1);
+    fill_mod_tables(mutab, nullptr, a.wt, a.d);
+    __syncthreads();
+    // per-stream salts (BKLM aggregation coefficients with ag_wt > 1: ag_salt || decimal index, prepared by
+    // k_index_salts) or the one or two warp-uniform salts of the call
+    const uint32_t* salt_w = a.stream_salts ? reinterpret_cast<const uint32_t*>(a.stream_salts + inst * SALT_BYTES)
+                                            : reinterpret_cast<const uint32_t*>(second ? a.salt2 : a.salt);
+    const int salt_len = a.stream_salts ? (int)a.stream_salt_len[inst] : (second ? a.salt2_len : a.salt_len);
+    const InputView iv{salt_w, salt_len, a.msgs + msg_begin, msg_end - msg_begin};
+    const DecodeParams dp{a.bd, a.wt, a.vec_len, a.idx_bits, a.mag_bits, a.pad_bits};
+    const StreamColsT<uint16_t> sc{ring + tid, bmap + tid, P, mutab, nullptr, nullptr, 0,
+                                   reinterpret_cast<uint16_t*>(a.idx_scratch) + inst_raw, a.idx_stride};
+    CT* dense = a.out_dense ? reinterpret_cast<CT*>(a.out_dense) + inst * a.dense_stride : nullptr;
+    CT* pairs = a.out_pairs ? reinterpret_cast<CT*>(a.out_pairs) + inst * a.vec_len * (int64_t)a.wt * 2 : nullptr;
+    const int wt = a.wt, d = a.d;
+    sample_stream_t<GeoAny, uint16_t>(geo, dp, iv, sc, [&](int poly, int e, int idx, int coef) {
+        if (!live) return;
+        if (dense) dense[(int64_t)poly * d + idx] = (CT)coef;
+        if (pairs) {
+            pairs[((int64_t)poly * wt + e) * 2] = (CT)idx;
+            pairs[((int64_t)poly * wt + e) * 2 + 1] = (CT)coef;
+        }
+    });
+}
+
+// salt' = salt || decimal(first + i), zero padded to SALT_BYTES, one per stream (aggregation coefficients)
+__global__ void k_index_salts(SamplerArgs a, uint8_t* __restrict__ salts, int32_t* __restrict__ lens) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    uint8_t* s = salts + i * SALT_BYTES;
+    for (int b = 0; b < SALT_BYTES; ++b) s[b] = b < a.salt_len ? a.salt[b] : 0;
+    uint64_t v = (uint64_t)(a.index_first + i);
+    int nd = 1;
+    for (uint64_t t = v; t >= 10; t /= 10) ++nd;
+    for (int pos = a.salt_len + nd - 1; pos >= a.salt_len; --pos, v /= 10) s[pos] = (uint8_t)('0' + v % 10);
+    lens[i] = a.salt_len + nd;
+}
+
+// ------------------------------------------------------------------------------------------------
 // BKLM aggregation coefficients (bklm_one_time_agg_sigs.py:60-81), ag_wt = ag_bd = 1: coefficient i is
 // +-X^k with k = first digest byte and sign = top bit of the second byte of
 // SHAKE256(ag_salt || str(i) || agmsg).  Every stream absorbs the SAME O(N)-byte message behind a
@@ -355,8 +410,27 @@ cudaError_t launch_shake256(const uint8_t* in, const int64_t* off, int64_t n, ui
     return cudaGetLastError();
 }
 
+cudaError_t launch_index_salts(const SamplerArgs& a, uint8_t* salts, int32_t* lens, cudaStream_t st) {
+    if (a.n <= 0) return cudaSuccess;
+    k_index_salts<<<(unsigned)((a.n + 127) / 128), 128, 0, st>>>(a, salts, lens);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_sampler_generic(const SamplerArgs& a, cudaStream_t st) {
+    constexpr int P = 64;
+    if (!a.idx_scratch || a.idx_stride < (a.n + P - 1) / P * P) return cudaErrorInvalidValue;
+    if (a.idx_bits > MAX_FIELD_BITS || 1 + a.mag_bits > MAX_FIELD_BITS) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)(RING_WORDS + a.d / 32) * P * 4 + (size_t)(a.d + 1) * 4;
+    auto kern = a.wide ? k_sampler_g<P, int32_t> : k_sampler_g<P, int16_t>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<(unsigned)((a.n + P - 1) / P), P, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st) {
     if (a.n <= 0) return cudaSuccess;
+    if (a.d != D || a.wide || a.stream_salts || a.shared_msg) return launch_sampler_generic(a, st);
     static int num_sms = 0;
     if (!num_sms) {
         int dev = 0;

@@ -82,6 +82,22 @@ struct InputView {
     }
 };
 
+// Ring geometry seen by the decoder: the shipped degree as compile-time constants (every shift and loop bound
+// folds), or any power-of-two degree 32..1024 at run time.
+struct Geo256 {
+    static constexpr bool kFixed = true;
+    __device__ __forceinline__ int d() const { return D; }
+    __device__ __forceinline__ int logd() const { return LOGD; }
+    __device__ __forceinline__ int words() const { return D / 32; }
+};
+struct GeoAny {
+    static constexpr bool kFixed = false;
+    int d_, logd_;
+    __device__ __forceinline__ int d() const { return d_; }
+    __device__ __forceinline__ int logd() const { return logd_; }
+    __device__ __forceinline__ int words() const { return d_ >> 5; }
+};
+
 struct DecodeParams {
     int bd, wt, vec_len;
     int idx_bits;              // LOGD + secpar
@@ -93,23 +109,25 @@ constexpr int RING_EXTRA = 20;                       // words a field may need b
 constexpr int RING_WORDS = RATE_WORDS + RING_EXTRA;  // per-stream window over the squeeze stream
 constexpr int MAX_FIELD_BITS = 32 * (RING_EXTRA - 1);
 
-struct StreamCols {
+template <typename IdxT>
+struct StreamColsT {
     uint32_t* ring;            // [RING_WORDS] column: big-endian stream words, window over the digest
-    uint32_t* bmap;            // [8] column: bitmap of still-unused positions (d = 256); MUST follow `ring`
+    uint32_t* bmap;            // [d / 32] column: bitmap of still-unused positions; MUST follow `ring`
     int pitch;
     const uint32_t* mutab;     // [257] floor((2^32-1)/m)   (block-shared)
     const uint32_t* r16tab;    // [257] 2^16 mod m
     const uint8_t* wtab;       // [257][wstride] 2^(32k) mod m, rows filled by fill_weight_table
     int wstride;               // pieces per row
-    uint8_t* idxs;             // global scratch, byte e of this stream at idxs[e * idx_stride]
+    IdxT* idxs;                // global scratch, index e of this stream at idxs[e * idx_stride]
     int64_t idx_stride;
 };
+using StreamCols = StreamColsT<uint8_t>;
 
 // Only the rows a sampler call can touch: the index moduli D-wt+1 .. D-1 (bd keeps its constants in registers).
-__device__ __forceinline__ void fill_mod_tables(uint32_t* mutab, uint32_t* r16tab, int wt) {
-    for (int m = max(1, D - wt + 1) + (int)threadIdx.x; m <= D; m += blockDim.x) {
+__device__ __forceinline__ void fill_mod_tables(uint32_t* mutab, uint32_t* r16tab, int wt, int d = D) {
+    for (int m = max(1, d - wt + 1) + (int)threadIdx.x; m <= d; m += blockDim.x) {
         mutab[m] = 0xFFFFFFFFu / (uint32_t)m;
-        r16tab[m] = 65536u % (uint32_t)m;
+        if (r16tab) r16tab[m] = 65536u % (uint32_t)m;
     }
 }
 
@@ -154,9 +172,9 @@ __device__ __forceinline__ uint32_t barrett_small(uint32_t x, uint32_t mu, uint3
 //   pad bits      : skipped.
 // Indices are parked in a global scratch column until their coefficients arrive (the coefficients of a
 // polynomial are drawn after ALL its indices).
-template <typename Emit>
-__device__ __forceinline__ void sample_stream(const DecodeParams& dp, const InputView& iv, const StreamCols& sc,
-                                              Emit&& emit) {
+template <typename Geo, typename IdxT, typename Emit>
+__device__ __forceinline__ void sample_stream_t(const Geo& geo, const DecodeParams& dp, const InputView& iv,
+                                                const StreamColsT<IdxT>& sc, Emit&& emit) {
     const int P = sc.pitch;
     const int64_t in_total = iv.total();
     // the pad byte always needs room; 32-bit division whenever the input is shorter than 4 GiB
@@ -225,36 +243,72 @@ __device__ __forceinline__ void sample_stream(const DecodeParams& dp, const Inpu
         const uint32_t lo = (uint32_t)acc, hi = (uint32_t)(acc >> 32);     // hi < 2^13
         return barrett_small(hi * wrow[1] + (lo >> 16) * r16 + (lo & 0xFFFFu), mu, m);
     };
+    // Value of the next `width` bits modulo m < 2^16 as a 16-bit Horner recurrence (any width; generic degrees and
+    // the bd > 256 sampler of key_ch), and the same for moduli up to 2^31 with 64-bit remainders (wide contexts).
+    auto field_horner = [&](int width, uint32_t m, uint32_t mu) -> uint32_t {
+        uint32_t r = 0;
+        int rem = width;
+        while (rem > 0) {
+            const int n = (rem & 15) ? (rem & 15) : 16;
+            r = barrett_small((r << n) | take(n), mu, m);
+            rem -= n;
+        }
+        return r;
+    };
+    auto field_horner64 = [&](int width, uint32_t m) -> uint32_t {
+        uint64_t r = 0;
+        int rem = width;
+        while (rem > 0) {
+            const int n = (rem & 31) ? (rem & 31) : 32;
+            r = ((r << n) | take(n)) % m;
+            rem -= n;
+        }
+        return (uint32_t)r;
+    };
     const uint32_t bd = (uint32_t)dp.bd;
     const uint32_t bd_mu = 0xFFFFFFFFu / bd, bd_r16 = 65536u % bd;
     const int wt = dp.wt;
     for (int poly = 0; poly < dp.vec_len; ++poly) {
+        if constexpr (Geo::kFixed) {
 #pragma unroll
-        for (int w = 0; w < 8; ++w) sc.bmap[w * P] = 0xFFFFFFFFu;
+            for (int w = 0; w < 8; ++w) sc.bmap[w * P] = 0xFFFFFFFFu;
+        } else {
+            for (int w = 0; w < geo.words(); ++w) sc.bmap[w * P] = 0xFFFFFFFFu;
+        }
         for (int f = 0; f <= 2 * wt; ++f) {
             const bool is_idx = f < wt, is_coef = f >= wt && f < 2 * wt;
-            ensure(f == 0 ? LOGD : (is_idx ? dp.idx_bits : (is_coef ? 1 + dp.mag_bits : dp.pad_bits)));   // the one call site
+            ensure(f == 0 ? geo.logd() : (is_idx ? dp.idx_bits : (is_coef ? 1 + dp.mag_bits : dp.pad_bits)));   // the one call site
             if (is_idx) {
                 // ---- one position of the index set
                 uint32_t selw, word, pos;
                 if (f == 0) {
-                    const uint32_t r = take(LOGD);
+                    const uint32_t r = take(geo.logd());
                     selw = r >> 5;
                     pos = r & 31;
                     word = sc.bmap[selw * P];
                 } else {
-                    const uint32_t m = (uint32_t)(D - f);
+                    const uint32_t m = (uint32_t)(geo.d() - f);
                     uint32_t k = 0;
                     if (m == 1) rp += dp.idx_bits;
-                    else k = field_small(dp.idx_bits, m, sc.mutab[m], sc.r16tab[m], sc.wtab + m * sc.wstride);
+                    else if constexpr (Geo::kFixed) k = field_small(dp.idx_bits, m, sc.mutab[m], sc.r16tab[m], sc.wtab + m * sc.wstride);
+                    else k = field_horner(dp.idx_bits, m, sc.mutab[m]);
                     // k-th (0-based) still-unused position in ascending order
                     bool found = false;
                     selw = 0; word = 0;
+                    if constexpr (Geo::kFixed) {
 #pragma unroll
-                    for (uint32_t w = 0; w < 8; ++w) {
-                        const uint32_t cand = sc.bmap[w * P];
-                        const uint32_t cnt = __popc(cand);
-                        if (!found) {
+                        for (uint32_t w = 0; w < 8; ++w) {
+                            const uint32_t cand = sc.bmap[w * P];
+                            const uint32_t cnt = __popc(cand);
+                            if (!found) {
+                                if (k < cnt) { found = true; selw = w; word = cand; }
+                                else k -= cnt;
+                            }
+                        }
+                    } else {
+                        for (uint32_t w = 0; w < (uint32_t)geo.words() && !found; ++w) {
+                            const uint32_t cand = sc.bmap[w * P];
+                            const uint32_t cnt = __popc(cand);
                             if (k < cnt) { found = true; selw = w; word = cand; }
                             else k -= cnt;
                         }
@@ -268,7 +322,7 @@ __device__ __forceinline__ void sample_stream(const DecodeParams& dp, const Inpu
                     cnt = wd & 1u;              if (k >= cnt) { pos += 1; }
                 }
                 sc.bmap[selw * P] = word & ~(1u << pos);
-                sc.idxs[f * sc.idx_stride] = (uint8_t)(selw * 32 + pos);
+                sc.idxs[f * sc.idx_stride] = (IdxT)(selw * 32 + pos);
             } else if (is_coef) {
                 // ---- one coefficient
                 const int e = f - wt;
@@ -276,15 +330,12 @@ __device__ __forceinline__ void sample_stream(const DecodeParams& dp, const Inpu
                 uint32_t r = 0;
                 if (bd == 1) {
                     rp += dp.mag_bits;
-                } else if (bd <= 256) {
+                } else if (Geo::kFixed && bd <= 256) {
                     r = field_small(dp.mag_bits, bd, bd_mu, bd_r16, sc.wtab + bd * sc.wstride);
+                } else if (bd < 65536u) {
+                    r = field_horner(dp.mag_bits, bd, bd_mu);
                 } else {
-                    int rem = dp.mag_bits;
-                    while (rem > 0) {
-                        const int n = (rem & 15) ? (rem & 15) : 16;
-                        r = barrett_small((r << n) | take(n), bd_mu, bd);
-                        rem -= n;
-                    }
+                    r = field_horner64(dp.mag_bits, bd);
                 }
                 const int mag = 1 + (int)r;
                 emit(poly, e, (int)sc.idxs[e * sc.idx_stride], sign ? mag : -mag);
@@ -293,6 +344,11 @@ __device__ __forceinline__ void sample_stream(const DecodeParams& dp, const Inpu
             }
         }
     }
+}
+
+template <typename Emit>
+__device__ __forceinline__ void sample_stream(const DecodeParams& dp, const InputView& iv, const StreamCols& sc, Emit&& emit) {
+    sample_stream_t<Geo256, uint8_t>(Geo256{}, dp, iv, sc, static_cast<Emit&&>(emit));
 }
 
 }  // namespace lcb

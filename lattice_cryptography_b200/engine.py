@@ -46,7 +46,7 @@ def _addr(x):
 
 
 _NP_OF_TORCH = {'torch.int16': np.int16, 'torch.uint16': np.uint16, 'torch.uint8': np.uint8, 'torch.int32': np.int32,
-                'torch.int64': np.int64}
+                'torch.uint32': np.uint32, 'torch.int64': np.int64}
 
 
 def _want(x, name: str, dtypes, shape):
@@ -126,6 +126,10 @@ class Engine(object):
             self._ctx = c_void_p()
             raise LcbError(st, detail)
         self.secpar, self.q, self.d, self.l, self.device = secpar, modulus, degree, length, device
+        # element formats (include/lcb200.h): 16-bit for q < 2^16, 32-bit ("wide") otherwise; BKLM partial sums are
+        # int32 / int64 accordingly
+        self.wide = modulus >= 65536
+        self.ct, self.nt, self.pt = (np.int32, np.uint32, np.int64) if self.wide else (np.int16, np.uint16, np.int32)
 
     # ------------------------------------------------------------------ plumbing
     def close(self):
@@ -147,7 +151,8 @@ class Engine(object):
     def _out(self, shape, dtype, device: bool):
         if device:
             import torch
-            tdt = {np.int16: torch.int16, np.uint16: torch.uint16, np.uint8: torch.uint8, np.int32: torch.int32}[dtype]
+            tdt = {np.int16: torch.int16, np.uint16: torch.uint16, np.uint8: torch.uint8, np.int32: torch.int32,
+                   np.uint32: torch.uint32, np.int64: torch.int64}[dtype]
             return torch.empty(shape, dtype=tdt, device=f'cuda:{self.device}')
         return np.empty(shape, dtype=dtype)
 
@@ -200,7 +205,7 @@ class Engine(object):
 
     # ------------------------------------------------------------------ K1 / K2
     def set_key_ch(self, key_ch_coef):
-        _want(key_ch_coef, 'key_ch', np.int16, (self.l, self.d))
+        _want(key_ch_coef, 'key_ch', self.ct, (self.l, self.d))
         self._key_ch_token = None
         self._ck(self._lib.lcb_set_key_ch(self._ctx, _addr(key_ch_coef)))
         if isinstance(key_ch_coef, np.ndarray):
@@ -222,36 +227,36 @@ class Engine(object):
                      want_pairs: bool = False, device: bool = False):
         blob, off = self._rag(msgs)
         n = self._count(off)
-        dense = self._out((n, vec_len, self.d), np.int16, device) if want_dense else None
-        pairs = self._out((n, vec_len, wt, 2), np.int16, device) if want_pairs else None
+        dense = self._out((n, vec_len, self.d), self.ct, device) if want_dense else None
+        pairs = self._out((n, vec_len, wt, 2), self.ct, device) if want_pairs else None
         self._ck(self._lib.lcb_hash2polyvec_batch(self._ctx, salt.encode(), _addr(blob), _addr(off), n, bd, wt,
                                                   vec_len, _addr(dense), _addr(pairs)))
         return dense, pairs
 
     # ------------------------------------------------------------------ K3 / K4 / K6
     def ntt_fwd(self, coef, device: bool = False):
-        npoly = _lead(coef, 'coef', np.int16, self.d)
-        out = self._out(tuple(coef.shape), np.uint16, device)
+        npoly = _lead(coef, 'coef', self.ct, self.d)
+        out = self._out(tuple(coef.shape), self.nt, device)
         self._ck(self._lib.lcb_ntt_fwd_batch(self._ctx, _addr(coef), npoly, _addr(out)))
         return out
 
     def ntt_inv(self, ntt, device: bool = False):
-        npoly = _lead(ntt, 'ntt', np.uint16, self.d)
-        out = self._out(tuple(ntt.shape), np.int16, device)
+        npoly = _lead(ntt, 'ntt', self.nt, self.d)
+        out = self._out(tuple(ntt.shape), self.ct, device)
         self._ck(self._lib.lcb_ntt_inv_batch(self._ctx, _addr(ntt), npoly, _addr(out)))
         return out
 
     def ntt_reference_repr(self, coef, device: bool = False):
         """lattice_algebra's Polynomial.ntt_representation: int16[..., 2d], rep[k] = a(rou^k), centred."""
-        npoly = _lead(coef, 'coef', np.int16, self.d)
-        out = self._out(tuple(coef.shape[:-1]) + (2 * self.d,), np.int16, device)
+        npoly = _lead(coef, 'coef', self.ct, self.d)
+        out = self._out(tuple(coef.shape[:-1]) + (2 * self.d,), self.ct, device)
         self._ck(self._lib.lcb_ntt_reference_repr_batch(self._ctx, _addr(coef), npoly, _addr(out)))
         return out
 
     def poly_mul(self, a, b, device: bool = False):
-        npoly = _lead(a, 'a', np.int16, self.d)
-        _want(b, 'b', np.int16, tuple(a.shape))
-        out = self._out(tuple(a.shape), np.int16, device)
+        npoly = _lead(a, 'a', self.ct, self.d)
+        _want(b, 'b', self.ct, tuple(a.shape))
+        out = self._out(tuple(a.shape), self.ct, device)
         self._ck(self._lib.lcb_poly_mul_batch(self._ctx, _addr(a), _addr(b), npoly, _addr(out)))
         return out
 
@@ -260,10 +265,10 @@ class Engine(object):
                   want_vk_ntt: bool = True, want_vk_coef: bool = True, device: bool = False):
         blob, off = self._rag(seeds)
         n = self._count(off)
-        sk_coef = self._out((n, 2, self.l, self.d), np.int16, device) if want_sk_coef else None
-        sk_ntt = self._out((n, 2, self.l, self.d), np.uint16, device) if want_sk_ntt else None
-        vk_ntt = self._out((n, 2, self.d), np.uint16, device) if want_vk_ntt else None
-        vk_coef = self._out((n, 2, self.d), np.int16, device) if want_vk_coef else None
+        sk_coef = self._out((n, 2, self.l, self.d), self.ct, device) if want_sk_coef else None
+        sk_ntt = self._out((n, 2, self.l, self.d), self.nt, device) if want_sk_ntt else None
+        vk_ntt = self._out((n, 2, self.d), self.nt, device) if want_vk_ntt else None
+        vk_coef = self._out((n, 2, self.d), self.ct, device) if want_vk_coef else None
         self._ck(self._lib.lcb_lm_keygen_batch(self._ctx, byref(sch), _addr(blob), _addr(off), n, _addr(sk_coef),
                                                _addr(sk_ntt), _addr(vk_ntt), _addr(vk_coef)))
         return sk_coef, sk_ntt, vk_ntt, vk_coef
@@ -271,15 +276,15 @@ class Engine(object):
     def challenge(self, sch: LcbScheme, chmsgs, device: bool = False):
         blob, off = self._rag(chmsgs)
         n = self._count(off)
-        pairs = self._out((n, sch.ch_wt, 2), np.int16, device)
+        pairs = self._out((n, sch.ch_wt, 2), self.ct, device)
         self._ck(self._lib.lcb_challenge_batch(self._ctx, byref(sch), _addr(blob), _addr(off), n, _addr(pairs)))
         return pairs
 
     def lm_sign(self, sch: LcbScheme, sk_ntt, chmsgs, device: bool = False):
         blob, off = self._rag(chmsgs)
         n = self._count(off)
-        _want(sk_ntt, 'sk_ntt', np.uint16, (n, 2, self.l, self.d))
-        sig = self._out((n, self.l, self.d), np.int16, device)
+        _want(sk_ntt, 'sk_ntt', self.nt, (n, 2, self.l, self.d))
+        sig = self._out((n, self.l, self.d), self.ct, device)
         self._ck(self._lib.lcb_lm_sign_batch(self._ctx, byref(sch), _addr(sk_ntt), _addr(blob), _addr(off), n,
                                              _addr(sig)))
         return sig
@@ -288,10 +293,10 @@ class Engine(object):
                   out=None):
         blob, off = self._rag(chmsgs)
         n = self._count(off)
-        _want(vk_ntt, 'vk_ntt', np.uint16, (n, 2, self.d))
-        _want(sig, 'sig', np.int16, (n, self.l, self.d))
+        _want(vk_ntt, 'vk_ntt', self.nt, (n, 2, self.d))
+        _want(sig, 'sig', self.ct, (n, self.l, self.d))
         if st_ntt is not None:
-            _want(st_ntt, 'st_ntt', np.uint16, (n, self.d))
+            _want(st_ntt, 'st_ntt', self.nt, (n, self.d))
         verdict = _want(out, 'out', np.uint8, (n,)) if out is not None else self._out((n,), np.uint8, device)
         self._ck(self._lib.lcb_lm_verify_batch(self._ctx, byref(sch), _addr(vk_ntt), _addr(blob), _addr(off),
                                                _addr(sig), _addr(st_ntt), n, bd, wt, _addr(verdict)))
@@ -331,40 +336,40 @@ class Engine(object):
         if isinstance(agmsg, (str, bytes, bytearray)):
             agmsg = np.frombuffer(agmsg.encode() if isinstance(agmsg, str) else bytes(agmsg), dtype=np.uint8)
         _want(agmsg, 'agmsg', np.uint8, (None,))
-        pairs = self._out((count, sch.ag_wt, 2), np.int16, device)
+        pairs = self._out((count, sch.ag_wt, 2), self.ct, device)
         self._ck(self._lib.lcb_bklm_agg_coefs(self._ctx, byref(sch), _addr(agmsg), int(agmsg.shape[0]), first,
                                               count, _addr(pairs)))
         return pairs
 
     def aggregate_partial(self, sch: LcbScheme, sig_sorted, ag_pairs, device: bool = False):
         count = int(sig_sorted.shape[0])
-        _want(sig_sorted, 'sig_sorted', np.int16, (count, self.l, self.d))
-        _want(ag_pairs, 'ag_pairs', np.int16, (count, sch.ag_wt, 2))
-        partial = self._out((self.l, self.d), np.int32, device)
+        _want(sig_sorted, 'sig_sorted', self.ct, (count, self.l, self.d))
+        _want(ag_pairs, 'ag_pairs', self.ct, (count, sch.ag_wt, 2))
+        partial = self._out((self.l, self.d), self.pt, device)
         self._ck(self._lib.lcb_bklm_aggregate_partial(self._ctx, byref(sch), _addr(sig_sorted), _addr(ag_pairs),
                                                       None, 0, 0, count, _addr(partial)))
         return partial
 
     def aggregate_finish(self, partial_sum, device: bool = False):
-        _want(partial_sum, 'partial_sum', np.int32, (self.l, self.d))
-        out = self._out((self.l, self.d), np.int16, device)
+        _want(partial_sum, 'partial_sum', self.pt, (self.l, self.d))
+        out = self._out((self.l, self.d), self.ct, device)
         self._ck(self._lib.lcb_bklm_aggregate_finish(self._ctx, _addr(partial_sum), _addr(out)))
         return out
 
     def aggverify_partial(self, sch: LcbScheme, vk_ntt_sorted, chmsgs_sorted, ag_pairs, device: bool = False):
         blob, off = self._rag(chmsgs_sorted)
         count = self._count(off)
-        _want(vk_ntt_sorted, 'vk_ntt_sorted', np.uint16, (count, 2, self.d))
-        _want(ag_pairs, 'ag_pairs', np.int16, (count, sch.ag_wt, 2))
-        partial = self._out((self.d,), np.int32, device)
+        _want(vk_ntt_sorted, 'vk_ntt_sorted', self.nt, (count, 2, self.d))
+        _want(ag_pairs, 'ag_pairs', self.ct, (count, sch.ag_wt, 2))
+        partial = self._out((self.d,), self.pt, device)
         self._ck(self._lib.lcb_bklm_aggverify_partial(self._ctx, byref(sch), _addr(vk_ntt_sorted), _addr(blob),
                                                       _addr(off), _addr(ag_pairs), None, 0, 0, count,
                                                       _addr(partial)))
         return partial
 
     def aggverify_finish(self, partial_sum, ag_sig, total: int, ag_cap: int, avf_bd: int, avf_wt: int) -> bool:
-        _want(partial_sum, 'partial_sum', np.int32, (self.d,))
-        _want(ag_sig, 'ag_sig', np.int16, (self.l, self.d))
+        _want(partial_sum, 'partial_sum', self.pt, (self.d,))
+        _want(ag_sig, 'ag_sig', self.ct, (self.l, self.d))
         verdict = np.zeros(1, dtype=np.uint8)
         self._ck(self._lib.lcb_bklm_aggverify_finish(self._ctx, _addr(partial_sum), _addr(ag_sig), total, ag_cap,
                                                      avf_bd, avf_wt, _addr(verdict)))
@@ -375,31 +380,31 @@ class Engine(object):
                want_st_coef: bool = True, device: bool = False):
         blob, off = self._rag(seeds)
         n = self._count(off)
-        wit = self._out((n, self.l, self.d), np.int16, device) if want_wit else None
-        st_ntt = self._out((n, self.d), np.uint16, device) if want_st_ntt else None
-        st_coef = self._out((n, self.d), np.int16, device) if want_st_coef else None
+        wit = self._out((n, self.l, self.d), self.ct, device) if want_wit else None
+        st_ntt = self._out((n, self.d), self.nt, device) if want_st_ntt else None
+        st_coef = self._out((n, self.d), self.ct, device) if want_st_coef else None
         self._ck(self._lib.lcb_adaptor_witgen_batch(self._ctx, byref(sch), _addr(blob), _addr(off), n, _addr(wit),
                                                     _addr(st_ntt), _addr(st_coef)))
         return wit, st_ntt, st_coef
 
     def vec_add(self, a, b, device: bool = False):
-        npoly = _lead(a, 'a', np.int16, self.d)
-        _want(b, 'b', np.int16, tuple(a.shape))
-        out = self._out(tuple(a.shape), np.int16, device)
+        npoly = _lead(a, 'a', self.ct, self.d)
+        _want(b, 'b', self.ct, tuple(a.shape))
+        out = self._out(tuple(a.shape), self.ct, device)
         self._ck(self._lib.lcb_vec_add_batch(self._ctx, _addr(a), _addr(b), npoly, _addr(out)))
         return out
 
     def vec_sub(self, a, b, device: bool = False):
-        npoly = _lead(a, 'a', np.int16, self.d)
-        _want(b, 'b', np.int16, tuple(a.shape))
-        out = self._out(tuple(a.shape), np.int16, device)
+        npoly = _lead(a, 'a', self.ct, self.d)
+        _want(b, 'b', self.ct, tuple(a.shape))
+        out = self._out(tuple(a.shape), self.ct, device)
         self._ck(self._lib.lcb_vec_sub_batch(self._ctx, _addr(a), _addr(b), npoly, _addr(out)))
         return out
 
     def witness_verify(self, wit_coef, st_ntt, bd: int, wt: int, device: bool = False):
         n = int(wit_coef.shape[0])
-        _want(wit_coef, 'wit_coef', np.int16, (n, self.l, self.d))
-        _want(st_ntt, 'st_ntt', np.uint16, (n, self.d))
+        _want(wit_coef, 'wit_coef', self.ct, (n, self.l, self.d))
+        _want(st_ntt, 'st_ntt', self.nt, (n, self.d))
         verdict = self._out((n,), np.uint8, device)
         self._ck(self._lib.lcb_adaptor_witness_verify_batch(self._ctx, _addr(wit_coef), _addr(st_ntt), n, bd, wt,
                                                             _addr(verdict)))

@@ -24,7 +24,11 @@ import numpy as np
 from .engine import Engine
 
 UNIFORM_INFINITY_WEIGHT: str = 'inf,wt,unif'
-D = 256
+
+
+def coef_dtype(lp) -> type:
+    """Element type of engine-format coefficient arrays: int16 for q < 2^16, int32 for wider moduli."""
+    return np.int32 if lp.modulus >= 65536 else np.int16
 
 
 # ------------------------------------------------------------------------------- host-side parameter logic
@@ -140,7 +144,7 @@ class Polynomial(object):
         if _coef is None and _ntt is None:
             if not isinstance(coefs, dict):
                 raise ValueError('Polynomial needs a coefficient dictionary.')
-            dense = np.zeros(lp.degree, dtype=np.int16)
+            dense = np.zeros(lp.degree, dtype=coef_dtype(lp))
             for i, v in coefs.items():
                 if not isinstance(i, int) or not isinstance(v, int) or not 0 <= i < lp.degree or abs(v) > lp.halfmod:
                     raise ValueError('Polynomial coefficient index or magnitude out of range.')
@@ -171,7 +175,7 @@ class Polynomial(object):
         nz = np.flatnonzero(c)
         if nz.size == 0:
             return {}, 0, 0
-        return {int(i): int(c[i]) for i in nz}, int(np.abs(c.astype(np.int32)).max()), int(nz.size)
+        return {int(i): int(c[i]) for i in nz}, int(np.abs(c.astype(np.int64)).max()), int(nz.size)
 
     def __eq__(self, other) -> bool:
         return isinstance(other, Polynomial) and self.lp == other.lp and np.array_equal(self.coef, other.coef)
@@ -193,7 +197,7 @@ class Polynomial(object):
         return self._wrap(engine_for(self.lp).vec_sub(self.coef[None], other.coef[None])[0])
 
     def __neg__(self):
-        zero = np.zeros((1, self.lp.degree), dtype=np.int16)
+        zero = np.zeros((1, self.lp.degree), dtype=coef_dtype(self.lp))
         return self._wrap(engine_for(self.lp).vec_sub(zero, self.coef[None])[0])
 
     def __mul__(self, other):
@@ -222,7 +226,7 @@ class PolynomialVector(object):
             if not isinstance(entries, list) or not all(isinstance(i, Polynomial) and i.lp == lp for i in entries):
                 raise ValueError('PolynomialVector needs a list of Polynomials over the same LatticeParameters.')
             self._entries = entries
-            self._coef = np.stack([e.coef for e in entries]) if entries else np.zeros((0, lp.degree), np.int16)
+            self._coef = np.stack([e.coef for e in entries]) if entries else np.zeros((0, lp.degree), coef_dtype(lp))
 
     @property
     def coef(self) -> np.ndarray:

@@ -49,7 +49,8 @@ def test_no_cpu_fallback():
         Engine(128, 11777, 256, 13)
     assert e.value.status == _ffi.LCB_ERR_NO_DEVICE
     # unsupported parameter sets are rejected before any device work
-    for bad in ((128, 11777, 128, 13), (128, 11779, 256, 13), (128, 65537, 256, 13), (128, 11777, 256, 0)):
+    for bad in ((128, 11777, 16, 13), (128, 11777, 2048, 13), (128, 11777, 96, 13), (128, 11779, 256, 13),
+                (128, 193, 256, 1), (128, 11777, 256, 0), (128, 11777, 256, 65), (0, 11777, 256, 13), (513, 11777, 256, 13)):
         with pytest.raises(LcbError) as e:
             Engine(*bad)
         assert e.value.status == _ffi.LCB_ERR_INVALID

@@ -451,8 +451,8 @@ def test_abi_error_paths():
             with pytest.raises(LcbError) as err:
                 e.hash2polyvec('S', ['x'], bad['bd'], bad['wt'], 1)
             assert err.value.status == _ffi.LCB_ERR_INVALID
-        with pytest.raises(LcbError) as err:            # non-monomial aggregation coefficients are rejected
-            e.agg_coefs(make_scheme(ag_wt=2), 'msg', 0, 4)
+        with pytest.raises(LcbError) as err:            # aggregation weights beyond the degree are rejected
+            e.agg_coefs(make_scheme(ag_wt=257), 'msg', 0, 4)
         assert err.value.status == _ffi.LCB_ERR_INVALID
         with pytest.raises(ValueError):                 # non-contiguous host buffers are refused by the shim
             e.ntt_fwd(np.zeros((4, 2 * D), np.int16)[:, ::2])
