@@ -14,12 +14,16 @@
  *   - calls are asynchronous only when EVERY buffer is device memory; otherwise they return after
  *     the results are in the caller's host buffer.  lcb_synchronize() waits for the stream.
  *
- * Data formats (d = ring degree = 256, l = vector length, q < 2^16 prime, q = 1 mod 2d)
+ * Data formats (d = ring degree, a power of two in 32..1024; l = vector length; q prime, q = 1 mod 2d)
  *   coefficient form : int16_t[d], centred residues in [-(q-1)/2, (q-1)/2], natural order
- *   NTT form         : uint16_t[d], residues in [0, q); slot p holds a(psi^(2*bitrev8(p)+1)),
+ *   NTT form         : uint16_t[d], residues in [0, q); slot p holds a(psi^(2*bitrev_logd(p)+1)),
  *                      psi = least primitive 2d-th root of unity mod q (the reference's `rou`)
  *   pairs            : int16_t[wt][2] = (index, coefficient) in sampler DRAW ORDER
  *   ragged bytes     : uint8_t blob + int64_t off[n+1]; item i is blob[off[i] .. off[i+1])
+ * WIDE contexts (q >= 2^16, up to 2^31): every int16_t / uint16_t array of this header then holds int32_t /
+ * uint32_t elements of the same shape, and the int32_t BKLM partial sums become int64_t; pass the wider arrays
+ * through the same pointers.  The shipped parameter sets (d = 256, q = 11777 / 39937) run on register-resident
+ * half-warp kernels; every other (d, q) runs on one-polynomial-per-warp shared-memory kernels (ring_generic.cu).
  * Caller-owned DEVICE buffers of 16-bit data must be 16-byte aligned (LCB_ERR_CUDA, "misaligned address", otherwise).
  */
 #ifndef LCB200_H
@@ -62,8 +66,9 @@ const char* lcb_last_error(const lcb_ctx* ctx);     /* detail string of the last
 int lcb_version(void);
 
 /* LatticeParameters(modulus=q, degree=d, length=l) + secpar (lattice_algebra; constructed at
- * lm_one_time_sigs.py:19-21).  Supported: d == 256, 3 <= q < 65536 prime with q % 512 == 1,
- * 1 <= l <= 64, 1 <= secpar <= 512.  device = CUDA ordinal. */
+ * lm_one_time_sigs.py:19-21; the reference's container tests use (d, q) = (32, 193), tests/test_one_time_keys.py:12-33).
+ * Supported: d a power of two in 32..1024, 3 <= q < 2^31 prime with q % (2d) == 1, 1 <= l <= 64,
+ * 1 <= secpar <= 512.  device = CUDA ordinal. */
 int lcb_ctx_create(lcb_ctx** out, int device, int secpar, int q, int d, int l);
 int lcb_ctx_destroy(lcb_ctx* ctx);
 int lcb_ctx_set_stream(lcb_ctx* ctx, void* cuda_stream);   /* run on a caller-owned cudaStream_t  */
@@ -126,6 +131,7 @@ int lcb_lm_verify_batch(lcb_ctx* ctx, const lcb_scheme* sch, const uint16_t* vk_
  * value i at bit offset i*bits, least significant bit first: 32*bits bytes per polynomial, polynomials
  * back to back.  Signatures: x = centred coefficient, bias = vf_bd, bits = ceil(log2(2*vf_bd+1)) (11 at
  * secpar 128, 13 at 256).  NTT-form keys: x = slot value, bias = 0, bits = ceil(log2 q) (14 / 16).
+ * Defined for d == 256, q < 2^16 contexts (LCB_ERR_INVALID otherwise).
  * `values` is int16 or uint16 [npoly][d]; packed buffers must be 4-byte aligned (LCB_ERR_INVALID otherwise);
  * lcb_lm_verify_packed_batch reads the shipped widths directly only from 16-byte aligned device buffers and
  * unpacks into scratch first when a caller-owned device buffer is merely 4-byte aligned.
@@ -144,12 +150,14 @@ int lcb_lm_verify_packed_batch(lcb_ctx* ctx, const lcb_scheme* sch, const uint8_
                                int sig_bits, int sig_bias, int64_t n, int bd, int wt, uint8_t* verdict);
 
 /* make_agg_coefs (bklm_one_time_agg_sigs.py:78-81): coefficient i = H2P(ag_salt+str(first+i) || agmsg),
- * wt = ag_wt (1 supported), out_pairs int16[count][ag_wt][2]. */
+ * out_pairs int16[count][ag_wt][2].  ag_wt = ag_bd = 1 (the shipped tables: signed monomials) takes the dedicated
+ * shared-message kernels; any other 1 <= ag_wt <= d, ag_bd >= 1 runs the full sampler per coefficient. */
 int lcb_bklm_agg_coefs(lcb_ctx* ctx, const lcb_scheme* sch, const uint8_t* agmsg, int64_t agmsg_len,
                        int64_t first, int64_t count, int16_t* out_pairs);
 
 /* aggregate (bklm_one_time_agg_sigs.py:92-96), one shard: partial[l][d] (int32, residues mod q,
- * not centred) = sum_i sig_sorted[i] ** ag_i over this shard's `count` signatures whose global
+ * not centred; ag_pairs int16[count][ag_wt][2], general polynomials when ag_wt > 1 or ag_bd > 1)
+ * = sum_i sig_sorted[i] ** ag_i over this shard's `count` signatures whose global
  * sorted positions start at `first`.  ag_pairs from lcb_bklm_agg_coefs (same first/count) or NULL to
  * derive them here from agmsg.  Shards are summed by the caller (NCCL reduce) and finished below. */
 int lcb_bklm_aggregate_partial(lcb_ctx* ctx, const lcb_scheme* sch, const int16_t* sig_sorted,

@@ -1,2 +1,2 @@
 set -x
-python -m pytest tests -q -x -m gpu 2>&1 | tail -12
+python -m pytest tests/test_gpu_wide.py -q -x 2>&1 | tail -30
