@@ -64,6 +64,12 @@ typedef struct lcb_scheme {
 const char* lcb_strerror(int status);
 const char* lcb_last_error(const lcb_ctx* ctx);     /* detail string of the last failure    */
 int lcb_version(void);
+/* 1 for the checked build (make CHECKED=1: device-side asserts on every hand-rolled bound of a global access - the
+ * stand-in for compute-sanitizer's memcheck, which is not available on the GPU pool), 0 for the production build.
+ * lcb_checked_selftest launches a kernel whose check fails on purpose: LCB_OK on the production build, LCB_ERR_CUDA
+ * ("device-side assert triggered", the context is unusable afterwards) on the checked one - proof that checks are live. */
+int lcb_build_is_checked(void);
+int lcb_checked_selftest(lcb_ctx* ctx);
 
 /* LatticeParameters(modulus=q, degree=d, length=l) + secpar (lattice_algebra; constructed at
  * lm_one_time_sigs.py:19-21; the reference's container tests use (d, q) = (32, 193), tests/test_one_time_keys.py:12-33).
@@ -82,6 +88,13 @@ int lcb_set_key_ch(lcb_ctx* ctx, const int16_t* key_ch_coef);
 /* hashlib.shake_256(item).digest(out_len) per item (lattice_algebra binary_digest without salt). */
 int lcb_shake256_batch(lcb_ctx* ctx, const uint8_t* in, const int64_t* in_off, int64_t n,
                        uint8_t* out, int64_t out_len);
+
+/* The unseeded keygen path for batches (make_random_seed, lm_one_time_sigs.py:58-61, draws secpar random bits per
+ * key from the OS): ONE 32-byte secret from the host's entropy source is expanded on the device into n seed
+ * bitstrings, seed i = the first secpar bits (most significant bit of each byte first) of
+ * SHAKE256(secret32 || le64(first + i)) as ASCII '0'/'1' - exactly the strings keygen hashes, so seed i reproduces
+ * key i.  seeds: uint8[n][secpar] (host or device); feed it to lcb_lm_keygen_batch with seed_off[i] = i * secpar. */
+int lcb_expand_seeds(lcb_ctx* ctx, const uint8_t* secret32, int64_t first, int64_t n, uint8_t* seeds);
 
 /* hash2polynomialvector / hash2polynomial (lm_one_time_sigs.py:70-91,142-160;
  * adaptor_sigs.py:86-96): SHAKE256(salt || item_i) -> vec_len polynomials with `wt` distinct

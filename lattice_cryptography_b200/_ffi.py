@@ -45,6 +45,8 @@ PROTOTYPES = {
     'lcb_strerror': (c_char_p, [c_int]),
     'lcb_last_error': (c_char_p, [c_void_p]),
     'lcb_version': (c_int, []),
+    'lcb_build_is_checked': (c_int, []),
+    'lcb_checked_selftest': (c_int, [c_void_p]),
     'lcb_ctx_create': (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int]),
     'lcb_ctx_destroy': (c_int, [c_void_p]),
     'lcb_ctx_set_stream': (c_int, [c_void_p, c_void_p]),
@@ -52,6 +54,7 @@ PROTOTYPES = {
     'lcb_ctx_root_of_unity': (c_int, [c_void_p]),
     'lcb_set_key_ch': (c_int, [c_void_p, _P]),
     'lcb_shake256_batch': (c_int, [c_void_p, _P, _P, c_int64, _P, c_int64]),
+    'lcb_expand_seeds': (c_int, [c_void_p, _P, c_int64, c_int64, _P]),
     'lcb_hash2polyvec_batch': (c_int, [c_void_p, c_char_p, _P, _P, c_int64, c_int, c_int, c_int, _P, _P]),
     'lcb_ntt_fwd_batch': (c_int, [c_void_p, _P, c_int64, _P]),
     'lcb_ntt_inv_batch': (c_int, [c_void_p, _P, c_int64, _P]),

@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/lcb200.h"
 #include "engine.h"
 
@@ -42,6 +44,14 @@ struct lcb_ctx {
 };
 
 namespace {
+
+// NVTX range over one ABI entry point: shows up as a named span on the CPU timeline of nsys /
+// ncu; header-only NVTX3 resolves to no-ops when no profiler is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+#define LCB_RANGE() NvtxRange nvtx_range_(__func__)
 
 thread_local std::string g_create_error;
 
@@ -401,9 +411,31 @@ const char* lcb_strerror(int status) {
 
 const char* lcb_last_error(const lcb_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_create_error.c_str(); }
 
-int lcb_version(void) { return 100; }
+int lcb_version(void) { return 200; }
+
+int lcb_build_is_checked(void) {
+#ifdef LCB_CHECKED
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+namespace {
+__global__ void k_check_selftest(int fail) { LCB_CHECK(!fail); }
+}  // namespace
+
+int lcb_checked_selftest(lcb_ctx* c) {
+    if (!c) return LCB_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    k_check_selftest<<<1, 1, 0, c->stream>>>(1);
+    CK(c, cudaGetLastError());
+    CK(c, cudaStreamSynchronize(c->stream));
+    return LCB_OK;
+}
 
 int lcb_ctx_create(lcb_ctx** out, int device, int secpar, int q, int d, int l) {
+    LCB_RANGE();
     if (!out) return LCB_ERR_INVALID;
     *out = nullptr;
     g_create_error.clear();
@@ -646,6 +678,7 @@ int lcb_profile_read(lcb_ctx* c, const char* kernel, double* total_ms, int64_t* 
 }
 
 int lcb_set_key_ch(lcb_ctx* c, const int16_t* key_ch_coef) {
+    LCB_RANGE();
     if (!c || !key_ch_coef) return LCB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     Staging sg(c);
@@ -675,6 +708,7 @@ int lcb_set_key_ch(lcb_ctx* c, const int16_t* key_ch_coef) {
 
 int lcb_shake256_batch(lcb_ctx* c, const uint8_t* in, const int64_t* in_off, int64_t n, uint8_t* out,
                        int64_t out_len) {
+    LCB_RANGE();
     if (!c || !in_off || !out || n < 0 || out_len < 0) return LCB_ERR_INVALID;
     if (n == 0 || out_len == 0) return LCB_OK;
     CK(c, cudaSetDevice(c->device));
@@ -692,8 +726,27 @@ int lcb_shake256_batch(lcb_ctx* c, const uint8_t* in, const int64_t* in_off, int
     return LCB_OK;
 }
 
+int lcb_expand_seeds(lcb_ctx* c, const uint8_t* secret32, int64_t first, int64_t n, uint8_t* seeds) {
+    LCB_RANGE();
+    if (!c || !secret32 || !seeds || n < 0 || first < 0) return LCB_ERR_INVALID;
+    if (c->secpar > 512 || (c->secpar & 7)) return fail(c, LCB_ERR_INVALID, "seed expansion needs secpar to be a multiple of 8, at most 512");
+    if (n == 0) return LCB_OK;
+    CK(c, cudaSetDevice(c->device));
+    Staging sg(c);
+    uint8_t* d_secret;
+    uint8_t* d_out;
+    CK(c, sg.alloc((void**)&d_secret, 32, true));           // engine-owned aligned copy, cleared afterwards
+    CK(c, cudaMemcpyAsync(d_secret, secret32, 32, cudaMemcpyDefault, c->stream));
+    CK(c, sg.out(&d_out, seeds, (size_t)n * c->secpar, true));
+    CK(c, timed(c, K_SHAKE, [&] { return launch_seed_expand(d_secret, first, n, c->secpar, d_out, c->stream); }));
+    CK(c, sg.finish());
+    if (!on_device(secret32)) CK(c, cudaStreamSynchronize(c->stream));     // the caller may wipe its copy on return
+    return LCB_OK;
+}
+
 int lcb_hash2polyvec_batch(lcb_ctx* c, const char* salt, const uint8_t* msgs, const int64_t* msg_off, int64_t n,
                            int bd, int wt, int vec_len, int16_t* out_dense, int16_t* out_pairs) {
+    LCB_RANGE();
     if (!c || !msg_off || n < 0) return LCB_ERR_INVALID;
     if (n == 0) return LCB_OK;
     CK(c, cudaSetDevice(c->device));
@@ -718,6 +771,7 @@ int lcb_hash2polyvec_batch(lcb_ctx* c, const char* salt, const uint8_t* msgs, co
 }
 
 int lcb_ntt_fwd_batch(lcb_ctx* c, const int16_t* coef, int64_t npoly, uint16_t* ntt) {
+    LCB_RANGE();
     if (!c || !coef || !ntt || npoly < 0) return LCB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     Staging sg(c);
@@ -733,6 +787,7 @@ int lcb_ntt_fwd_batch(lcb_ctx* c, const int16_t* coef, int64_t npoly, uint16_t* 
 }
 
 int lcb_ntt_reference_repr_batch(lcb_ctx* c, const int16_t* coef, int64_t npoly, int16_t* rep) {
+    LCB_RANGE();
     if (!c || !coef || !rep || npoly < 0) return LCB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     Staging sg(c);
@@ -748,6 +803,7 @@ int lcb_ntt_reference_repr_batch(lcb_ctx* c, const int16_t* coef, int64_t npoly,
 }
 
 int lcb_ntt_inv_batch(lcb_ctx* c, const uint16_t* ntt, int64_t npoly, int16_t* coef) {
+    LCB_RANGE();
     if (!c || !coef || !ntt || npoly < 0) return LCB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     Staging sg(c);
@@ -763,6 +819,7 @@ int lcb_ntt_inv_batch(lcb_ctx* c, const uint16_t* ntt, int64_t npoly, int16_t* c
 }
 
 int lcb_poly_mul_batch(lcb_ctx* c, const int16_t* a, const int16_t* b, int64_t npoly, int16_t* out) {
+    LCB_RANGE();
     if (!c || !a || !b || !out || npoly < 0) return LCB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     Staging sg(c);
@@ -780,6 +837,7 @@ int lcb_poly_mul_batch(lcb_ctx* c, const int16_t* a, const int16_t* b, int64_t n
 
 int lcb_lm_keygen_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* seeds, const int64_t* seed_off, int64_t n,
                         int16_t* sk_coef, uint16_t* sk_ntt, uint16_t* vk_ntt, int16_t* vk_coef) {
+    LCB_RANGE();
     if (!c || !sch || !seed_off || n < 0) return LCB_ERR_INVALID;
     if (!c->has_key_ch) return fail(c, LCB_ERR_NO_KEY_CH, "lcb_lm_keygen_batch before lcb_set_key_ch");
     if (n == 0) return LCB_OK;
@@ -846,6 +904,7 @@ int lcb_lm_keygen_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* seeds,
 
 int lcb_challenge_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* chmsg, const int64_t* chmsg_off, int64_t n,
                         int16_t* out_pairs) {
+    LCB_RANGE();
     if (!c || !sch || !chmsg_off || !out_pairs || n < 0) return LCB_ERR_INVALID;
     if (n == 0) return LCB_OK;
     CK(c, cudaSetDevice(c->device));
@@ -866,6 +925,7 @@ int lcb_challenge_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* chmsg,
 
 int lcb_lm_sign_batch(lcb_ctx* c, const lcb_scheme* sch, const uint16_t* sk_ntt, const uint8_t* chmsg,
                       const int64_t* chmsg_off, int64_t n, int16_t* sig) {
+    LCB_RANGE();
     if (!c || !sch || !sk_ntt || !chmsg_off || !sig || n < 0) return LCB_ERR_INVALID;
     if (n == 0) return LCB_OK;
     CK(c, cudaSetDevice(c->device));
@@ -896,6 +956,7 @@ int lcb_lm_sign_batch(lcb_ctx* c, const lcb_scheme* sch, const uint16_t* sk_ntt,
 int lcb_lm_verify_batch(lcb_ctx* c, const lcb_scheme* sch, const uint16_t* vk_ntt, const uint8_t* chmsg,
                         const int64_t* chmsg_off, const int16_t* sig, const uint16_t* st_ntt, int64_t n, int bd,
                         int wt, uint8_t* verdict) {
+    LCB_RANGE();
     if (!c || !sch || !vk_ntt || !chmsg_off || !sig || !verdict || n < 0 || bd < 0 || wt < 0) return LCB_ERR_INVALID;
     if (!c->has_key_ch) return fail(c, LCB_ERR_NO_KEY_CH, "lcb_lm_verify_batch before lcb_set_key_ch");
     if (n == 0) return LCB_OK;
@@ -956,6 +1017,7 @@ int lcb_lm_verify_batch(lcb_ctx* c, const lcb_scheme* sch, const uint16_t* vk_nt
 // ---- wire format ----------------------------------------------------------------------
 int lcb_pack_batch(lcb_ctx* c, const void* values, int64_t npoly, int bits, int bias, uint8_t* packed,
                    uint8_t* in_range) {
+    LCB_RANGE();
     if (!c || !values || !packed || npoly < 0 || bits < 1 || bits > 16 || bias < 0 || bias > 65535) return LCB_ERR_INVALID;
     if (c->generic) return fail(c, LCB_ERR_INVALID, "the packed wire format is defined for d == 256, q < 2^16 contexts only");
     if (npoly == 0) return LCB_OK;
@@ -973,6 +1035,7 @@ int lcb_pack_batch(lcb_ctx* c, const void* values, int64_t npoly, int bits, int 
 }
 
 int lcb_unpack_batch(lcb_ctx* c, const uint8_t* packed, int64_t npoly, int bits, int bias, void* values) {
+    LCB_RANGE();
     if (!c || !values || !packed || npoly < 0 || bits < 1 || bits > 16 || bias < 0 || bias > 65535) return LCB_ERR_INVALID;
     if (c->generic) return fail(c, LCB_ERR_INVALID, "the packed wire format is defined for d == 256, q < 2^16 contexts only");
     if (npoly == 0) return LCB_OK;
@@ -994,6 +1057,7 @@ int lcb_unpack_batch(lcb_ctx* c, const uint8_t* packed, int64_t npoly, int bits,
 int lcb_lm_verify_packed_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* vk_packed, int vk_bits,
                                const uint8_t* chmsg, const int64_t* chmsg_off, const uint8_t* sig_packed, int sig_bits,
                                int sig_bias, int64_t n, int bd, int wt, uint8_t* verdict) {
+    LCB_RANGE();
     if (!c || !sch || !vk_packed || !chmsg_off || !sig_packed || !verdict || n < 0 || bd < 0 || wt < 0 ||
         vk_bits < 1 || vk_bits > 16 || sig_bits < 1 || sig_bits > 16 || sig_bias < 0 || sig_bias > 32767)
         return LCB_ERR_INVALID;
@@ -1079,6 +1143,7 @@ int lcb_lm_verify_packed_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t*
 
 int lcb_bklm_agg_coefs(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* agmsg, int64_t agmsg_len, int64_t first,
                        int64_t count, int16_t* out_pairs) {
+    LCB_RANGE();
     if (!c || !sch || !agmsg || !out_pairs || agmsg_len < 0 || first < 0 || count < 0) return LCB_ERR_INVALID;
     if (count == 0) return LCB_OK;
     CK(c, cudaSetDevice(c->device));
@@ -1096,6 +1161,7 @@ int lcb_bklm_agg_coefs(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* agmsg, 
 int lcb_bklm_aggregate_partial(lcb_ctx* c, const lcb_scheme* sch, const int16_t* sig_sorted, const int16_t* ag_pairs,
                                const uint8_t* agmsg, int64_t agmsg_len, int64_t first, int64_t count,
                                int32_t* partial) {
+    LCB_RANGE();
     if (!c || !sch || !partial || count < 0 || (count > 0 && !sig_sorted) || (!ag_pairs && !agmsg)) return LCB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     const int l = c->l;
@@ -1131,6 +1197,7 @@ int lcb_bklm_aggregate_partial(lcb_ctx* c, const lcb_scheme* sch, const int16_t*
 }
 
 int lcb_bklm_aggregate_finish(lcb_ctx* c, const int32_t* partial_sum, int16_t* ag_sig) {
+    LCB_RANGE();
     if (!c || !partial_sum || !ag_sig) return LCB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     Staging sg(c);
@@ -1149,6 +1216,7 @@ int lcb_bklm_aggverify_partial(lcb_ctx* c, const lcb_scheme* sch, const uint16_t
                                const uint8_t* chmsg_sorted, const int64_t* chmsg_off, const int16_t* ag_pairs,
                                const uint8_t* agmsg, int64_t agmsg_len, int64_t first, int64_t count,
                                int32_t* partial) {
+    LCB_RANGE();
     if (!c || !sch || !partial || count < 0 || (count > 0 && (!vk_ntt_sorted || !chmsg_off)) || (!ag_pairs && !agmsg))
         return LCB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
@@ -1195,6 +1263,7 @@ int lcb_bklm_aggverify_partial(lcb_ctx* c, const lcb_scheme* sch, const uint16_t
 
 int lcb_bklm_aggverify_finish(lcb_ctx* c, const int32_t* partial_sum, const int16_t* ag_sig, int64_t total, int ag_cap,
                               int avf_bd, int avf_wt, uint8_t* verdict) {
+    LCB_RANGE();
     if (!c || !partial_sum || !ag_sig || !verdict) return LCB_ERR_INVALID;
     if (!c->has_key_ch) return fail(c, LCB_ERR_NO_KEY_CH, "lcb_bklm_aggverify_finish before lcb_set_key_ch");
     CK(c, cudaSetDevice(c->device));
@@ -1215,6 +1284,7 @@ int lcb_bklm_aggverify_finish(lcb_ctx* c, const int32_t* partial_sum, const int1
 
 int lcb_adaptor_witgen_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* seeds, const int64_t* seed_off,
                              int64_t n, int16_t* wit_coef, uint16_t* st_ntt, int16_t* st_coef) {
+    LCB_RANGE();
     if (!c || !sch || !seed_off || n < 0) return LCB_ERR_INVALID;
     if (!c->has_key_ch) return fail(c, LCB_ERR_NO_KEY_CH, "lcb_adaptor_witgen_batch before lcb_set_key_ch");
     if (n == 0) return LCB_OK;
@@ -1250,6 +1320,7 @@ int lcb_adaptor_witgen_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* s
 }
 
 static int vec_addsub(lcb_ctx* c, const int16_t* a, const int16_t* b, int64_t npoly, int sub, int16_t* out) {
+    NvtxRange nvtx_range_(sub ? "lcb_vec_sub_batch" : "lcb_vec_add_batch");
     if (!c || !a || !b || !out || npoly < 0) return LCB_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     Staging sg(c);
@@ -1276,6 +1347,7 @@ int lcb_vec_sub_batch(lcb_ctx* c, const int16_t* a, const int16_t* b, int64_t np
 
 int lcb_adaptor_witness_verify_batch(lcb_ctx* c, const int16_t* wit_coef, const uint16_t* st_ntt, int64_t n, int bd,
                                      int wt, uint8_t* verdict) {
+    LCB_RANGE();
     if (!c || !wit_coef || !st_ntt || !verdict || n < 0 || bd < 0 || wt < 0) return LCB_ERR_INVALID;
     if (!c->has_key_ch) return fail(c, LCB_ERR_NO_KEY_CH, "lcb_adaptor_witness_verify_batch before lcb_set_key_ch");
     if (n == 0) return LCB_OK;

@@ -45,6 +45,7 @@ struct SamplerArgs {
 };
 
 cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st);
+cudaError_t launch_seed_expand(const uint8_t* secret, int64_t first, int64_t n, int secpar, uint8_t* out, cudaStream_t st);
 cudaError_t launch_index_salts(const SamplerArgs& a, uint8_t* salts, int32_t* lens, cudaStream_t st);
 inline int64_t sampler_stride(int64_t n) { return (n + 127) / 128 * 128; }
 // parked indices: one byte each for d = 256, two bytes on the generic path

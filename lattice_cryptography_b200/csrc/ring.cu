@@ -298,9 +298,13 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 constexpr int VERIFY_BLOCKS = 4;     // resident blocks per SM k_verify is compiled for
 
-__device__ __forceinline__ void load_u16x16_smem(uint32_t (&r)[EPT], const unsigned char* p) {
-    const uint4* v = reinterpret_cast<const uint4*>(p);
-    const uint4 a = v[0], b = v[1];
+// 16 slots of one lane from a staged 512-byte row.  The row is staged SPLIT: the first 16 bytes of every lane's 32
+// (256 bytes), then the second 16 bytes of every lane - so that the eight lanes of a quarter-warp read 128
+// contiguous bytes per 128-bit load.  (Staged as it lies in HBM, lane t at byte 32 t, lanes t and t + 4 share their
+// banks: a 2-way conflict on every load, 27 % of k_sign's shared wavefronts in round 1.)
+__device__ __forceinline__ void load_u16x16_smem(uint32_t (&r)[EPT], const unsigned char* row, int lane) {
+    const uint4 a = *reinterpret_cast<const uint4*>(row + 16 * lane);
+    const uint4 b = *reinterpret_cast<const uint4*>(row + D + 16 * lane);
     const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int i = 0; i < 8; ++i) { r[2 * i] = w[i] & 0xFFFFu; r[2 * i + 1] = w[i] >> 16; }
@@ -331,11 +335,11 @@ __global__ void __launch_bounds__(RBS) k_sign(ModQ m, StageConst sc, const NttTa
             it_item = it_item < n ? it_item : n - 1;
             const unsigned char* left = reinterpret_cast<const unsigned char*>(sk_ntt + (it_item * 2 * l + pf_i) * D) + 32 * h.lane;
             const unsigned char* right = left + (int64_t)l * D * 2;
-            unsigned char* dst = stage + pf_buf * (2 * D * 2) + 32 * h.lane;
+            unsigned char* dst = stage + pf_buf * (2 * D * 2) + 16 * h.lane;      // split layout, see load_u16x16_smem
             cp_async16(dst, left);
-            cp_async16(dst + 16, left + 16);
+            cp_async16(dst + D, left + 16);
             cp_async16(dst + D * 2, right);
-            cp_async16(dst + D * 2 + 16, right + 16);
+            cp_async16(dst + D * 2 + D, right + 16);
             if (++pf_i == l) { pf_i = 0; ++pf_it; }
             pf_buf ^= 1u;
         }
@@ -361,9 +365,9 @@ __global__ void __launch_bounds__(RBS) k_sign(ModQ m, StageConst sc, const NttTa
             cp_async_wait<1>();
             __syncwarp();
             uint32_t a[EPT], b[EPT];
-            const unsigned char* rows = stage + cur * (2 * D * 2) + 32 * h.lane;
-            load_u16x16_smem(a, rows);
-            load_u16x16_smem(b, rows + D * 2);
+            const unsigned char* rows = stage + cur * (2 * D * 2);
+            load_u16x16_smem(a, rows, h.lane);
+            load_u16x16_smem(b, rows + D * 2, h.lane);
             __syncwarp();
             issue();                            // refill the buffer just drained with row pair (+2)
             cur ^= 1u;
@@ -445,6 +449,7 @@ __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageCons
             int64_t it_item = first + pf_it * stride + h.slot;
             it_item = it_item < n ? it_item : n - 1;
             const unsigned char* src = reinterpret_cast<const unsigned char*>(vec_coef) + (it_item * l + pf_i) * ROW_BYTES;
+            LCB_CHECK(it_item >= 0 && it_item < n && pf_i < l);          // the staged row is a row of the batch
             unsigned char* dst = stage + pf_buf * (D * 2);
 #pragma unroll
             for (int o = 0; o < ROW_BYTES; o += 16 * LANES)

@@ -63,6 +63,38 @@ __global__ void __launch_bounds__(SBS) k_shake256(const uint8_t* __restrict__ in
 }
 
 // ------------------------------------------------------------------------------------------------
+// Device-side expansion of host entropy into seed bitstrings (the unseeded keygen path, make_random_seed at
+// lm_one_time_sigs.py:58-61, for batches): seed i = the first `secpar` bits, most significant bit of each byte first,
+// of SHAKE256(secret[0..32) || le64(first + i)), written as the ASCII '0'/'1' string the reference hashes.
+// One thread per seed; the 40-byte input and the <= 64-byte output each fit one rate block.
+__global__ void __launch_bounds__(128) k_seed_expand(const uint8_t* __restrict__ secret, int64_t first, int64_t n, int secpar,
+                                                     uint8_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    KeccakState s;
+#pragma unroll
+    for (int k = 0; k < 25; ++k) { s.lo[k] = 0; s.hi[k] = 0; }
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(secret);       // engine-owned, 4-byte aligned copy
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { s.lo[k] = __ldg(sw + 2 * k); s.hi[k] = __ldg(sw + 2 * k + 1); }
+    const uint64_t ctr = (uint64_t)(first + i);
+    s.lo[4] = (uint32_t)ctr;
+    s.hi[4] = (uint32_t)(ctr >> 32);
+    s.lo[5] ^= 0x1Fu;                  // SHAKE domain separation + first pad bit at byte 40
+    s.hi[16] ^= 0x80000000u;           // last pad bit at byte 135
+    keccak_f1600(s, c_keccak_rc);
+    uint8_t* o = out + i * secpar;
+    for (int b = 0; b < secpar; ++b) {
+        const int byte = b >> 3, word = byte >> 3, sh = 8 * (byte & 7) + (7 - (b & 7));
+        uint32_t w = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k == word) w = sh < 32 ? s.lo[k] >> sh : s.hi[k] >> (sh - 32);
+        o[b] = (uint8_t)('0' + (w & 1u));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Fused SHAKE256 squeeze + decode2polycoefs (sampler_device.cuh), one stream per thread.
 // Shared memory per block: ring [54][P] u32, bmap [8][P] u32, two modulus tables, the piece-weight table.
 template <int P>   // streams (threads) per block; compile-time so that column addressing is shifts, not multiplies
@@ -223,6 +255,13 @@ __global__ void __launch_bounds__(ABS) k_agg_coefs(SamplerArgs a) {
             const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
             const uint32_t* w = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
             const unsigned sh = (unsigned)(addr & 3) * 8;
+#ifdef LCB_CHECKED
+            {   // the 34 or 35 aligned words of this block lie inside the (word-rounded) message
+                const uintptr_t lo_ok = reinterpret_cast<uintptr_t>(msg) & ~(uintptr_t)3;
+                const uintptr_t hi_ok = (reinterpret_cast<uintptr_t>(msg) + (uintptr_t)a.shared_len + 3) & ~(uintptr_t)3;
+                LCB_CHECK(reinterpret_cast<uintptr_t>(w) >= lo_ok && reinterpret_cast<uintptr_t>(w + 34 + (sh ? 1 : 0)) <= hi_ok);
+            }
+#endif
             uint32_t prev = __ldg(w);
 #pragma unroll
             for (int i = 0; i < 17; ++i) {
@@ -407,6 +446,12 @@ cudaError_t launch_shake256(const uint8_t* in, const int64_t* off, int64_t n, ui
     if (n <= 0) return cudaSuccess;
     int64_t blocks = (n + SBS - 1) / SBS;
     k_shake256<<<(unsigned)blocks, SBS, 0, st>>>(in, off, n, out, out_len);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_seed_expand(const uint8_t* secret, int64_t first, int64_t n, int secpar, uint8_t* out, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    k_seed_expand<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(secret, first, n, secpar, out);
     return cudaGetLastError();
 }
 

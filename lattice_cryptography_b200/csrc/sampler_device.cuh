@@ -66,6 +66,14 @@ struct InputView {
         const int64_t end = (int64_t)(reinterpret_cast<uintptr_t>(msg) + (uintptr_t)msg_len + 3 - reinterpret_cast<uintptr_t>(aw)) >> 2;
         const int j_lo = (int)(first < 0 ? 0 : (first > RATE_WORDS + 1 ? RATE_WORDS + 1 : first));
         const int j_hi = msg_len > 0 ? (int)(end < 0 ? 0 : (end > RATE_WORDS + 1 ? RATE_WORDS + 1 : end)) : 0;
+#ifdef LCB_CHECKED
+        // every aligned word this block may read lies inside [msg & ~3, (msg + msg_len + 3) & ~3)
+        if (j_hi > j_lo) {
+            const uintptr_t lo_ok = reinterpret_cast<uintptr_t>(msg) & ~(uintptr_t)3;
+            const uintptr_t hi_ok = (reinterpret_cast<uintptr_t>(msg) + (uintptr_t)msg_len + 3) & ~(uintptr_t)3;
+            LCB_CHECK(reinterpret_cast<uintptr_t>(aw + j_lo) >= lo_ok && reinterpret_cast<uintptr_t>(aw + j_hi) <= hi_ok);
+        }
+#endif
         uint32_t prev = (0 >= j_lo && 0 < j_hi) ? __ldg(aw) : 0u;
 #pragma unroll
         for (int w = 0; w < RATE_WORDS; ++w) {
@@ -322,6 +330,7 @@ __device__ __forceinline__ void sample_stream_t(const Geo& geo, const DecodePara
                     cnt = wd & 1u;              if (k >= cnt) { pos += 1; }
                 }
                 sc.bmap[selw * P] = word & ~(1u << pos);
+                LCB_CHECK(selw * 32 + pos < (uint32_t)geo.d() && ((word >> pos) & 1u));     // an unused position of the ring
                 sc.idxs[f * sc.idx_stride] = (IdxT)(selw * 32 + pos);
             } else if (is_coef) {
                 // ---- one coefficient

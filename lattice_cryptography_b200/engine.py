@@ -223,6 +223,21 @@ class Engine(object):
         self._ck(self._lib.lcb_shake256_batch(self._ctx, _addr(blob), _addr(off), n, _addr(out), out_len))
         return out
 
+    def expand_seeds(self, secret32: bytes, n: int, first: int = 0, device: bool = False):
+        """n seed bitstrings (uint8[n, secpar], ASCII '0'/'1') from ONE 32-byte secret: seed i = first secpar bits of
+        SHAKE256(secret32 || le64(first + i)) (include/lcb200.h, lcb_expand_seeds).  -> (blob, offsets) as keygen takes."""
+        if not isinstance(secret32, (bytes, bytearray)) or len(secret32) != 32:
+            raise ValueError('secret32 must be 32 bytes')
+        sec = np.frombuffer(bytes(secret32), dtype=np.uint8).copy()
+        out = self._out((n, self.secpar), np.uint8, device)
+        self._ck(self._lib.lcb_expand_seeds(self._ctx, _addr(sec), first, n, _addr(out)))
+        sec[:] = 0
+        if device:
+            import torch
+            off = torch.arange(n + 1, dtype=torch.int64, device=out.device) * self.secpar
+            return out.view(-1), off
+        return out.reshape(-1), np.arange(n + 1, dtype=np.int64) * self.secpar
+
     def hash2polyvec(self, salt: str, msgs, bd: int, wt: int, vec_len: int, want_dense: bool = True,
                      want_pairs: bool = False, device: bool = False):
         blob, off = self._rag(msgs)

@@ -84,15 +84,15 @@ def keygen_batch(pp: PublicParameters, seeds: Sequence[Any], want_coef: bool = T
     return {'sk_ntt': sk_ntt, 'vk_ntt': vk_ntt, 'sk_coef': sk_coef, 'vk_coef': vk_coef}
 
 
-def random_seed_batch(pp: PublicParameters, n: int):
-    """The unseeded keygen path (make_random_seed, reference lm_one_time_sigs.py:58-61) for a batch: n fresh
-    secpar-bit seeds from the OS entropy source (`secrets`), as the ASCII bitstrings the reference hashes, in
-    the (blob, offsets) form keygen_batch takes.  Row i of blob.reshape(n, secpar) is seed i."""
+def random_seed_batch(pp: PublicParameters, n: int, device: bool = False, secret: Optional[bytes] = None):
+    """The unseeded keygen path (make_random_seed, reference lm_one_time_sigs.py:58-61) for a batch: ONE fresh 32-byte
+    secret from the OS entropy source (`secrets`) is expanded on the GPU (SHAKE256 in counter mode, lcb_expand_seeds)
+    into n secpar-bit seeds, as the ASCII bitstrings the reference hashes, in the (blob, offsets) form keygen_batch
+    takes.  Row i of blob.reshape(n, secpar) is seed i: it reproduces key i through the seeded path.  `secret`
+    (32 bytes) makes the batch reproducible; by default nobody ever sees it."""
     from secrets import token_bytes
-    secpar = pp['scheme_parameters'].secpar
-    raw = np.frombuffer(token_bytes(n * secpar // 8), dtype=np.uint8)
-    blob = (np.unpackbits(raw) + ord('0')).astype(np.uint8)
-    return blob, np.arange(n + 1, dtype=np.int64) * secpar
+    eng, _ = _ctx(pp)
+    return eng.expand_seeds(secret if secret is not None else token_bytes(32), n, device=device)
 
 
 def sign_batch(pp: PublicParameters, sk_ntt, chmsgs, device: bool = False):

@@ -55,18 +55,6 @@ def test_key_objects_pickle_and_index():
     assert ' object at 0x' in str(vk)
 
 
-def test_random_seed_batch_shape_and_alphabet():
-    from lattice_cryptography_b200 import lm_one_time_sigs as lm
-
-    class _SP:
-        secpar = 256
-    blob, off = lm.random_seed_batch({'scheme_parameters': _SP()}, 1000)
-    assert blob.dtype == np.uint8 and blob.shape == (256000,) and set(np.unique(blob)) <= {48, 49}
-    assert off.dtype == np.int64 and off[0] == 0 and off[-1] == 256000 and (np.diff(off) == 256).all()
-    rows = blob.reshape(1000, 256)
-    assert len({bytes(r) for r in rows}) == 1000 and 0.45 < (rows == 49).mean() < 0.55
-
-
 def test_wire_widths_and_ragged_helpers():
     """Host-only arithmetic of the wire format (bits per coefficient / slot) and of the ragged-blob helper."""
     from lattice_cryptography_b200 import ragged, wire
