@@ -199,6 +199,40 @@ int lcb_vec_sub_batch(lcb_ctx* ctx, const int16_t* a, const int16_t* b, int64_t 
 int lcb_adaptor_witness_verify_batch(lcb_ctx* ctx, const int16_t* wit_coef, const uint16_t* st_ntt, int64_t n,
                                      int bd, int wt, uint8_t* verdict);
 
+/* ---- Multi-device context: ONE call shards a HOST-resident batch over several GPUs of the box.
+ * devices[] lists CUDA ordinals (an ordinal may repeat: two contexts on one GPU).  Independent units (keygen, sign,
+ * verify) are split into contiguous ranges by the reference's distribute_tasks rule (lm_one_time_sigs.py:194-215: the
+ * first n % ndev shards are one longer), one host thread per device, no data-path communication.  BKLM aggregate /
+ * aggregate_verify (bklm_one_time_agg_sigs.py:92-116) shard the SORTED list; the per-device int32 partial sums are
+ * gathered on device 0 by peer copies (NVLink where peer access exists), added by a kernel and finished there - the
+ * exchange step that lattice_cryptography_b200/distributed.py performs with one NCCL reduce when there is one
+ * process per GPU.  Every data pointer of these calls must be HOST memory; device-resident work goes through the
+ * per-device contexts (lcb_mctx_ctx).  Arguments are those of the single-device calls. */
+typedef struct lcb_mctx lcb_mctx;
+int lcb_mctx_create(lcb_mctx** out, const int* devices, int ndev, int secpar, int q, int d, int l);
+int lcb_mctx_destroy(lcb_mctx* m);
+int lcb_mctx_ndev(const lcb_mctx* m);
+lcb_ctx* lcb_mctx_ctx(lcb_mctx* m, int i);
+const char* lcb_mctx_last_error(const lcb_mctx* m);
+int lcb_mctx_set_key_ch(lcb_mctx* m, const int16_t* key_ch_coef);
+int lcb_mctx_lm_keygen_batch(lcb_mctx* m, const lcb_scheme* sch, const uint8_t* seeds, const int64_t* seed_off, int64_t n,
+                             int16_t* sk_coef, uint16_t* sk_ntt, uint16_t* vk_ntt, int16_t* vk_coef);
+int lcb_mctx_lm_sign_batch(lcb_mctx* m, const lcb_scheme* sch, const uint16_t* sk_ntt, const uint8_t* chmsg,
+                           const int64_t* chmsg_off, int64_t n, int16_t* sig);
+int lcb_mctx_lm_verify_batch(lcb_mctx* m, const lcb_scheme* sch, const uint16_t* vk_ntt, const uint8_t* chmsg,
+                             const int64_t* chmsg_off, const int16_t* sig, const uint16_t* st_ntt, int64_t n, int bd,
+                             int wt, uint8_t* verdict);
+int lcb_mctx_lm_verify_packed_batch(lcb_mctx* m, const lcb_scheme* sch, const uint8_t* vk_packed, int vk_bits,
+                                    const uint8_t* chmsg, const int64_t* chmsg_off, const uint8_t* sig_packed,
+                                    int sig_bits, int sig_bias, int64_t n, int bd, int wt, uint8_t* verdict);
+/* whole aggregate / aggregate_verify in one call: coefficient derivation, sharded sums, device-side reduce, finish */
+int lcb_mctx_bklm_aggregate(lcb_mctx* m, const lcb_scheme* sch, const int16_t* sig_sorted, const uint8_t* agmsg,
+                            int64_t agmsg_len, int64_t n, int16_t* ag_sig);
+int lcb_mctx_bklm_aggregate_verify(lcb_mctx* m, const lcb_scheme* sch, const uint16_t* vk_ntt_sorted,
+                                   const uint8_t* chmsg_sorted, const int64_t* chmsg_off, const uint8_t* agmsg,
+                                   int64_t agmsg_len, int64_t n, const int16_t* ag_sig, int ag_cap, int avf_bd,
+                                   int avf_wt, uint8_t* verdict);
+
 /* Instrumentation: kernels launched by this ctx since creation (bench.py's gpu_launches). */
 int64_t lcb_launch_count(const lcb_ctx* ctx);
 /* Optional per-kernel timing with CUDA events on the ctx stream (what bench.py's roofline reads).

@@ -9,4 +9,4 @@ There is no CPU fallback.
 __version__ = '0.1.0'
 
 from ._ffi import LcbError, LcbScheme  # noqa: F401
-from .engine import Engine, make_scheme, ragged  # noqa: F401
+from .engine import Engine, MultiEngine, make_scheme, ragged  # noqa: F401

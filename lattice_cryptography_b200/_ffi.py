@@ -78,6 +78,20 @@ PROTOTYPES = {
     'lcb_vec_add_batch': (c_int, [c_void_p, _P, _P, c_int64, _P]),
     'lcb_vec_sub_batch': (c_int, [c_void_p, _P, _P, c_int64, _P]),
     'lcb_adaptor_witness_verify_batch': (c_int, [c_void_p, _P, _P, c_int64, c_int, c_int, _P]),
+    'lcb_mctx_create': (c_int, [POINTER(c_void_p), POINTER(c_int), c_int, c_int, c_int, c_int, c_int]),
+    'lcb_mctx_destroy': (c_int, [c_void_p]),
+    'lcb_mctx_ndev': (c_int, [c_void_p]),
+    'lcb_mctx_ctx': (c_void_p, [c_void_p, c_int]),
+    'lcb_mctx_last_error': (c_char_p, [c_void_p]),
+    'lcb_mctx_set_key_ch': (c_int, [c_void_p, _P]),
+    'lcb_mctx_lm_keygen_batch': (c_int, [c_void_p, POINTER(LcbScheme), _P, _P, c_int64, _P, _P, _P, _P]),
+    'lcb_mctx_lm_sign_batch': (c_int, [c_void_p, POINTER(LcbScheme), _P, _P, _P, c_int64, _P]),
+    'lcb_mctx_lm_verify_batch': (c_int, [c_void_p, POINTER(LcbScheme), _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
+    'lcb_mctx_lm_verify_packed_batch': (c_int, [c_void_p, POINTER(LcbScheme), _P, c_int, _P, _P, _P, c_int, c_int, c_int64,
+                                                c_int, c_int, _P]),
+    'lcb_mctx_bklm_aggregate': (c_int, [c_void_p, POINTER(LcbScheme), _P, _P, c_int64, c_int64, _P]),
+    'lcb_mctx_bklm_aggregate_verify': (c_int, [c_void_p, POINTER(LcbScheme), _P, _P, _P, _P, c_int64, c_int64, _P, c_int,
+                                               c_int, c_int, _P]),
     'lcb_launch_count': (c_int64, [c_void_p]),
     'lcb_profile_enable': (c_int, [c_void_p, c_int]),
     'lcb_profile_reset': (c_int, [c_void_p]),

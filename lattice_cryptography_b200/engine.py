@@ -424,3 +424,115 @@ class Engine(object):
         self._ck(self._lib.lcb_adaptor_witness_verify_batch(self._ctx, _addr(wit_coef), _addr(st_ntt), n, bd, wt,
                                                             _addr(verdict)))
         return verdict
+
+
+class MultiEngine(object):
+    """Single-process multi-GPU face of the C ABI (lcb_mctx_*, include/lcb200.h): host-resident batches are sharded
+    over `devices` inside ONE call; BKLM partial sums are reduced on the devices.  One process per GPU with
+    torch.distributed (lattice_cryptography_b200.distributed) is the other way to use several GPUs."""
+
+    def __init__(self, secpar: int, modulus: int, degree: int, length: int, devices: Sequence[int]):
+        import ctypes
+        self._lib = _ffi.load()
+        self._m = c_void_p()
+        arr = (ctypes.c_int * len(devices))(*devices)
+        st = self._lib.lcb_mctx_create(byref(self._m), arr, len(devices), secpar, modulus, degree, length)
+        if st != _ffi.LCB_OK:
+            detail = self._lib.lcb_last_error(None).decode() or self._lib.lcb_strerror(st).decode()
+            self._m = c_void_p()
+            raise LcbError(st, detail)
+        self.secpar, self.q, self.d, self.l, self.devices = secpar, modulus, degree, length, list(devices)
+        self.wide = modulus >= 65536
+        self.ct, self.nt = (np.int32, np.uint32) if self.wide else (np.int16, np.uint16)
+
+    def close(self):
+        if getattr(self, '_m', None) is not None and self._m.value:
+            self._lib.lcb_mctx_destroy(self._m)
+            self._m = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st: int):
+        if st != _ffi.LCB_OK:
+            raise LcbError(st, f'{self._lib.lcb_strerror(st).decode()} ({self._lib.lcb_mctx_last_error(self._m).decode()})')
+
+    @property
+    def launch_count(self) -> int:
+        return sum(self._lib.lcb_launch_count(self._lib.lcb_mctx_ctx(self._m, i)) for i in range(len(self.devices)))
+
+    def set_key_ch(self, key_ch_coef):
+        _want(key_ch_coef, 'key_ch', self.ct, (self.l, self.d))
+        self._ck(self._lib.lcb_mctx_set_key_ch(self._m, _addr(key_ch_coef)))
+
+    def lm_keygen(self, sch: LcbScheme, seeds, want_sk_coef: bool = True, want_sk_ntt: bool = True):
+        blob, off = Engine._rag(seeds)
+        n = Engine._count(off)
+        sk_coef = np.empty((n, 2, self.l, self.d), self.ct) if want_sk_coef else None
+        sk_ntt = np.empty((n, 2, self.l, self.d), self.nt) if want_sk_ntt else None
+        vk_ntt, vk_coef = np.empty((n, 2, self.d), self.nt), np.empty((n, 2, self.d), self.ct)
+        self._ck(self._lib.lcb_mctx_lm_keygen_batch(self._m, byref(sch), _addr(blob), _addr(off), n, _addr(sk_coef),
+                                                    _addr(sk_ntt), _addr(vk_ntt), _addr(vk_coef)))
+        return sk_coef, sk_ntt, vk_ntt, vk_coef
+
+    def lm_sign(self, sch: LcbScheme, sk_ntt, chmsgs):
+        blob, off = Engine._rag(chmsgs)
+        n = Engine._count(off)
+        _want(sk_ntt, 'sk_ntt', self.nt, (n, 2, self.l, self.d))
+        sig = np.empty((n, self.l, self.d), self.ct)
+        self._ck(self._lib.lcb_mctx_lm_sign_batch(self._m, byref(sch), _addr(sk_ntt), _addr(blob), _addr(off), n, _addr(sig)))
+        return sig
+
+    def lm_verify(self, sch: LcbScheme, vk_ntt, chmsgs, sig, bd: int, wt: int, st_ntt=None, out=None):
+        blob, off = Engine._rag(chmsgs)
+        n = Engine._count(off)
+        _want(vk_ntt, 'vk_ntt', self.nt, (n, 2, self.d))
+        _want(sig, 'sig', self.ct, (n, self.l, self.d))
+        if st_ntt is not None:
+            _want(st_ntt, 'st_ntt', self.nt, (n, self.d))
+        verdict = _want(out, 'out', np.uint8, (n,)) if out is not None else np.empty(n, np.uint8)
+        self._ck(self._lib.lcb_mctx_lm_verify_batch(self._m, byref(sch), _addr(vk_ntt), _addr(blob), _addr(off), _addr(sig),
+                                                    _addr(st_ntt), n, bd, wt, _addr(verdict)))
+        return verdict
+
+    def lm_verify_packed(self, sch: LcbScheme, vk_packed, vk_bits: int, chmsgs, sig_packed, sig_bits: int, sig_bias: int,
+                         bd: int, wt: int, out=None):
+        blob, off = Engine._rag(chmsgs)
+        n = Engine._count(off)
+        _want(vk_packed, 'vk_packed', np.uint8, (n, 2, self.d * vk_bits // 8))
+        _want(sig_packed, 'sig_packed', np.uint8, (n, self.l, self.d * sig_bits // 8))
+        verdict = _want(out, 'out', np.uint8, (n,)) if out is not None else np.empty(n, np.uint8)
+        self._ck(self._lib.lcb_mctx_lm_verify_packed_batch(self._m, byref(sch), _addr(vk_packed), vk_bits, _addr(blob), _addr(off),
+                                                           _addr(sig_packed), sig_bits, sig_bias, n, bd, wt, _addr(verdict)))
+        return verdict
+
+    @staticmethod
+    def _msg(agmsg):
+        if isinstance(agmsg, (str, bytes, bytearray)):
+            agmsg = np.frombuffer(agmsg.encode() if isinstance(agmsg, str) else bytes(agmsg), dtype=np.uint8)
+        return _want(agmsg, 'agmsg', np.uint8, (None,))
+
+    def bklm_aggregate(self, sch: LcbScheme, sig_sorted, agmsg):
+        agmsg = self._msg(agmsg)
+        n = int(sig_sorted.shape[0])
+        _want(sig_sorted, 'sig_sorted', self.ct, (n, self.l, self.d))
+        out = np.empty((self.l, self.d), self.ct)
+        self._ck(self._lib.lcb_mctx_bklm_aggregate(self._m, byref(sch), _addr(sig_sorted), _addr(agmsg), int(agmsg.shape[0]), n,
+                                                   _addr(out)))
+        return out
+
+    def bklm_aggregate_verify(self, sch: LcbScheme, vk_ntt_sorted, chmsgs_sorted, agmsg, ag_sig, ag_cap: int, avf_bd: int,
+                              avf_wt: int) -> bool:
+        agmsg = self._msg(agmsg)
+        blob, off = Engine._rag(chmsgs_sorted)
+        n = Engine._count(off)
+        _want(vk_ntt_sorted, 'vk_ntt_sorted', self.nt, (n, 2, self.d))
+        _want(ag_sig, 'ag_sig', self.ct, (self.l, self.d))
+        verdict = np.zeros(1, dtype=np.uint8)
+        self._ck(self._lib.lcb_mctx_bklm_aggregate_verify(self._m, byref(sch), _addr(vk_ntt_sorted), _addr(blob), _addr(off),
+                                                          _addr(agmsg), int(agmsg.shape[0]), n, _addr(ag_sig), ag_cap, avf_bd,
+                                                          avf_wt, _addr(verdict)))
+        return bool(verdict[0])
