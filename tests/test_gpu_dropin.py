@@ -202,3 +202,101 @@ def test_container_validation_messages():
     assert otk.bits_to_indices(128, 256, 20) == 2592 and otk.bits_to_decode(128, 1) == 129
     with pytest.raises(ValueError, match='non-positive'):
         otk.bits_per_coefficient(128, 0)
+
+
+@pytest.mark.parametrize('secpar', [128, 256])
+def test_bklm_all_at_the_reference_sample_size(secpar):
+    """tests/test_bklm_one_time_agg_sigs.py:406-415 (test_all) as the reference runs it: SAMPLE_SIZE = 64 rounds per
+    security parameter of keygen(ag_cap) -> sign -> verify -> aggregate -> aggregate_verify, fresh random keys and
+    32-bit messages every round."""
+    from lattice_cryptography_b200 import bklm_one_time_agg_sigs as bk
+    from lattice_cryptography_b200.lm_one_time_sigs import keygen, sign, verify
+    pp = bk.make_setup_parameters(secpar)
+    for _ in range(64):
+        keys = keygen(pp=pp, num_keys_to_gen=pp['ag_cap'])
+        msgs = [bin(randbits(32))[2:].zfill(32) for _ in range(pp['ag_cap'])]
+        sigs = [sign(pp=pp, otk=k, msg=m) for k, m in zip(keys, msgs)]
+        for k, m, s in zip(keys, msgs, sigs):
+            assert verify(pp=pp, otvk=k[2], msg=m, sig=s)
+        otvks = [k[2] for k in keys]
+        ag_sig = bk.aggregate(pp=pp, otvks=otvks, msgs=msgs, sigs=sigs)
+        assert bk.aggregate_verify(pp=pp, otvks=otvks, msgs=msgs, ag_sig=ag_sig)
+
+
+@pytest.mark.parametrize('secpar', [128, 256])
+def test_lower_seam_alone_carries_the_schemes(secpar):
+    """INTEGRATION.md option (b): the reference's scheme modules only use the ten names they import from
+    lattice_algebra.  Here every scheme operation is computed a second time from those names
+    and operators ALONE on the GPU-backed objects - the way the reference's own function bodies do it
+    (lm_one_time_sigs.py:64-97,141-191; bklm_one_time_agg_sigs.py:60-116; adaptor_sigs.py:80-101,191-266) - and must
+    agree with the batched drop-in functions object for object and verdict for verdict."""
+    from lattice_cryptography_b200 import adaptor_sigs as ad
+    from lattice_cryptography_b200 import bklm_one_time_agg_sigs as bk
+    from lattice_cryptography_b200 import lm_one_time_sigs as lm
+    from lattice_cryptography_b200.lattice_algebra import (UNIFORM_INFINITY_WEIGHT as DIST, bits_to_decode, bits_to_indices,
+                                                           hash2polynomial, hash2polynomialvector)
+    pp = ad.make_setup_parameters(secpar)
+    bpp = bk.make_setup_parameters(secpar)
+    bpp['scheme_parameters'] = pp['scheme_parameters']
+    sp = pp['scheme_parameters']
+    lp, key_ch, d = sp.lp, sp.key_ch, sp.lp.degree
+
+    def h2pv(salt, msg, bd, wt):
+        return hash2polynomialvector(secpar=secpar, lp=lp, distribution=DIST, dist_pars={'bd': bd, 'wt': wt}, num_coefs=wt,
+                                     bti=bits_to_indices(secpar, d, wt), btd=bits_to_decode(secpar, bd), msg=msg, salt=salt,
+                                     const_time_flag=False)
+
+    def h2p(salt, msg, bd, wt):
+        return hash2polynomial(secpar=secpar, lp=lp, distribution=DIST, dist_pars={'bd': bd, 'wt': wt}, salt=salt, msg=msg,
+                               num_coefs=wt, bti=bits_to_indices(secpar, d, wt), btd=bits_to_decode(secpar, bd),
+                               const_time_flag=False)
+
+    def within(vec, bd, wt, lower=False):
+        cnw = vec.get_coef_rep()
+        n, w = max(i[1] for i in cnw), max(i[2] for i in cnw)
+        return n <= bd and w <= wt and (not lower or (n >= 1 and w >= 1))
+
+    keys = lm.keygen(pp=pp, num_keys_to_gen=2)
+    msgs = [bin(randbits(32))[2:].zfill(32) for _ in keys]
+    for (seed, sk, vk), msg in zip(keys, msgs):
+        # make_one_key
+        left, right = h2pv(pp['sk_salt'] + 'LEFT', seed.seed, pp['sk_bd'], pp['sk_wt']), h2pv(pp['sk_salt'] + 'RIGHT', seed.seed, pp['sk_bd'], pp['sk_wt'])
+        assert left == sk[0] and right == sk[1] and key_ch * left == vk[0] and key_ch * right == vk[1]
+        # make_signature_challenge / sign / verify
+        c = h2p(pp['ch_salt'], str(vk) + ', ' + msg, pp['ch_bd'], pp['ch_wt'])
+        assert c == lm.make_signature_challenge(pp=pp, otvk=vk, msg=msg)
+        sig = left ** c + right
+        assert sig == lm.sign(pp=pp, otk=(seed, sk, vk), msg=msg)
+        lpp = lm.make_setup_parameters(secpar)
+        assert (within(sig, lpp['vf_bd'], lpp['vf_wt']) and key_ch * sig == vk[0] * c + vk[1]) is True
+    # aggregation coefficients, aggregate, aggregate_verify
+    vks = [k[2] for k in keys]
+    sigs = [lm.sign(pp=bpp, otk=k, msg=m) for k, m in zip(keys, msgs)]
+    order = sorted(range(2), key=lambda i: str(vks[i]))
+    s_keys, s_msgs, s_sigs = [vks[i] for i in order], [msgs[i] for i in order], [sigs[i] for i in order]
+    agmsg = str(list(zip(s_keys, s_msgs)))
+    coefs = [h2p(bpp['ag_salt'] + str(i), agmsg, bpp['ag_bd'], bpp['ag_wt']) for i in range(2)]
+    assert coefs == bk.make_agg_coefs(pp=bpp, otvks=vks, msgs=msgs)
+    ag_sig = sum([s ** a for s, a in zip(s_sigs, coefs)])
+    assert ag_sig == bk.aggregate(pp=bpp, otvks=vks, msgs=msgs, sigs=sigs)
+    challs = [h2p(bpp['ch_salt'], str(k) + ', ' + m, bpp['ch_bd'], bpp['ch_wt']) for k, m in zip(s_keys, s_msgs)]
+    total = sum([(k[0] * c + k[1]) * a for a, c, k in zip(coefs, challs, s_keys)])
+    assert within(ag_sig, bpp['avf_bd'], bpp['avf_wt'], lower=True) and key_ch * ag_sig == total
+    assert bk.aggregate_verify(pp=bpp, otvks=vks, msgs=msgs, ag_sig=ag_sig) is True
+    # adaptor: witness / statement, presign, preverify, adapt, verify, extract, witness_verify
+    (seed, sk, vk), msg = keys[0], 'Blessed are the cheesemakers.'
+    wseed, wit, st = ad.witgen(pp=pp, num_wits_to_gen=1)[0]
+    w = h2pv(pp['wit_salt'], wseed.seed, pp['wit_bd'], pp['wit_wt'])
+    assert w == wit.key and key_ch * w == st.key
+    c = h2p(pp['ch_salt'], str(st) + ', ' + str(vk) + ', ' + msg, pp['ch_bd'], pp['ch_wt'])
+    presig = sk[0] ** c + sk[1]
+    assert presig == ad.presign(pp=pp, otk=keys[0], msg=msg, st=st)
+    assert (within(presig, pp['pvf_bd'], pp['pvf_wt']) and key_ch * presig == vk[0] * c + vk[1]) is True
+    assert ad.preverify(pp=pp, otvk=vk, msg=msg, st=st, presig=presig) is True
+    full = presig + w
+    assert full == ad.adapt(presig=presig, wit=wit)
+    assert (within(full, pp['vf_bd'], pp['vf_wt']) and key_ch * full == vk[0] * c + vk[1] + st.key) is True
+    assert ad.verify(pp=pp, otvk=vk, msg=msg, st=st, sig=full) is True
+    ext = full - presig
+    assert ext == ad.extract(pp=pp, presig=presig, sig=full).key == w
+    assert (within(ext, pp['ext_wit_bd'], pp['ext_wit_wt']) and key_ch * ext == st.key) is True
