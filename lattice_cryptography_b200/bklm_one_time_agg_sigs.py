@@ -90,12 +90,41 @@ def prepare_aggregate(otvks: List[OneTimeVerificationKey], msgs: List[Message], 
 
 
 # ------------------------------------------------------------------------------- sharded engine API
+# Aggregation coefficients are a function of (ag_salt, ag_bd, ag_wt, ring, the aggregation message, the index range)
+# alone, and deriving them is the O(N^2) part of both aggregate and aggregate_verify (bklm_one_time_agg_sigs.py:60-81).
+# A process that aggregates and then verifies the same list (the reference's own test_all does) would hash every
+# coefficient twice; the last few derivations are therefore kept, keyed by a digest of the message CONTENT.
+_AG_CACHE: Dict[tuple, object] = {}
+_AG_CACHE_SLOTS = 4
+
+
+def clear_agg_coef_cache() -> None:
+    _AG_CACHE.clear()
+
+
+def _agg_coefs_cached(pp: PublicParameters, eng, sch, agmsg, first: int, count: int, device: bool):
+    import hashlib
+    raw = agmsg.encode() if isinstance(agmsg, str) else (bytes(agmsg) if isinstance(agmsg, (bytes, bytearray)) else None)
+    if raw is None:                                    # device / array messages: no content key, derive
+        return eng.agg_coefs(sch, agmsg, first, count, device=device)
+    lp = pp['scheme_parameters'].lp
+    key = (hashlib.blake2b(raw, digest_size=20).digest(), len(raw), first, count, device, pp['scheme_parameters'].secpar,
+           lp.modulus, lp.degree, pp.get('ag_salt', 'AG_SALT'), pp.get('ag_bd', 1), pp.get('ag_wt', 1))
+    hit = _AG_CACHE.get(key)
+    if hit is None:
+        hit = eng.agg_coefs(sch, raw, first, count, device=device)
+        while len(_AG_CACHE) >= _AG_CACHE_SLOTS:
+            _AG_CACHE.pop(next(iter(_AG_CACHE)))
+        _AG_CACHE[key] = hit
+    return hit
+
+
 def aggregate_shard(pp: PublicParameters, sig_sorted, agmsg, first: int, device: bool = False):
     """int32[l,d] partial sum over the shard of the SORTED signature list that starts at global
     position `first` (sig_sorted int16[count,l,d]); aggregation coefficients are derived here."""
     eng, sch = _ctx(pp)
     count = int(sig_sorted.shape[0])
-    ag = eng.agg_coefs(sch, agmsg, first, count, device=device)
+    ag = _agg_coefs_cached(pp, eng, sch, agmsg, first, count, device)
     return eng.aggregate_partial(sch, sig_sorted, ag, device=device)
 
 
@@ -108,7 +137,7 @@ def aggregate_verify_shard(pp: PublicParameters, vk_ntt_sorted, chmsgs_sorted, a
     """int32[d] partial sum (NTT form) of (vk_left*c + vk_right) * ag over one shard of the sorted list."""
     eng, sch = _ctx(pp)
     count = int(vk_ntt_sorted.shape[0])
-    ag = eng.agg_coefs(sch, agmsg, first, count, device=device)
+    ag = _agg_coefs_cached(pp, eng, sch, agmsg, first, count, device)
     return eng.aggverify_partial(sch, vk_ntt_sorted, chmsgs_sorted, ag, device=device)
 
 

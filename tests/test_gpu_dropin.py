@@ -300,3 +300,28 @@ def test_lower_seam_alone_carries_the_schemes(secpar):
     ext = full - presig
     assert ext == ad.extract(pp=pp, presig=presig, sig=full).key == w
     assert (within(ext, pp['ext_wit_bd'], pp['ext_wit_wt']) and key_ch * ext == st.key) is True
+
+
+def test_aggregation_coefficient_cache_is_keyed_by_content():
+    """aggregate followed by aggregate_verify of the same list derives the O(N^2) coefficients once; any change of the
+    message content, the index range or the parameters misses."""
+    from lattice_cryptography_b200 import bklm_one_time_agg_sigs as bk
+    from lattice_cryptography_b200.lm_one_time_sigs import _ctx, keygen, sign
+    pp = bk.set_aggregation_capacity(bk.make_setup_parameters(128), 6)
+    keys = keygen(pp=pp, num_keys_to_gen=6)
+    msgs = [bin(randbits(32))[2:].zfill(32) for _ in keys]
+    sigs = [sign(pp=pp, otk=k, msg=m) for k, m in zip(keys, msgs)]
+    vks = [k[2] for k in keys]
+    bk.clear_agg_coef_cache()
+    eng = _ctx(pp)[0]
+    before = eng.launch_count
+    ag_sig = bk.aggregate(pp=pp, otvks=vks, msgs=msgs, sigs=sigs)
+    mid = eng.launch_count
+    assert len(bk._AG_CACHE) == 1
+    assert bk.aggregate_verify(pp=pp, otvks=vks, msgs=msgs, ag_sig=ag_sig)
+    assert len(bk._AG_CACHE) == 1                                   # hit: same sorted list, same range
+    cold = bk.aggregate(pp=pp, otvks=vks, msgs=msgs, sigs=sigs)
+    bk.clear_agg_coef_cache()
+    assert bk.aggregate(pp=pp, otvks=vks, msgs=msgs, sigs=sigs) == cold == ag_sig          # cached == derived
+    assert not bk.aggregate_verify(pp=pp, otvks=vks, msgs=msgs[::-1], ag_sig=ag_sig)       # other content: miss, and rejected
+    assert len(bk._AG_CACHE) == 2 and mid > before
