@@ -35,6 +35,8 @@ struct lcb_ctx {
     size_t idx_scratch_bytes = 0;
     uint2* il_scratch = nullptr;         // bit-split copies of the BKLM aggregation message (grow-only)
     size_t il_scratch_bytes = 0;
+    uint32_t* coop_scratch = nullptr;    // digest scratch of the cooperative low-latency sampler (grow-only)
+    size_t coop_scratch_bytes = 0;
     // optional per-kernel CUDA-event timing (lcb_profile_*)
     bool profile = false;
     struct Pending { int id; cudaEvent_t a, b; };
@@ -99,10 +101,15 @@ cudaError_t timed(lcb_ctx* c, int id, F&& launch) {
 
 // Point a sampler launch at the ctx's index scratch, growing it when the batch needs more.
 cudaError_t sampler_scratch(lcb_ctx* c, SamplerArgs& a) {
-    const size_t need = sampler_scratch_bytes(a.n, a.wt, true);   // sized for 16-bit indices: either kernel may run
+    // a handful of streams: the cooperative kernel (one block per stream, sponge and per-polynomial decoders side by side)
+    a.coop_digest = reinterpret_cast<uint32_t*>(1);
+    const bool coop = sampler_coop_applies(a, c->ring.num_sms);
+    a.coop_digest = nullptr;
+    const int64_t slots = coop ? a.n * a.vec_len : a.n;
+    const size_t need = sampler_scratch_bytes(slots, a.wt, true);   // sized for 16-bit indices: either kernel may run
+    cudaError_t e;
     if (need > c->idx_scratch_bytes) {
-        cudaError_t e = cudaStreamSynchronize(c->stream);
-        if (e != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return e;
         if (c->idx_scratch) cudaFree(c->idx_scratch);
         c->idx_scratch = nullptr;
         c->idx_scratch_bytes = 0;
@@ -110,7 +117,20 @@ cudaError_t sampler_scratch(lcb_ctx* c, SamplerArgs& a) {
         c->idx_scratch_bytes = need;
     }
     a.idx_scratch = c->idx_scratch;
-    a.idx_stride = sampler_stride(a.n);
+    a.idx_stride = sampler_stride(slots);
+    if (coop) {
+        const int64_t bits = (int64_t)a.logd + (int64_t)(a.wt - 1) * a.idx_bits + (int64_t)a.wt * (1 + a.mag_bits) + a.pad_bits;
+        const size_t dneed = (size_t)a.n * sampler_coop_digest_words(a.vec_len, (int)(bits / 32)) * sizeof(uint32_t);
+        if (dneed > c->coop_scratch_bytes) {
+            if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return e;
+            if (c->coop_scratch) cudaFree(c->coop_scratch);
+            c->coop_scratch = nullptr;
+            c->coop_scratch_bytes = 0;
+            if ((e = cudaMalloc(&c->coop_scratch, dneed)) != cudaSuccess) return e;
+            c->coop_scratch_bytes = dneed;
+        }
+        a.coop_digest = c->coop_scratch;
+    }
     return cudaSuccess;
 }
 
@@ -307,6 +327,7 @@ int fill_sampler(lcb_ctx* c, SamplerArgs& a, const char* salt, const char* suffi
     a.wide = c->wide ? 1 : 0;
     a.stream_salts = nullptr;
     a.stream_salt_len = nullptr;
+    a.coop_digest = nullptr;
     a.idx_bits = logd + c->secpar;
     const int btd = ceil_log2(bd) + 1 + c->secpar;
     a.mag_bits = btd - 1;
@@ -601,6 +622,7 @@ int lcb_ctx_destroy(lcb_ctx* c) {
     if (c->d_a_hat) cudaFree(c->d_a_hat);
     if (c->idx_scratch) cudaFree(c->idx_scratch);
     if (c->il_scratch) cudaFree(c->il_scratch);
+    if (c->coop_scratch) cudaFree(c->coop_scratch);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);

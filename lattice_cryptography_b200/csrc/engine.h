@@ -42,10 +42,17 @@ struct SamplerArgs {
     // per-stream salts (aggregation coefficients with ag_wt > 1): [n][SALT_BYTES] bytes + [n] lengths, or nullptr
     const uint8_t* stream_salts;
     const int32_t* stream_salt_len;
+    // cooperative low-latency kernel (few streams): digest scratch, sampler_coop_digest_words() words per stream;
+    // nullptr = the ordinary one-thread-per-stream kernel
+    uint32_t* coop_digest;
 };
 
 cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st);
 cudaError_t launch_seed_expand(const uint8_t* secret, int64_t first, int64_t n, int secpar, uint8_t* out, cudaStream_t st);
+bool sampler_coop_applies(const SamplerArgs& a, int num_sms);     // with a.coop_digest set to any non-null value
+inline int64_t sampler_coop_digest_words(int vec_len, int words_per_poly) {
+    return ((int64_t)vec_len * words_per_poly + 34 + 20 + 34 + 63) / 64 * 64;      // + one window and one block of slack
+}
 cudaError_t launch_index_salts(const SamplerArgs& a, uint8_t* salts, int32_t* lens, cudaStream_t st);
 inline int64_t sampler_stride(int64_t n) { return (n + 127) / 128 * 128; }
 // parked indices: one byte each for d = 256, two bytes on the generic path

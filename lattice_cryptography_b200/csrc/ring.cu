@@ -241,26 +241,79 @@ __global__ void __launch_bounds__(RBS, 4) k_matvec(ModQ m, StageConst sc, StageC
                                                 const uint32_t* __restrict__ a_hat_g, int l,
                                                 const int16_t* __restrict__ vec_coef, int64_t nvec,
                                                 uint16_t* __restrict__ vec_ntt, uint16_t* __restrict__ y_ntt,
+                                                int16_t* __restrict__ y_coef);
+
+// ------------------------------------------------------------------------------------------------
+// Asynchronous global->shared staging (LDGSTS, L2-only) used by k_sign and k_verify: each half-warp owns two
+// stage buffers and keeps the next two rows of its work list in flight while it works on the current one, so
+// HBM latency never reaches the scoreboard.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int STAGE_HALF_BYTES = 2 * D * 2 + 32;   // two polynomials + 32 B so half-warps differ by 8 banks
+
+// Coefficient-form rows reach k_matvec the way they reach k_verify: through a 2-deep cp.async pipeline per half-warp
+// and conflict-free 16-bit shared loads.  (Round 1 read them with 16 strided 2-byte global loads per lane: 35 % of
+// the warp samples sat on the long scoreboard.)
+__global__ void __launch_bounds__(RBS, 4) k_matvec(ModQ m, StageConst sc, StageConstF scf, const NttTables* __restrict__ tab,
+                                                const uint32_t* __restrict__ a_hat_g, int l,
+                                                const int16_t* __restrict__ vec_coef, int64_t nvec,
+                                                uint16_t* __restrict__ vec_ntt, uint16_t* __restrict__ y_ntt,
                                                 int16_t* __restrict__ y_coef) {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* a_hat = smem;
     uint32_t* xbuf = smem + l * AROW;
     copy_a_hat(a_hat, a_hat_g, l);
     const HalfWarp h = half_warp(xbuf);
-    uint4* twtab = reinterpret_cast<uint4*>(xbuf + (RBS / 32) * XWARP);
+    unsigned char* stage_base = reinterpret_cast<unsigned char*>(xbuf + (RBS / 32) * XWARP);
+    unsigned char* stage = stage_base + h.slot * STAGE_HALF_BYTES;
+    uint4* twtab = reinterpret_cast<uint4*>(stage_base + HWB * STAGE_HALF_BYTES);
     fill_tw_shared(twtab, tab);
     const LaneTwFShared twf{twtab + h.lane * TW_ROW};
-    for (int64_t base = (int64_t)blockIdx.x * HWB; base < nvec; base += (int64_t)gridDim.x * HWB) {
-        const int64_t raw = base + h.slot;
+    const int64_t first = (int64_t)blockIdx.x * HWB, stride = (int64_t)gridDim.x * HWB;
+    const int64_t trips = first < nvec ? (nvec - first + stride - 1) / stride : 0;   // uniform over the block
+    int64_t pf_it = 0;
+    int pf_i = 0;
+    unsigned pf_buf = 0;
+    auto issue = [&]() {
+        if (pf_it < trips) {
+            int64_t it_item = first + pf_it * stride + h.slot;
+            it_item = it_item < nvec ? it_item : nvec - 1;
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(vec_coef + (it_item * l + pf_i) * D);
+            unsigned char* dst = stage + pf_buf * (D * 2);
+            cp_async16(dst + 16 * h.lane, src + 16 * h.lane);
+            cp_async16(dst + 256 + 16 * h.lane, src + 256 + 16 * h.lane);
+            if (++pf_i == l) { pf_i = 0; ++pf_it; }
+            pf_buf ^= 1u;
+        }
+        cp_async_commit();
+    };
+    issue();
+    issue();
+    unsigned cur = 0;
+    for (int64_t it = 0; it < trips; ++it) {
+        const int64_t raw = first + it * stride + h.slot;
         const bool live = raw < nvec;
         const int64_t item = live ? raw : nvec - 1;
         uint64_t acc[EPT];
 #pragma unroll
         for (int i = 0; i < EPT; ++i) acc[i] = 0;
         for (int i = 0; i < l; ++i) {
+            cp_async_wait<1>();
+            __syncwarp();
             uint32_t r[EPT];
             int x[EPT];
-            load_coef_raw(x, vec_coef + (item * l + i) * D, h.lane);
+            const unsigned sp = (unsigned)__cvta_generic_to_shared(stage + cur * (D * 2) + 2 * h.lane);
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) asm volatile("ld.shared.s16 %0, [%1];" : "=r"(x[j]) : "r"(sp + 32 * j));
+            __syncwarp();
+            issue();
+            cur ^= 1u;
             ntt_fwd_256_fp(x, r, m, scf, twf, h.xb, h.lane);
 #pragma unroll
             for (int k = 0; k < EPT; ++k) r[k] -= FP_BIAS;
@@ -283,18 +336,6 @@ __global__ void __launch_bounds__(RBS, 4) k_matvec(ModQ m, StageConst sc, StageC
         }
     }
 }
-
-// ------------------------------------------------------------------------------------------------
-// Asynchronous global->shared staging (LDGSTS, L2-only) used by k_sign and k_verify: each half-warp owns two
-// stage buffers and keeps the next two rows of its work list in flight while it works on the current one, so
-// HBM latency never reaches the scoreboard.
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 constexpr int VERIFY_BLOCKS = 4;     // resident blocks per SM k_verify is compiled for
 
@@ -386,8 +427,6 @@ __global__ void __launch_bounds__(RBS) k_sign(ModQ m, StageConst sc, const NttTa
 // Asynchronous global->shared staging of coefficient-form polynomials (LDGSTS, L2-only): each
 // half-warp owns two 512-byte stage buffers and keeps the next two polynomials of its work list
 // in flight while it transforms the current one, so HBM latency never reaches the scoreboard.
-constexpr int STAGE_HALF_BYTES = 2 * D * 2 + 32;   // two polynomials + 32 B so half-warps differ by 8 banks
-
 // 16 NTT slots of one lane from a 14-bit packed polynomial (wire.cu layout): 16 * 14 bits = exactly 7 words
 __device__ __forceinline__ void load_u14x16(uint32_t (&r)[EPT], const uint32_t* __restrict__ p) {
     uint32_t w[8];
@@ -793,7 +832,7 @@ cudaError_t launch_poly_mul(const RingCtx& c, const int16_t* a, const int16_t* b
 cudaError_t launch_matvec(const RingCtx& c, const int16_t* vec_coef, int64_t nvec, uint16_t* vec_ntt,
                           uint16_t* y_ntt, int16_t* y_coef, cudaStream_t st) {
     if (nvec <= 0) return cudaSuccess;
-    size_t smem = ring_smem(c.l) + TW_BYTES;
+    size_t smem = verify_smem(c.l);
     cudaError_t e = allow_smem(k_matvec, smem);
     if (e != cudaSuccess) return e;
     unsigned grid = persistent_grid(nvec, HWB, c.num_sms, resident_blocks(k_matvec, RBS, smem));

@@ -18,6 +18,23 @@ namespace {
 
 constexpr int SBS = 128;          // threads per block = SHAKE streams per block
 
+// round constants split into even-bit / odd-bit halves (keccak_f1600_half)
+struct Rc2Table {
+    uint32_t v[2][24];      // [even-bit halves | odd-bit halves] of the round constants
+};
+constexpr uint32_t cx_even_bits(uint64_t x) {
+    uint32_t r = 0;
+    for (int i = 0; i < 32; ++i) r |= (uint32_t)((x >> (2 * i)) & 1u) << i;
+    return r;
+}
+constexpr Rc2Table make_rc2() {
+    constexpr uint64_t rc[24] = LCB_KECCAK_RC_INIT;
+    Rc2Table t{};
+    for (int i = 0; i < 24; ++i) { t.v[0][i] = cx_even_bits(rc[i]); t.v[1][i] = cx_even_bits(rc[i] >> 1); }
+    return t;
+}
+static __constant__ Rc2Table c_keccak_rc2 = make_rc2();
+
 // Absorb an input into a fresh state; leaves the state PERMUTED, i.e. its first 136 bytes are the
 // first squeeze block.  `rate` is this block's [34][SBS] staging area in shared memory.
 __device__ __forceinline__ void absorb(KeccakState& s, uint32_t* rate, int tid, const InputView& in) {
@@ -165,7 +182,8 @@ __global__ void __launch_bounds__(P) k_sampler_g(SamplerArgs a) {
     CT* dense = a.out_dense ? reinterpret_cast<CT*>(a.out_dense) + inst * a.dense_stride : nullptr;
     CT* pairs = a.out_pairs ? reinterpret_cast<CT*>(a.out_pairs) + inst * a.vec_len * (int64_t)a.wt * 2 : nullptr;
     const int wt = a.wt, d = a.d;
-    sample_stream_t<GeoAny, uint16_t>(geo, dp, iv, sc, [&](int poly, int e, int idx, int coef) {
+    SpongeFeed feed;
+    sample_stream_t<GeoAny, uint16_t>(geo, dp, iv, sc, feed, [&](int poly, int e, int idx, int coef) {
         if (!live) return;
         if (dense) dense[(int64_t)poly * d + idx] = (CT)coef;
         if (pairs) {
@@ -173,6 +191,101 @@ __global__ void __launch_bounds__(P) k_sampler_g(SamplerArgs a) {
             pairs[((int64_t)poly * wt + e) * 2 + 1] = (CT)coef;
         }
     });
+}
+
+// ------------------------------------------------------------------------------------------------
+// Low-latency form for a HANDFUL of streams (a single key generation is two streams of 829 / 2,853 permutations:
+// 7.8 / 20.8 ms when one thread squeezes and decodes everything, lm_one_time_sigs.py:64-97).  One block per stream:
+//   warp 0        : the sponge on a lane pair (keccak_f1600_half: 110 instead of ~185 issue slots per round),
+//                   digest written to a global scratch as little-endian stream words, progress published in shared memory;
+//   warps 1 .. l  : ONE decoder lane each (its own warp, so that each has its own issue slots), polynomial p of the
+//                   vector, whose bits start at digest byte p * nb - the l decoders run behind the producer instead of
+//                   after it, so the stream costs about the sponge alone.
+// d = 256, 16-bit outputs; chunk sizes nb that are not a multiple of 8 bytes fall back to k_sampler.
+constexpr int COOP_MAX_POLYS = 23;       // the widest shipped vector (secpar 256); 24 warps per block
+
+// decoder k runs in warp 1 + k + k / 3: warps 4, 8, 12, ... stay empty, because they would share warp 0's scheduler
+// (warp id mod 4) and take issue slots from the sponge, which is the critical path
+__host__ __device__ constexpr int coop_warps(int polys) { return 1 + polys + (polys + 2) / 3; }
+
+__global__ void __launch_bounds__(32 * coop_warps(COOP_MAX_POLYS)) k_sampler_coop(SamplerArgs a, uint32_t* __restrict__ digest,
+                                                                          int64_t digest_stride, int words_per_poly) {
+    __shared__ uint32_t rc_sh[2][24];
+    __shared__ volatile unsigned produced;
+    extern __shared__ uint32_t smem[];                       // decoders: [RING_WORDS + 8][vec_len] columns, then tables
+    const int nd = a.vec_len;                                // decoder warps
+    uint32_t* ring = smem;
+    uint32_t* bmap = ring + RING_WORDS * nd;
+    uint32_t* mutab = bmap + 8 * nd;
+    uint32_t* r16tab = mutab + 260;
+    uint8_t* wtab = reinterpret_cast<uint8_t*>(r16tab + 260);
+    const int pieces = weight_pieces(a.idx_bits, a.mag_bits);
+    if (threadIdx.x < 48) rc_sh[threadIdx.x / 24][threadIdx.x % 24] = c_keccak_rc2.v[threadIdx.x / 24][threadIdx.x % 24];
+    if (threadIdx.x == 0) produced = 0;
+    fill_mod_tables(mutab, r16tab, a.wt);
+    fill_weight_table(wtab, a.wt, a.bd, pieces);
+    __syncthreads();
+    const int64_t inst = blockIdx.x;                         // one block per stream
+    const int64_t item = a.paired ? inst >> 1 : inst;
+    const bool second = a.paired && (inst & 1);
+    uint32_t* dg = digest + inst * digest_stride;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) {
+        // ---- producer: absorb salt || message, then squeeze vec_len * words_per_poly (+ one window) words
+        const unsigned odd = lane & 1u;
+        const int64_t msg_begin = __ldg(a.off + item), msg_end = __ldg(a.off + item + 1);
+        const InputView iv{reinterpret_cast<const uint32_t*>(second ? a.salt2 : a.salt), second ? a.salt2_len : a.salt_len,
+                           a.msgs + msg_begin, msg_end - msg_begin};
+        const int64_t tot = iv.total();
+        const int64_t in_blocks = tot / 136 + 1, in_last = in_blocks * 136 - 1;
+        const uint32_t* rc = rc_sh[odd];
+        KeccakHalfRot rot;
+        keccak_half_rot_init(rot, odd);
+        KeccakHalf s;
+#pragma unroll
+        for (int i = 0; i < 25; ++i) s.a[i] = 0;
+        for (int64_t blk = 0; blk < in_blocks; ++blk) {
+#pragma unroll 1
+            for (int i = 0; i < 17; ++i) {
+                const int64_t g = blk * 17 + i;
+                const uint64_t x = (uint64_t)iv.word_at(2 * g, tot, in_last) | ((uint64_t)iv.word_at(2 * g + 1, tot, in_last) << 32);
+                const uint32_t hv = keccak_half_of(x, odd);
+#pragma unroll
+                for (int j = 0; j < 17; ++j)
+                    if (j == i) s.a[j] ^= hv;
+            }
+            keccak_f1600_half(s, rc, rot);
+        }
+        const unsigned total_words = (unsigned)(nd * words_per_poly) + RATE_WORDS + RING_EXTRA;
+        unsigned blocks_out = 0;
+        for (unsigned done = 0; done < total_words; done += RATE_WORDS) {
+            // the lanes' state halves go out as they are ((even, odd) pair per sponge word); the decoders interleave
+#pragma unroll
+            for (int i = 0; i < 17; ++i)
+                if (lane < 2) dg[done + 2 * i + odd] = s.a[i];
+            // publish every fourth block (and the last): a device-wide fence costs hundreds of cycles of the critical path
+            if ((++blocks_out & 3u) == 0 || done + RATE_WORDS >= total_words) {
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) produced = done + RATE_WORDS;
+            }
+            keccak_f1600_half(s, rc, rot);
+        }
+    } else if ((warp & 3) != 0 && lane == 0 && warp - 1 - warp / 4 < nd) {
+        // ---- decoder of polynomial p
+        const int p = warp - 1 - warp / 4;
+        const DecodeParams dp{a.bd, a.wt, 1, a.idx_bits, a.mag_bits, a.pad_bits};
+        const StreamCols sc{ring + p, bmap + p, nd, mutab, r16tab, wtab, pieces,
+                            a.idx_scratch + (inst * nd + p), a.idx_stride};
+        BufferFeed feed{dg + (int64_t)p * words_per_poly, &produced, (unsigned)(p * words_per_poly), 0u};
+        const InputView none{nullptr, 0, nullptr, 0};
+        int16_t* dense = a.out_dense ? a.out_dense + inst * a.dense_stride + (int64_t)p * D : nullptr;
+        uint32_t* pairs = a.out_pairs ? reinterpret_cast<uint32_t*>(a.out_pairs) + (inst * a.vec_len + p) * (int64_t)a.wt : nullptr;
+        sample_stream_t<Geo256, uint8_t>(Geo256{}, dp, none, sc, feed, [&](int, int e, int idx, int coef) {
+            if (dense) dense[idx] = (int16_t)coef;
+            if (pairs) pairs[e] = (uint32_t)idx | ((uint32_t)(uint16_t)(int16_t)coef << 16);
+        });
+    }
 }
 
 // salt' = salt || decimal(first + i), zero padded to SALT_BYTES, one per stream (aggregation coefficients)
@@ -297,21 +410,6 @@ __global__ void __launch_bounds__(ABS) k_agg_coefs(SamplerArgs a) {
 // 8 t + delta, delta = (-slen) mod 8, at the start of its word g0 + t - and an interior rate block is then 17
 // aligned 32-bit loads and 17 XORs per lane (no funnel shifts at all; warp-uniform addresses wherever the
 // decimal index has the same number of digits).
-struct Rc2Table {
-    uint32_t v[2][24];      // [even-bit halves | odd-bit halves] of the round constants
-};
-constexpr uint32_t cx_even_bits(uint64_t x) {
-    uint32_t r = 0;
-    for (int i = 0; i < 32; ++i) r |= (uint32_t)((x >> (2 * i)) & 1u) << i;
-    return r;
-}
-constexpr Rc2Table make_rc2() {
-    constexpr uint64_t rc[24] = LCB_KECCAK_RC_INIT;
-    Rc2Table t{};
-    for (int i = 0; i < 24; ++i) { t.v[0][i] = cx_even_bits(rc[i]); t.v[1][i] = cx_even_bits(rc[i] >> 1); }
-    return t;
-}
-static __constant__ Rc2Table c_keccak_rc2 = make_rc2();
 
 // il[delta][t] = (even, odd) halves of the little-endian 64-bit word msg[8 t + delta .. 8 t + delta + 8), for every t
 // whose 8 bytes lie inside the message; grid.y = delta.
@@ -473,9 +571,32 @@ static cudaError_t launch_sampler_generic(const SamplerArgs& a, cudaStream_t st)
     return cudaGetLastError();
 }
 
+// Streams x polynomials-per-stream up to which the cooperative kernel (one block per stream) is used: below about one
+// block per SM its latency advantage (the sponge alone instead of sponge + decoder on one thread) is what counts.
+bool sampler_coop_applies(const SamplerArgs& a, int num_sms) {
+    if (const char* env = getenv("LCB_SAMPLER_COOP")) { if (!atoi(env)) return false; }
+    const int64_t bits = (int64_t)LOGD + (int64_t)(a.wt - 1) * a.idx_bits + (int64_t)a.wt * (1 + a.mag_bits) + a.pad_bits;
+    return a.d == D && !a.wide && !a.stream_salts && !a.shared_msg && a.n <= num_sms && a.vec_len >= 2 &&
+           a.vec_len <= COOP_MAX_POLYS && (bits / 8) % 8 == 0 && a.coop_digest != nullptr;     // chunks start on a 64-bit sponge word
+}
+
+static cudaError_t launch_sampler_coop(const SamplerArgs& a, cudaStream_t st) {
+    const int64_t bits = (int64_t)LOGD + (int64_t)(a.wt - 1) * a.idx_bits + (int64_t)a.wt * (1 + a.mag_bits) + a.pad_bits;
+    const int words_per_poly = (int)(bits / 32);
+    const int pieces = weight_pieces(a.idx_bits, a.mag_bits);
+    if (pieces > WT_K || a.idx_stride < a.n * a.vec_len) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)(RING_WORDS + 8) * a.vec_len * 4 + 2 * 260 * 4 + (size_t)(257 * pieces + 15) / 16 * 16;
+    cudaError_t e = cudaFuncSetAttribute(k_sampler_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_sampler_coop<<<(unsigned)a.n, 32 * coop_warps(a.vec_len), smem, st>>>(a, a.coop_digest, sampler_coop_digest_words(a.vec_len, words_per_poly),
+                                                                     words_per_poly);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st) {
     if (a.n <= 0) return cudaSuccess;
     if (a.d != D || a.wide || a.stream_salts || a.shared_msg) return launch_sampler_generic(a, st);
+    if (a.coop_digest) return launch_sampler_coop(a, st);
     static int num_sms = 0;
     if (!num_sms) {
         int dev = 0;

@@ -180,9 +180,44 @@ __device__ __forceinline__ uint32_t barrett_small(uint32_t x, uint32_t mu, uint3
 //   pad bits      : skipped.
 // Indices are parked in a global scratch column until their coefficients arrive (the coefficients of a
 // polynomial are drawn after ALL its indices).
-template <typename Geo, typename IdxT, typename Emit>
+// Where the digest words come from: the stream's own sponge (the normal case: squeeze fused with the decoder, the
+// digest never leaves the SM), or a buffer that ANOTHER warp fills (k_sampler_coop: one producer runs the sponge, one
+// consumer warp per polynomial decodes behind it - the low-latency form for a handful of streams).
+struct SpongeFeed {
+    static constexpr bool kBuffered = false;
+};
+struct BufferFeed {
+    static constexpr bool kBuffered = true;
+    const uint32_t* words;               // digest as (even-bit half, odd-bit half) pairs per 64-bit sponge word - the
+                                         // producer's registers as they are; this polynomial's first pair at [0]
+    const volatile unsigned* produced;   // 32-bit stream words the producer has published so far (shared memory)
+    unsigned base;                       // index of words[0] in the producer's stream
+    unsigned next;                       // words consumed so far
+    static __device__ __forceinline__ uint32_t spread16(uint32_t x) {      // bit i of the low half -> bit 2 i
+        x &= 0xFFFFu;
+        x = (x | (x << 8)) & 0x00FF00FFu;
+        x = (x | (x << 4)) & 0x0F0F0F0Fu;
+        x = (x | (x << 2)) & 0x33333333u;
+        return (x | (x << 1)) & 0x55555555u;
+    }
+    __device__ __forceinline__ void refill(uint32_t* col, int P) {
+        const unsigned need = base + next + RATE_WORDS;
+        while (*produced < need) __nanosleep(100);
+        __threadfence_block();
+#pragma unroll
+        for (int i = 0; i < RATE_WORDS / 2; ++i) {
+            // the interleaving the producer skipped: 64-bit word = even bits from one half, odd bits from the other
+            const uint2 h = __ldcg(reinterpret_cast<const uint2*>(words + next) + i);
+            col[(2 * i) * P] = __byte_perm(spread16(h.x) | (spread16(h.y) << 1), 0, 0x0123);
+            col[(2 * i + 1) * P] = __byte_perm(spread16(h.x >> 16) | (spread16(h.y >> 16) << 1), 0, 0x0123);
+        }
+        next += RATE_WORDS;
+    }
+};
+
+template <typename Geo, typename IdxT, typename Feed, typename Emit>
 __device__ __forceinline__ void sample_stream_t(const Geo& geo, const DecodeParams& dp, const InputView& iv,
-                                                const StreamColsT<IdxT>& sc, Emit&& emit) {
+                                                const StreamColsT<IdxT>& sc, Feed& feed, Emit&& emit) {
     const int P = sc.pitch;
     const int64_t in_total = iv.total();
     // the pad byte always needs room; 32-bit division whenever the input is shorter than 4 GiB
@@ -199,23 +234,27 @@ __device__ __forceinline__ void sample_stream_t(const Geo& geo, const DecodePara
             const int drop = rp >> 5, keep = nw - drop;          // keep <= RING_EXTRA
             for (int i = 0; i < keep; ++i) sc.ring[i * P] = sc.ring[(drop + i) * P];
             rp -= 32 * drop;
-            do {
-                if (in_blk < in_blocks) {
-                    // the not-yet-valid part of the window doubles as staging for the input block
-                    iv.load_block(in_blk, in_total, in_last, sc.ring + keep * P, P);
+            if constexpr (Feed::kBuffered) {
+                feed.refill(sc.ring + keep * P, P);
+            } else {
+                do {
+                    if (in_blk < in_blocks) {
+                        // the not-yet-valid part of the window doubles as staging for the input block
+                        iv.load_block(in_blk, in_total, in_last, sc.ring + keep * P, P);
 #pragma unroll
-                    for (int i = 0; i < 17; ++i) {
-                        s.lo[i] ^= sc.ring[(keep + 2 * i) * P];
-                        s.hi[i] ^= sc.ring[(keep + 2 * i + 1) * P];
+                        for (int i = 0; i < 17; ++i) {
+                            s.lo[i] ^= sc.ring[(keep + 2 * i) * P];
+                            s.hi[i] ^= sc.ring[(keep + 2 * i + 1) * P];
+                        }
+                        ++in_blk;
                     }
-                    ++in_blk;
-                }
-                keccak_f1600(s, c_keccak_rc);
-            } while (in_blk < in_blocks);
+                    keccak_f1600(s, c_keccak_rc);
+                } while (in_blk < in_blocks);
 #pragma unroll
-            for (int i = 0; i < 17; ++i) {
-                sc.ring[(keep + 2 * i) * P] = __byte_perm(s.lo[i], 0, 0x0123);
-                sc.ring[(keep + 2 * i + 1) * P] = __byte_perm(s.hi[i], 0, 0x0123);
+                for (int i = 0; i < 17; ++i) {
+                    sc.ring[(keep + 2 * i) * P] = __byte_perm(s.lo[i], 0, 0x0123);
+                    sc.ring[(keep + 2 * i + 1) * P] = __byte_perm(s.hi[i], 0, 0x0123);
+                }
             }
             nw = keep + RATE_WORDS;
         }
@@ -357,7 +396,8 @@ __device__ __forceinline__ void sample_stream_t(const Geo& geo, const DecodePara
 
 template <typename Emit>
 __device__ __forceinline__ void sample_stream(const DecodeParams& dp, const InputView& iv, const StreamCols& sc, Emit&& emit) {
-    sample_stream_t<Geo256, uint8_t>(Geo256{}, dp, iv, sc, static_cast<Emit&&>(emit));
+    SpongeFeed feed;
+    sample_stream_t<Geo256, uint8_t>(Geo256{}, dp, iv, sc, feed, static_cast<Emit&&>(emit));
 }
 
 }  // namespace lcb

@@ -175,8 +175,10 @@ def test_ntt_any_int16_input(engines):
 
 
 # ------------------------------------------------------------------------------------------- LM-OTS
+@pytest.mark.parametrize('coop', ['1', '0'])          # few streams: cooperative low-latency sampler on / off
 @pytest.mark.parametrize('secpar', [128, 256])
-def test_lm_golden(engines, golden, secpar):
+def test_lm_golden(engines, golden, monkeypatch, secpar, coop):
+    monkeypatch.setenv('LCB_SAMPLER_COOP', coop)
     arrays, meta = golden
     e = engines[secpar]
     m = meta['cases'][str(secpar)]
@@ -352,8 +354,10 @@ def test_agg_coefs_vs_hashlib(engines, monkeypatch, n, first, msg_len, lanes):
 
 
 # ------------------------------------------------------------------------------------------- adaptor
+@pytest.mark.parametrize('coop', ['1', '0'])
 @pytest.mark.parametrize('secpar', [128, 256])
-def test_adaptor_golden(engines, golden, secpar):
+def test_adaptor_golden(engines, golden, monkeypatch, secpar, coop):
+    monkeypatch.setenv('LCB_SAMPLER_COOP', coop)
     arrays, meta = golden
     e = engines[secpar]
     sch = scheme(secpar)
@@ -569,3 +573,24 @@ def test_other_ntt_friendly_moduli_vs_c_oracle(q, l):
         assert np.array_equal(e.poly_mul(a, b), np.stack([negacyclic_mul(x, y, q) for x, y in zip(a, b)]).astype(np.int16))
     finally:
         e.close()
+
+
+@pytest.mark.parametrize('secpar', [128, 256])
+@pytest.mark.parametrize('n', [1, 2, 37, 74, 75])
+def test_cooperative_sampler_equals_one_thread_per_stream(engines, monkeypatch, secpar, n):
+    """k_sampler_coop (one block per stream: a lane-pair sponge feeding one decoder warp per polynomial) against
+    k_sampler on the same seeds: keys (paired mode: 2 n streams, up to one block per SM), witnesses and a generic
+    hash2polynomialvector call, including seeds whose salt || seed crosses a rate block."""
+    e = engines[secpar]
+    sch = scheme(secpar)
+    seeds = [bin(3 ** (j + 5))[2:].zfill(secpar)[-secpar:] + '01' * (j % 4) for j in range(n)]
+    out = {}
+    for coop in ('0', '1'):
+        monkeypatch.setenv('LCB_SAMPLER_COOP', coop)
+        keys = e.lm_keygen(sch, seeds)
+        wit = e.witgen(sch, seeds)
+        dense, pairs = e.hash2polyvec('COOP', seeds, 45, 256, 5, want_pairs=True)
+        sparse, sp = e.hash2polyvec('COOP', seeds, 7, 33, 3, want_pairs=True)
+        out[coop] = keys + wit + (dense, pairs, sparse, sp)
+    for a, b in zip(out['0'], out['1']):
+        assert np.array_equal(a, b)
