@@ -14,6 +14,7 @@
 // single reduction per output coefficient.  Grids are persistent: (#SM x resident blocks) blocks
 // striding over the batch.
 #include "engine.h"
+#include "sampler_device.cuh"
 
 namespace lcb {
 
@@ -89,6 +90,22 @@ __device__ __forceinline__ void load_pairs_raw(int (&x)[EPT], const int16_t* __r
     for (int e = lane; e < wt; e += LANES) {
         uint32_t pr = __ldg(pp + e);
         int idx = (int)(pr & 0xFFu);
+        xb[XROW * (idx >> 4) + (idx & 15)] = (uint32_t)(int)(int16_t)(pr >> 16);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) x[j] = (int)xb[XROW * j + lane];
+    __syncwarp();
+}
+
+// the same from a row of (index | coefficient << 16) words in SHARED memory (k_verify's fused form)
+__device__ __forceinline__ void load_pairs_raw_sh(int (&x)[EPT], const uint32_t* prow, int wt, uint32_t* xb, int lane) {
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) xb[XROW * j + lane] = 0;
+    __syncwarp();
+    for (int e = lane; e < wt; e += LANES) {
+        const uint32_t pr = *reinterpret_cast<const volatile uint32_t*>(prow + e);
+        const int idx = (int)(pr & 0xFFu);
         xb[XROW * (idx >> 4) + (idx & 15)] = (uint32_t)(int)(int16_t)(pr >> 16);
     }
     __syncwarp();
@@ -441,7 +458,19 @@ __device__ __forceinline__ void load_u14x16(uint32_t (&r)[EPT], const uint32_t* 
 // SIG_BITS / VK_BITS: 0 = int16 coefficients / uint16 slots; otherwise the inputs are rows of the packed wire
 // format (wire.cu): signatures SIG_BITS bits per coefficient with bias sig_bias, keys VK_BITS (14) bits per slot.
 // The packed rows ride through the same cp.async stage buffers and are expanded on the way into registers.
-template <bool CHECK_WT, int SIG_BITS, int VK_BITS>
+// FUSED: the challenges are hashed INSIDE the kernel.  A block is three transform warps (six half-warps = six items
+// per block iteration) and ONE sponge warp: its 32 lanes run make_signature_challenge's SHAKE256 + decoder
+// (sampler_device.cuh, one stream per lane) for the items of the next FUSED_IPR block iterations and leave the
+// (index, coefficient) pairs in a two-round ring in shared memory; the transform warps pick theirs up after the l
+// signature rows.  The sponge is pure ALU-pipe work at one instruction every two cycles, the transform warps leave
+// about a quarter of their scheduler's issue slots idle (latency), so the fourth warp of each scheduler hashes in the
+// gaps: the challenge sampler's 1.75 ms per 2^20 disappear into k_verify instead of running before it.  Which warp
+// of the block hashes comes from a per-SM arrival counter, so that the four resident blocks of an SM put their
+// sponge warps on four different schedulers (warp id mod 4).
+constexpr int FUSED_IPR = 5;                 // block iterations per sponge round: 5 x 6 = 30 of the 32 lanes busy
+constexpr int FUSED_MAX_WT = 64;             // parked indices per stream (ch_wt is 20 / 50 in the shipped sets)
+
+template <bool CHECK_WT, int SIG_BITS, int VK_BITS, bool FUSED>
 __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageConst sc, StageConstF scf, const NttTables* __restrict__ tab,
                                                 const uint32_t* __restrict__ a_hat_g, int l,
                                                 const int16_t* __restrict__ vec_coef,
@@ -449,18 +478,96 @@ __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageCons
                                                 const int16_t* __restrict__ ch_pairs, int ch_wt,
                                                 const uint16_t* __restrict__ rhs_only,
                                                 const uint16_t* __restrict__ extra_rhs, int64_t n, int bd, int wt,
-                                                int sig_bias, uint8_t* __restrict__ verdict) {
+                                                int sig_bias, uint8_t* __restrict__ verdict, FusedCh fc,
+                                                unsigned* __restrict__ sm_slots) {
     constexpr int ROW_BYTES = SIG_BITS ? 32 * SIG_BITS : D * 2;
+    constexpr int HW = FUSED ? HWB - 2 : HWB;          // half-warps (items) per block iteration
+    constexpr int TWARPS = HW / 2;                     // transform warps
     extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ unsigned s_arrival, s_sched[RBS / 32];
     uint32_t* a_hat = smem;
     uint32_t* xbuf = smem + l * AROW;
-    unsigned char* stage_base = reinterpret_cast<unsigned char*>(xbuf + (RBS / 32) * XWARP);
+    unsigned char* stage_base = reinterpret_cast<unsigned char*>(xbuf + TWARPS * XWARP);
+    uint4* twtab = reinterpret_cast<uint4*>(stage_base + HW * STAGE_HALF_BYTES);
+    // fused extras: sampler window + bitmap columns, modulus tables, parked indices, pair ring, progress words
+    uint32_t* f_ring = reinterpret_cast<uint32_t*>(twtab + LANES * TW_ROW);       // [RING_WORDS][32]
+    uint32_t* f_bmap = f_ring + RING_WORDS * 32;                                  // [8][32] (directly after the ring)
+    uint32_t* f_mutab = f_bmap + 8 * 32;                                          // [260]
+    uint32_t* f_r16tab = f_mutab + 260;                                           // [260]
+    volatile unsigned* f_ctrl = f_r16tab + 260;                                   // [4]: rounds produced, iterations consumed by each transform warp
+    const int f_pitch = ch_wt | 1;                                                // odd row pitch: conflict-free both ways
+    uint32_t* f_pairs = f_r16tab + 264;                                           // [2][32][f_pitch]
+    uint8_t* f_idx = reinterpret_cast<uint8_t*>(f_pairs + 2 * 32 * f_pitch);      // [FUSED_MAX_WT][32]
+    uint8_t* f_wtab = f_idx + FUSED_MAX_WT * 32;                                  // [257][pieces]
+    if (FUSED) {
+        if ((threadIdx.x & 31) == 0) {
+            unsigned wslot;                                 // hardware warp slot: its scheduler is slot mod 4
+            asm volatile("mov.u32 %0, %%warpid;" : "=r"(wslot));
+            s_sched[threadIdx.x >> 5] = wslot & 3u;
+        }
+        if (threadIdx.x == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            s_arrival = atomicAdd(sm_slots + (smid & 1023u), 1u) & 3u;
+            f_ctrl[0] = 0;
+            f_ctrl[1] = 0;
+            f_ctrl[2] = 0;
+            f_ctrl[3] = 0;
+        }
+        fill_mod_tables(f_mutab, f_r16tab, ch_wt);
+        fill_weight_table(f_wtab, ch_wt, fc.bd, weight_pieces(fc.idx_bits, fc.mag_bits));
+    }
     copy_a_hat(a_hat, a_hat_g, l);
-    const HalfWarp h = half_warp(xbuf);
-    unsigned char* stage = stage_base + h.slot * STAGE_HALF_BYTES;
-    uint4* twtab = reinterpret_cast<uint4*>(stage_base + HWB * STAGE_HALF_BYTES);
+    HalfWarp h = half_warp(xbuf);
+    // the sponge warp of the j-th block to arrive on this SM is the one on scheduler j (B200 places warp w of that block
+    // on slot 4 j + (w + j) mod 4, tools/warpid_probe.cu); any warp will do if the slots ever look different
+    int kw = -1;
+    if (FUSED) {
+        kw = (int)s_arrival;
+#pragma unroll
+        for (int w = RBS / 32 - 1; w >= 0; --w)
+            if (s_sched[w] == s_arrival) kw = w;
+    }
+    if (FUSED) {
+        const int warp = threadIdx.x >> 5;
+        const int tw = warp - (warp > kw ? 1 : 0);          // ordinal among the transform warps
+        h.slot = 2 * tw + ((threadIdx.x >> 4) & 1);
+        h.xb = xbuf + (tw < TWARPS ? tw : 0) * XWARP + ((threadIdx.x >> 4) & 1) * XHALF;
+    }
+    unsigned char* stage = stage_base + (h.slot < HW ? h.slot : 0) * STAGE_HALF_BYTES;
     fill_tw_shared(twtab, tab);
     const LaneTwFShared twf{twtab + h.lane * TW_ROW};
+    const int64_t first = (int64_t)blockIdx.x * HW, stride = (int64_t)gridDim.x * HW;
+    const int64_t trips = first < n ? (n - first + stride - 1) / stride : 0;   // uniform over the block
+    if (FUSED && (int)(threadIdx.x >> 5) == kw) {
+        // ---- the sponge warp: no block-wide barrier below this point
+        const int lane32 = threadIdx.x & 31;
+        const int sub = lane32 / HW, fslot = lane32 - sub * HW;              // lanes 30, 31 idle along
+        const int pieces = weight_pieces(fc.idx_bits, fc.mag_bits);
+        const DecodeParams dp{fc.bd, ch_wt, 1, fc.idx_bits, fc.mag_bits, fc.pad_bits};
+        const StreamCols scol{f_ring + lane32, f_bmap + lane32, 32, f_mutab, f_r16tab, f_wtab, pieces, f_idx + lane32, 32};
+        const int64_t rounds = (trips + FUSED_IPR - 1) / FUSED_IPR;
+        for (int64_t r = 0; r < rounds; ++r) {
+            const int64_t it = r * FUSED_IPR + sub;
+            const int64_t raw = first + it * stride + fslot;
+            const int64_t item = (sub < FUSED_IPR && it < trips && raw < n) ? raw : n - 1;
+            const int64_t mb = __ldg(fc.off + item), me = __ldg(fc.off + item + 1);
+            if (r >= 2) {           // the ring holds two rounds: round r - 2 must have been picked up
+                const unsigned need = (unsigned)((r - 1) * FUSED_IPR);      // <= trips: round r exists
+                while (f_ctrl[1] < need || f_ctrl[2] < need || f_ctrl[3] < need) __nanosleep(200);
+            }
+            __syncwarp();
+            uint32_t* prow = f_pairs + ((int)(r & 1) * 32 + lane32) * f_pitch;
+            const InputView iv{reinterpret_cast<const uint32_t*>(fc.salt), fc.salt_len, fc.msgs + mb, me - mb};
+            sample_stream(dp, iv, scol, [&](int, int e, int idx, int coef) {
+                prow[e] = (uint32_t)idx | ((uint32_t)(uint16_t)(int16_t)coef << 16);
+            });
+            __threadfence_block();
+            __syncwarp();
+            if (lane32 == 0) f_ctrl[0] = (unsigned)(r + 1);
+        }
+        return;
+    }
     // The FP32-assisted transform returns biased values (r + FP_BIAS); the row-vector product then carries
     // FP_BIAS * sum_i a_hat[i][slot], removed once per slot before the comparison.
     uint32_t corr[EPT];
@@ -476,9 +583,7 @@ __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageCons
         for (int k = 0; k < EPT; ++k) corr[k] = mulmod_full(barrett_full(colsum[k], m), m.bias_mod_q, m);
     }
     constexpr bool check_wt = CHECK_WT;
-
-    const int64_t first = (int64_t)blockIdx.x * HWB, stride = (int64_t)gridDim.x * HWB;
-    const int64_t trips = first < n ? (n - first + stride - 1) / stride : 0;   // uniform over the block
+    unsigned f_round = 0, f_sub = 0;            // FUSED: sponge round / iteration within it of the current `it`
     // work list of this half-warp: polynomial i of item(it), it = 0..trips-1; the prefetch cursor runs 2 ahead
     int64_t pf_it = 0;
     int pf_i = 0;
@@ -562,7 +667,16 @@ __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageCons
         if (vk_ntt) {
             uint32_t c[EPT], vl[EPT];
             int cx[EPT];
-            load_pairs_raw(cx, ch_pairs + item * ch_wt * 2, ch_wt, h.xb, h.lane);
+            if (FUSED) {
+                while (f_ctrl[0] <= f_round) __nanosleep(100);
+                __threadfence_block();
+                load_pairs_raw_sh(cx, f_pairs + ((f_round & 1u) * 32 + f_sub * HW + h.slot) * f_pitch, ch_wt, h.xb, h.lane);
+                __syncwarp();
+                if ((threadIdx.x & 31) == 0) f_ctrl[1 + (h.slot >> 1)] = (unsigned)it + 1u;      // this warp is done with iteration `it`
+                if (++f_sub == FUSED_IPR) { f_sub = 0; ++f_round; }
+            } else {
+                load_pairs_raw(cx, ch_pairs + item * ch_wt * 2, ch_wt, h.xb, h.lane);
+            }
             ntt_fwd_256_fp(cx, c, m, scf, twf, h.xb, h.lane);
             if (VK_BITS == 14) {
                 const uint32_t* vp = reinterpret_cast<const uint32_t*>(vk_ntt) + item * (2 * 112) + 7 * h.lane;
@@ -792,6 +906,13 @@ inline unsigned persistent_grid(int64_t items, int per_block, int num_sms, int r
 
 inline size_t ring_smem(int l) { return (size_t)l * AROW * 4 + (size_t)(RBS / 32) * XWARP * 4; }
 inline size_t verify_smem(int l) { return ring_smem(l) + (size_t)HWB * STAGE_HALF_BYTES + (size_t)TW_BYTES; }
+// fused form: three transform warps, six stage slots, then the sponge warp's scratch (same order as in the kernel)
+inline size_t verify_fused_smem(int l, int ch_wt, int pieces) {
+    const size_t base = (size_t)l * AROW * 4 + (size_t)(HWB - 2) / 2 * XWARP * 4 + (size_t)(HWB - 2) * STAGE_HALF_BYTES + (size_t)TW_BYTES;
+    const size_t extra = (size_t)(RING_WORDS + 8) * 32 * 4 + 2 * 260 * 4 + 16 + (size_t)2 * 32 * (ch_wt | 1) * 4 +
+                         (size_t)FUSED_MAX_WT * 32 + (size_t)257 * pieces;
+    return (base + extra + 15) / 16 * 16;
+}
 
 template <typename K>
 cudaError_t allow_smem(K kernel, size_t smem) {
@@ -855,13 +976,39 @@ cudaError_t launch_verify_t(const RingCtx& c, const void* vec, const void* vk, c
                             uint8_t* verdict, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     size_t smem = verify_smem(c.l);
-    auto kern = wt < D ? k_verify<true, SIG_BITS, VK_BITS> : k_verify<false, SIG_BITS, VK_BITS>;
+    auto kern = wt < D ? k_verify<true, SIG_BITS, VK_BITS, false> : k_verify<false, SIG_BITS, VK_BITS, false>;
     cudaError_t e = allow_smem(kern, smem);
     if (e != cudaSuccess) return e;
     unsigned grid = persistent_grid(n, HWB, c.num_sms, resident_blocks(kern, RBS, smem));
     kern<<<grid, RBS, smem, st>>>(c.m, c.sc, c.scf, c.tab, c.a_hat, c.l, static_cast<const int16_t*>(vec),
                                   static_cast<const uint16_t*>(vk), ch_pairs, ch_wt, rhs_only, extra_rhs, n, bd, wt,
-                                  sig_bias, verdict);
+                                  sig_bias, verdict, FusedCh{}, nullptr);
+    return cudaGetLastError();
+}
+
+// Fused form: worth it when the batch fills the persistent grid several times over (the sponge warp runs two rounds
+// = ten block iterations ahead) and four blocks stay resident.
+bool verify_fused_applies(const RingCtx& c, int ch_wt, int idx_bits, int mag_bits, int64_t n, int wt) {
+    if (wt < D || ch_wt < 1 || ch_wt > FUSED_MAX_WT || c.sm_slots == nullptr) return false;
+    if (n < (int64_t)c.num_sms * VERIFY_BLOCKS * (HWB - 2) * 4 * FUSED_IPR) return false;
+    const size_t smem = verify_fused_smem(c.l, ch_wt, weight_pieces(idx_bits, mag_bits));
+    auto kern = k_verify<false, 0, 0, true>;
+    if (allow_smem(kern, smem) != cudaSuccess) return false;
+    return resident_blocks(kern, RBS, smem) >= VERIFY_BLOCKS;
+}
+
+cudaError_t launch_verify_fused(const RingCtx& c, const FusedCh& fc, const int16_t* vec_coef, const uint16_t* vk_ntt,
+                                int ch_wt, const uint16_t* extra_rhs, int64_t n, int bd, int wt, uint8_t* verdict,
+                                cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    if (wt < D || ch_wt > FUSED_MAX_WT || !vk_ntt || !c.sm_slots) return cudaErrorNotSupported;
+    const size_t smem = verify_fused_smem(c.l, ch_wt, weight_pieces(fc.idx_bits, fc.mag_bits));
+    auto kern = k_verify<false, 0, 0, true>;
+    cudaError_t e = allow_smem(kern, smem);
+    if (e != cudaSuccess) return e;
+    unsigned grid = persistent_grid(n, HWB - 2, c.num_sms, resident_blocks(kern, RBS, smem));
+    kern<<<grid, RBS, smem, st>>>(c.m, c.sc, c.scf, c.tab, c.a_hat, c.l, vec_coef, vk_ntt, nullptr, ch_wt, nullptr,
+                                  extra_rhs, n, bd, wt, 0, verdict, fc, c.sm_slots);
     return cudaGetLastError();
 }
 

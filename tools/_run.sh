@@ -1,6 +1,5 @@
 set -x
-nvidia-smi -L | wc -l
-python -m pytest tests/test_gpu_multi.py tests/test_gpu_mctx.py -q -x 2>&1 | tail -4
-for N in 8 4; do
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N > gpurun_out/bench_r2_${N}gpu.json 2> gpurun_out/bench_r2_${N}gpu.err; echo rc=$?; tail -2 gpurun_out/bench_r2_${N}gpu.err
-done
+timeout 300 python tools/verify_timing.py 128 20 10 2>&1 | tail -4
+timeout 300 python tools/verify_timing.py 128 17 10 2>&1 | tail -2
+LCB_VERIFY_FUSED=1 timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_verify -s 3 -c 1 -o gpurun_out/prof_r2_verify_fused_a python tools/verify_timing.py 128 18 2 > gpurun_out/ncu_fused.log 2>&1
+tail -3 gpurun_out/ncu_fused.log
