@@ -375,7 +375,7 @@ bool fused_verify(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* d_msg, const
     if (!env || env[0] != '1') return false;
     SamplerArgs a{};
     if (fill_sampler(c, a, salt_of(sch->ch_salt).c_str(), nullptr, sch->ch_bd, sch->ch_wt, 1) != LCB_OK) return false;
-    if (!verify_fused_applies(c->ring, sch->ch_wt, a.idx_bits, a.mag_bits, INT64_MAX, wt)) return false;
+    if (!verify_fused_applies(c->ring, sch->ch_bd, sch->ch_wt, a.idx_bits, a.mag_bits, INT64_MAX, wt)) return false;
     fc.msgs = d_msg;
     fc.off = d_off;
     std::memcpy(fc.salt, a.salt, sizeof(fc.salt));
@@ -615,6 +615,16 @@ int lcb_ctx_create(lcb_ctx** out, int device, int secpar, int q, int d, int l) {
     m.bias_mod_q = FP_BIAS % uq;
     m.z1c = (int32_t)t.w[1] > (int32_t)m.half ? (int32_t)t.w[1] - (int32_t)uq : (int32_t)t.w[1];
     m.k1 = (uint32_t)((((1ull << 30) + (1ull << 15) + uq - 1) / uq) * uq);
+    {
+        uint64_t inv = uq;                                   // Newton: correct to 3 bits, doubled five times
+        for (int it = 0; it < 6; ++it) inv *= 2 - (uint64_t)uq * inv;
+        m.qinv_lo = (uint32_t)inv;
+        m.qinv_hi = (uint32_t)(inv >> 32);
+        const uint64_t lim = ~0ull / uq;
+        m.dlim_lo = (uint32_t)lim;
+        m.dlim_hi = (uint32_t)(lim >> 32);
+        m.kq18 = (((1u << 18) + uq - 1) / uq) * uq;
+    }
     for (int k = 0; k < 16; ++k) {
         c->ring.sc.w[k] = t.w[k];
         c->ring.sc.ws[k] = t.ws[k];

@@ -153,7 +153,7 @@ cudaError_t launch_verify(const RingCtx& c, const int16_t* vec_coef, const uint1
 cudaError_t launch_verify_fused(const RingCtx& c, const FusedCh& fc, const int16_t* vec_coef, const uint16_t* vk_ntt,
                                 int ch_wt, const uint16_t* extra_rhs, int64_t n, int bd, int wt, uint8_t* verdict,
                                 cudaStream_t st);
-bool verify_fused_applies(const RingCtx& c, int ch_wt, int idx_bits, int mag_bits, int64_t n, int wt);
+bool verify_fused_applies(const RingCtx& c, int ch_bd, int ch_wt, int idx_bits, int mag_bits, int64_t n, int wt);
 // the same on packed wire-format rows (sig_bits/vk_bits = 11/14 or 13/16); cudaErrorNotSupported otherwise
 cudaError_t launch_verify_packed(const RingCtx& c, const uint8_t* sig_packed, int sig_bits, int sig_bias,
                                  const uint8_t* vk_packed, int vk_bits, const int16_t* ch_pairs, int ch_wt, int64_t n,
