@@ -28,7 +28,6 @@ struct lcb_ctx {
     uint32_t* d_gen_tab = nullptr;       // generic twiddle tables: w, ws, iw, iws [d] each, pw [2d]
     NttTables* d_tab = nullptr;
     uint32_t* d_a_hat = nullptr;
-    unsigned* d_sm_slots = nullptr;      // per-SM arrival counters of k_verify's fused form
     bool has_key_ch = false;
     std::string last_error;
     int64_t launches = 0;
@@ -78,11 +77,10 @@ int fail_cuda(lcb_ctx* c, cudaError_t e, const char* what) {
 constexpr int64_t kPipeChunk = 1 << 17;
 
 enum KernelId { K_SAMPLER = 0, K_SHAKE, K_NTT_FWD, K_NTT_INV, K_POLY_MUL, K_MATVEC, K_SIGN, K_VERIFY, K_ADDSUB,
-                K_AGG_COEFS, K_AGG_PARTIAL, K_AGG_FINISH, K_AGGV_PARTIAL, K_AGGV_FINISH, K_PACK, K_UNPACK, K_VERIFY_FUSED,
-                K_COUNT };
+                K_AGG_COEFS, K_AGG_PARTIAL, K_AGG_FINISH, K_AGGV_PARTIAL, K_AGGV_FINISH, K_PACK, K_UNPACK, K_COUNT };
 const char* const kKernelNames[K_COUNT] = {"sampler", "shake256", "ntt_fwd", "ntt_inv", "poly_mul", "matvec", "sign",
                                            "verify", "vec_addsub", "agg_coefs", "agg_partial", "agg_finish",
-                                           "aggv_partial", "aggv_finish", "pack", "unpack", "verify_fused"};
+                                           "aggv_partial", "aggv_finish", "pack", "unpack"};
 
 // Launch wrapper: counts the launch and, when profiling is on, brackets it with CUDA events on the
 // ctx stream (resolved lazily in lcb_profile_read).
@@ -365,28 +363,6 @@ int run_challenge(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* d_msg, const
     return LCB_OK;
 }
 
-// k_verify's fused form hashes the challenges itself (ring.cu).  Measured slower than the sampler + k_verify pair so
-// far (the two instruction streams together overflow the SM's 32 KB instruction cache), so it
-// runs only on request: LCB_VERIFY_FUSED=1.
-bool fused_verify(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* d_msg, const int64_t* d_off, int64_t n, int wt,
-                  FusedCh& fc) {
-    if (c->generic || n <= 0) return false;
-    const char* env = std::getenv("LCB_VERIFY_FUSED");
-    if (!env || env[0] != '1') return false;
-    SamplerArgs a{};
-    if (fill_sampler(c, a, salt_of(sch->ch_salt).c_str(), nullptr, sch->ch_bd, sch->ch_wt, 1) != LCB_OK) return false;
-    if (!verify_fused_applies(c->ring, sch->ch_bd, sch->ch_wt, a.idx_bits, a.mag_bits, INT64_MAX, wt)) return false;
-    fc.msgs = d_msg;
-    fc.off = d_off;
-    std::memcpy(fc.salt, a.salt, sizeof(fc.salt));
-    fc.salt_len = a.salt_len;
-    fc.bd = a.bd;
-    fc.idx_bits = a.idx_bits;
-    fc.mag_bits = a.mag_bits;
-    fc.pad_bits = a.pad_bits;
-    return true;
-}
-
 int run_agg_coefs(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* d_agmsg, int64_t agmsg_len, int64_t first,
                   int64_t count, int16_t* d_pairs) {
     SamplerArgs a{};
@@ -638,9 +614,6 @@ int lcb_ctx_create(lcb_ctx** out, int device, int secpar, int q, int d, int l) {
     if ((e = cudaMalloc(&c->d_tab, sizeof(NttTables))) != cudaSuccess) return bail(e, "cudaMalloc tables");
     if ((e = cudaMemcpy(c->d_tab, &t, sizeof(NttTables), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy tables");
     if ((e = cudaMalloc(&c->d_a_hat, (size_t)l * D * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc key_ch");
-    if ((e = cudaMalloc(&c->d_sm_slots, 1024 * sizeof(unsigned))) != cudaSuccess) return bail(e, "cudaMalloc sm slots");
-    if ((e = cudaMemset(c->d_sm_slots, 0, 1024 * sizeof(unsigned))) != cudaSuccess) return bail(e, "cudaMemset sm slots");
-    c->ring.sm_slots = c->d_sm_slots;
     c->ring.tab = c->d_tab;
     c->ring.a_hat = c->d_a_hat;
     c->gen.a_hat = c->d_a_hat;
@@ -657,7 +630,6 @@ int lcb_ctx_destroy(lcb_ctx* c) {
     if (c->d_tab) cudaFree(c->d_tab);
     if (c->d_gen_tab) cudaFree(c->d_gen_tab);
     if (c->d_a_hat) cudaFree(c->d_a_hat);
-    if (c->d_sm_slots) cudaFree(c->d_sm_slots);
     if (c->idx_scratch) cudaFree(c->idx_scratch);
     if (c->il_scratch) cudaFree(c->il_scratch);
     if (c->coop_scratch) cudaFree(c->coop_scratch);
@@ -1058,15 +1030,6 @@ int lcb_lm_verify_batch(lcb_ctx* c, const lcb_scheme* sch, const uint16_t* vk_nt
     for (int64_t first = 0, k = 0; first < n; first += chunk, ++k) {
         const int64_t m = n - first < chunk ? n - first : chunk;
         int16_t* pairs = d_pairs + (size_t)first * sch->ch_wt * 2 * ew(c);
-        FusedCh fc{};
-        if (fused_verify(c, sch, d_msg, d_off + first, m, wt, fc)) {
-            if (piped) CK(c, cudaStreamWaitEvent(c->stream, arrived[k], 0));
-            CK(c, timed(c, K_VERIFY_FUSED, [&] {
-                return launch_verify_fused(c->ring, fc, d_sig + (size_t)first * l * D_, d_vk + (size_t)first * 2 * D_, sch->ch_wt,
-                                           d_st ? d_st + (size_t)first * D_ : nullptr, m, vbd, wt, d_verdict + first, c->stream);
-            }));
-            continue;
-        }
         int st = run_challenge(c, sch, d_msg, d_off + first, m, pairs);
         if (st != LCB_OK) return st;
         if (piped) CK(c, cudaStreamWaitEvent(c->stream, arrived[k], 0));

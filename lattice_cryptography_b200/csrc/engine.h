@@ -119,19 +119,6 @@ struct RingCtx {
     const uint32_t* a_hat;     // device, uint32[l][256]: NTT(key_ch), slot order
     int l;
     int num_sms;
-    unsigned* sm_slots;        // device, [1024] zero-initialised: arrival counter per SM (k_verify's fused form draws the
-                               // position of its sponge warp from it, so that the four blocks of an SM differ)
-};
-
-// Challenge hashing folded into k_verify (one SHAKE256 warp per block beside three transform warps): the sampler
-// arguments of make_signature_challenge for the batch, by value.
-struct FusedCh {
-    const uint8_t* msgs;       // ragged challenge inputs (device)
-    const int64_t* off;        // [n + 1] (device)
-    alignas(8) uint8_t salt[SALT_BYTES];
-    int salt_len;
-    int bd;                    // ch_bd
-    int idx_bits, mag_bits, pad_bits;
 };
 
 cudaError_t launch_ntt_fwd(const RingCtx& c, const int16_t* coef, int64_t npoly, uint16_t* out, cudaStream_t st);
@@ -148,12 +135,6 @@ cudaError_t launch_sign(const RingCtx& c, const uint16_t* sk_ntt, const int16_t*
 cudaError_t launch_verify(const RingCtx& c, const int16_t* vec_coef, const uint16_t* vk_ntt,
                           const int16_t* ch_pairs, int ch_wt, const uint16_t* rhs_only, const uint16_t* extra_rhs,
                           int64_t n, int bd, int wt, uint8_t* verdict, cudaStream_t st);
-// the same with the challenges hashed inside the kernel (d = 256, vf_wt >= d); cudaErrorNotSupported when the shape
-// does not fit (the caller then runs the sampler and launch_verify)
-cudaError_t launch_verify_fused(const RingCtx& c, const FusedCh& fc, const int16_t* vec_coef, const uint16_t* vk_ntt,
-                                int ch_wt, const uint16_t* extra_rhs, int64_t n, int bd, int wt, uint8_t* verdict,
-                                cudaStream_t st);
-bool verify_fused_applies(const RingCtx& c, int ch_bd, int ch_wt, int idx_bits, int mag_bits, int64_t n, int wt);
 // the same on packed wire-format rows (sig_bits/vk_bits = 11/14 or 13/16); cudaErrorNotSupported otherwise
 cudaError_t launch_verify_packed(const RingCtx& c, const uint8_t* sig_packed, int sig_bits, int sig_bias,
                                  const uint8_t* vk_packed, int vk_bits, const int16_t* ch_pairs, int ch_wt, int64_t n,

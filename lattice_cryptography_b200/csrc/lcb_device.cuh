@@ -297,9 +297,7 @@ __device__ __forceinline__ uint32_t fp_mul(uint32_t yb, uint32_t w, float wq, fl
 // Forward transform of RAW centred int16 coefficients with FP32-assisted butterflies.  Values stay biased
 // throughout (inputs x + cq < 2^17, +4q per stage: < 2^17 + 32 q < 2^21 < 2^23); outputs are UNBIASED lazy
 // values < 2^21 PLUS FP_BIAS in layout B (what ntt_fwd_256 would deliver, up to multiples of q, plus the bias).
-// ALU_ADD: the sum of a butterfly as a 3-input IADD3 on the ALU pipe (see ModQ::zero) or, when false, left to ptxas
-// (IMAD.IADD on the FMA-heavy pipe) - for k_verify_fused, where the sponge warp needs the ALU pipe.
-template <bool ALU_ADD = true, typename TW>
+template <typename TW>
 __device__ __forceinline__ void ntt_fwd_256_fp(const int (&x)[EPT], uint32_t (&r)[EPT], const ModQ& m,
                                                const StageConstF& sc, const TW& tw, uint32_t* xb, int lane) {
     // stage 1: only the multiplied operands are biased explicitly; the others take the input offset
@@ -319,7 +317,7 @@ __device__ __forceinline__ void ntt_fwd_256_fp(const int (&x)[EPT], uint32_t (&r
             const int k = (1 << (s - 1)) + (j >> (5 - s));
             const uint32_t t = fp_mul(r[j + len], sc.w[k], sc.wq[k], sc.cst[k], sc.kw[k], m);
             r[j + len] = r[j] + m.q4 - t;
-            r[j] = ALU_ADD ? r[j] + t + m.zero : r[j] + t;
+            r[j] = r[j] + t + m.zero;
         }
     }
     xpose_a_to_b(r, xb, lane);
@@ -336,7 +334,7 @@ __device__ __forceinline__ void ntt_fwd_256_fp(const int (&x)[EPT], uint32_t (&r
             tw.get(k, w_, wq_, cst_, kw_);
             const uint32_t t = fp_mul(r[j + len], w_, wq_, cst_, kw_, m);
             r[j + len] = r[j] + m.q4 - t;
-            r[j] = ALU_ADD ? r[j] + t + m.zero : r[j] + t;
+            r[j] = r[j] + t + m.zero;
         }
     }
     // outputs stay BIASED (r + FP_BIAS): the caller's multiply-accumulate removes the bias once per slot
@@ -462,35 +460,6 @@ struct KeccakRhoPi<25> {
 
 __device__ __forceinline__ void keccak_f1600(KeccakState& s, const uint64_t* __restrict__ rc) {
 #pragma unroll 2
-    for (int round = 0; round < 24; ++round) {
-        uint32_t clo[5], chi[5], rlo[5], rhi[5];
-#pragma unroll
-        for (int x = 0; x < 5; ++x) {
-            clo[x] = lop_xor3(lop_xor3(s.lo[x], s.lo[x + 5], s.lo[x + 10]), s.lo[x + 15], s.lo[x + 20]);
-            chi[x] = lop_xor3(lop_xor3(s.hi[x], s.hi[x + 5], s.hi[x + 10]), s.hi[x + 15], s.hi[x + 20]);
-        }
-#pragma unroll
-        for (int x = 0; x < 5; ++x) rotl64_pair<1>(clo[x], chi[x], rlo[x], rhi[x]);
-        KeccakState b;
-        KeccakRhoPi<0>::run(s, clo, chi, rlo, rhi, b);
-#pragma unroll
-        for (int y = 0; y < 5; ++y)
-#pragma unroll
-            for (int x = 0; x < 5; ++x) {
-                s.lo[x + 5 * y] = lop_chi(b.lo[x + 5 * y], b.lo[(x + 1) % 5 + 5 * y], b.lo[(x + 2) % 5 + 5 * y]);
-                s.hi[x + 5 * y] = lop_chi(b.hi[x + 5 * y], b.hi[(x + 1) % 5 + 5 * y], b.hi[(x + 2) % 5 + 5 * y]);
-            }
-        const uint64_t c = rc[round];
-        s.lo[0] ^= (uint32_t)c;
-        s.hi[0] ^= (uint32_t)(c >> 32);
-    }
-}
-
-// The same permutation with the round loop NOT unrolled (184 instead of 364 instructions of code): for the sponge
-// warp inside k_verify_fused, where the instruction cache is shared with the transform warps and code size is what
-// counts.  Costs one loop branch and one constant load per round.
-__device__ __forceinline__ void keccak_f1600_rolled(KeccakState& s, const uint64_t* __restrict__ rc) {
-#pragma unroll 1
     for (int round = 0; round < 24; ++round) {
         uint32_t clo[5], chi[5], rlo[5], rhi[5];
 #pragma unroll

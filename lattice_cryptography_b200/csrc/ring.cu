@@ -14,7 +14,6 @@
 // single reduction per output coefficient.  Grids are persistent: (#SM x resident blocks) blocks
 // striding over the batch.
 #include "engine.h"
-#include "sampler_device.cuh"
 
 namespace lcb {
 
@@ -90,22 +89,6 @@ __device__ __forceinline__ void load_pairs_raw(int (&x)[EPT], const int16_t* __r
     for (int e = lane; e < wt; e += LANES) {
         uint32_t pr = __ldg(pp + e);
         int idx = (int)(pr & 0xFFu);
-        xb[XROW * (idx >> 4) + (idx & 15)] = (uint32_t)(int)(int16_t)(pr >> 16);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < EPT; ++j) x[j] = (int)xb[XROW * j + lane];
-    __syncwarp();
-}
-
-// the same from a row of (index | coefficient << 16) words in SHARED memory (k_verify_fused)
-__device__ __forceinline__ void load_pairs_raw_sh(int (&x)[EPT], const uint32_t* prow, int wt, uint32_t* xb, int lane) {
-#pragma unroll
-    for (int j = 0; j < EPT; ++j) xb[XROW * j + lane] = 0;
-    __syncwarp();
-    for (int e = lane; e < wt; e += LANES) {
-        const uint32_t pr = *reinterpret_cast<const volatile uint32_t*>(prow + e);
-        const int idx = (int)(pr & 0xFFu);
         xb[XROW * (idx >> 4) + (idx & 15)] = (uint32_t)(int)(int16_t)(pr >> 16);
     }
     __syncwarp();
@@ -609,219 +592,6 @@ __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageCons
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_verify with the challenges hashed INSIDE the kernel (int16 signatures, uint16 keys, vf_wt >= d, ch_bd == 1).
-// A block is three transform warps (six half-warps = six items per block iteration) and ONE sponge warp: its lanes
-// run make_signature_challenge's SHAKE256 + decoder (challenge_stream_lean, one stream per lane) for the items of
-// the next FUSED_IPR block iterations and leave the (index, coefficient) pairs in a two-round ring in shared
-// memory; a transform warp picks its pairs up after the l signature rows.  The sponge is pure ALU-pipe work, the
-// transform warps leave about a quarter of their scheduler's issue slots idle, so the fourth warp of each scheduler
-// hashes in the gaps and the challenge sampler's 1.75 ms per 2^20 disappear into the verify kernel.
-//   * Which warp of a block hashes: B200 places warp w of the j-th block to arrive on an SM on hardware slot
-//     4 j + (w + j) mod 4 and a warp's scheduler is slot mod 4 (tools/warpid_probe.cu), so the block takes j from a
-//     per-SM arrival counter and makes the warp on scheduler j its sponge warp - four resident blocks, four
-//     different schedulers.  Any warp works if the slots ever look different; only the balance would suffer.
-//   * Both instruction streams have to fit the SM's 32 KB instruction cache together (the first version, with
-//     sample_stream and the ordinary k_verify body side by side, hit 85 % and ran 8.9 instead of 6.3 ms): the
-//     challenge transform shares the row loop's copy of the butterflies (it is row l, multiplied by cq2 - vk_left
-//     through the transposition buffer), the final comparison is the divisibility test, the sponge side is
-//     challenge_stream_lean.
-#ifndef LCB_FUSED_ALU_ADD
-#define LCB_FUSED_ALU_ADD false
-#endif
-constexpr bool FUSED_ALU_ADD = LCB_FUSED_ALU_ADD;
-constexpr int FUSED_IPR = 5;                 // block iterations per sponge round: 5 x 6 = 30 of the 32 lanes busy
-constexpr int FUSED_MAX_WT = 64;             // parked indices per stream (ch_wt is 20 / 50 in the shipped sets)
-constexpr int FHW = HWB - 2;                 // half-warps (items) per block iteration
-constexpr int FTW = FHW / 2;                 // transform warps
-
-__global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify_fused(ModQ m, StageConstF scf, const NttTables* __restrict__ tab,
-                                                const uint32_t* __restrict__ a_hat_g, int l,
-                                                const int16_t* __restrict__ vec_coef,
-                                                const uint16_t* __restrict__ vk_ntt, int ch_wt,
-                                                const uint16_t* __restrict__ extra_rhs, int64_t n, int bd,
-                                                uint8_t* __restrict__ verdict, FusedCh fc,
-                                                unsigned* __restrict__ sm_slots) {
-    extern __shared__ __align__(16) uint32_t smem[];
-    __shared__ unsigned s_arrival, s_sched[RBS / 32];
-    uint32_t* a_hat = smem;
-    uint32_t* xbuf = smem + l * AROW;
-    unsigned char* stage_base = reinterpret_cast<unsigned char*>(xbuf + FTW * XWARP);
-    uint4* twtab = reinterpret_cast<uint4*>(stage_base + FHW * STAGE_HALF_BYTES);
-    // sponge warp: window + bitmap columns, modulus tables, progress words, pair ring, parked indices, piece weights
-    uint32_t* f_ring = reinterpret_cast<uint32_t*>(twtab + LANES * TW_ROW);       // [RING_WORDS][32]
-    uint32_t* f_bmap = f_ring + RING_WORDS * 32;                                  // [8][32] (directly after the ring)
-    uint32_t* f_mutab = f_bmap + 8 * 32;                                          // [260]
-    uint32_t* f_r16tab = f_mutab + 260;                                           // [260]
-    volatile unsigned* f_ctrl = f_r16tab + 260;                                   // [4]: rounds produced, iterations consumed by each transform warp
-    const int f_pitch = ch_wt | 1;                                                // odd row pitch: conflict-free both ways
-    uint32_t* f_pairs = f_r16tab + 264;                                           // [2][32][f_pitch]
-    uint8_t* f_idx = reinterpret_cast<uint8_t*>(f_pairs + 2 * 32 * f_pitch);      // [FUSED_MAX_WT][32]
-    uint8_t* f_wtab = f_idx + FUSED_MAX_WT * 32;                                  // [257][pieces]
-    const int pieces = weight_pieces(fc.idx_bits, fc.mag_bits);
-    if ((threadIdx.x & 31) == 0) {
-        unsigned wslot;                                 // hardware warp slot: its scheduler is slot mod 4
-        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wslot));
-        s_sched[threadIdx.x >> 5] = wslot & 3u;
-    }
-    if (threadIdx.x == 0) {
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        s_arrival = atomicAdd(sm_slots + (smid & 1023u), 1u) & 3u;
-        f_ctrl[0] = 0;
-        f_ctrl[1] = 0;
-        f_ctrl[2] = 0;
-        f_ctrl[3] = 0;
-    }
-    fill_mod_tables(f_mutab, f_r16tab, ch_wt);
-    fill_weight_table(f_wtab, ch_wt, 1, pieces);
-    copy_a_hat(a_hat, a_hat_g, l);
-    int kw = (int)s_arrival;
-#pragma unroll
-    for (int w = RBS / 32 - 1; w >= 0; --w)
-        if (s_sched[w] == s_arrival) kw = w;
-    HalfWarp h = half_warp(xbuf);
-    {
-        const int warp = threadIdx.x >> 5;
-        const int tw = warp - (warp > kw ? 1 : 0);          // ordinal among the transform warps
-        h.slot = 2 * tw + ((threadIdx.x >> 4) & 1);
-        h.xb = xbuf + (tw < FTW ? tw : 0) * XWARP + ((threadIdx.x >> 4) & 1) * XHALF;
-    }
-    unsigned char* stage = stage_base + (h.slot < FHW ? h.slot : 0) * STAGE_HALF_BYTES;
-    fill_tw_shared(twtab, tab);
-    const LaneTwFShared twf{twtab + h.lane * TW_ROW};
-    const int64_t first = (int64_t)blockIdx.x * FHW, stride = (int64_t)gridDim.x * FHW;
-    const int64_t trips = first < n ? (n - first + stride - 1) / stride : 0;   // uniform over the block
-    if ((int)(threadIdx.x >> 5) == kw) {
-        // ---- the sponge warp: no block-wide barrier below this point
-        const int lane32 = threadIdx.x & 31;
-        const int sub = lane32 / FHW, fslot = lane32 - sub * FHW;            // lanes 30, 31 idle along
-        const StreamCols scol{f_ring + lane32, f_bmap + lane32, 32, f_mutab, f_r16tab, f_wtab, pieces, f_idx + lane32, 32};
-        const int64_t rounds = (trips + FUSED_IPR - 1) / FUSED_IPR;
-#pragma unroll 1
-        for (int64_t r = 0; r < rounds; ++r) {
-            const int64_t it = r * FUSED_IPR + sub;
-            const int64_t raw = first + it * stride + fslot;
-            const int64_t item = (sub < FUSED_IPR && it < trips && raw < n) ? raw : n - 1;
-            const int64_t mb = __ldg(fc.off + item), me = __ldg(fc.off + item + 1);
-            if (r >= 2) {           // the ring holds two rounds: round r - 2 must have been picked up
-                const unsigned need = (unsigned)((r - 1) * FUSED_IPR);
-                while (f_ctrl[1] < need || f_ctrl[2] < need || f_ctrl[3] < need) __nanosleep(200);
-            }
-            __syncwarp();
-            const InputView iv{reinterpret_cast<const uint32_t*>(fc.salt), fc.salt_len, fc.msgs + mb, me - mb};
-            challenge_stream_lean(ch_wt, fc.idx_bits, fc.mag_bits, iv, scol, f_pairs + ((int)(r & 1) * 32 + lane32) * f_pitch);
-            __threadfence_block();
-            __syncwarp();
-            if (lane32 == 0) f_ctrl[0] = (unsigned)(r + 1);
-        }
-        return;
-    }
-    // bias carried by the FP32-assisted transform, as in k_verify: corr = kq18 - FP_BIAS * sum_i a_hat[i][slot]
-    uint32_t corr[EPT];
-    {
-        uint32_t colsum[EPT];
-#pragma unroll
-        for (int k = 0; k < EPT; ++k) colsum[k] = 0;
-        for (int i = 0; i < l; ++i) {
-#pragma unroll
-            for (int k = 0; k < EPT; ++k) colsum[k] += a_hat[i * AROW + XROW * h.lane + k];
-        }
-#pragma unroll
-        for (int k = 0; k < EPT; ++k) corr[k] = m.kq18 - mulmod_full(barrett_full(colsum[k], m), m.bias_mod_q, m);
-    }
-    unsigned f_round = 0, f_sub = 0;            // sponge round / iteration within it of the current `it`
-    int64_t pf_it = 0;
-    int pf_i = 0;
-    unsigned pf_buf = 0;
-    auto issue = [&]() {
-        if (pf_it < trips) {
-            int64_t it_item = first + pf_it * stride + h.slot;
-            it_item = it_item < n ? it_item : n - 1;
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(vec_coef) + (it_item * l + pf_i) * (D * 2);
-            LCB_CHECK(it_item >= 0 && it_item < n && pf_i < l);
-            unsigned char* dst = stage + pf_buf * (D * 2);
-            cp_async16(dst + 16 * h.lane, src + 16 * h.lane);
-            cp_async16(dst + 256 + 16 * h.lane, src + 256 + 16 * h.lane);
-            if (++pf_i == l) { pf_i = 0; ++pf_it; }
-            pf_buf ^= 1u;
-        }
-        cp_async_commit();
-    };
-    issue();
-    issue();
-    unsigned cur = 0;
-#pragma unroll 1
-    for (int64_t it = 0; it < trips; ++it) {
-        const int64_t raw = first + it * stride + h.slot;
-        const bool live = raw < n;
-        const int64_t item = live ? raw : n - 1;
-        uint64_t acc[EPT];
-#pragma unroll
-        for (int i = 0; i < EPT; ++i) acc[i] = 0;
-        int hi = 0, lo = 0;                     // running max / min coefficient of the whole vector
-#pragma unroll 1
-        for (int i = 0; i <= l; ++i) {          // rows 0 .. l-1: the signature; row l: the challenge
-            int pre[EPT];
-            const uint32_t* mrow;
-            if (i < l) {
-                cp_async_wait<1>();
-                __syncwarp();
-                const unsigned sp = (unsigned)__cvta_generic_to_shared(stage + cur * (D * 2) + 2 * h.lane);
-#pragma unroll
-                for (int j = 0; j < EPT; ++j) asm volatile("ld.shared.s16 %0, [%1];" : "=r"(pre[j]) : "r"(sp + 32 * j));
-                __syncwarp();
-                issue();
-                cur ^= 1u;
-#pragma unroll
-                for (int j = 0; j < EPT; j += 2) {
-                    hi = __vimax3_s32(hi, pre[j], pre[j + 1]);
-                    lo = __vimin3_s32(lo, pre[j], pre[j + 1]);
-                }
-                mrow = a_hat + i * AROW;
-            } else {
-                while (f_ctrl[0] <= f_round) __nanosleep(100);
-                __threadfence_block();
-                load_pairs_raw_sh(pre, f_pairs + ((f_round & 1u) * 32 + f_sub * FHW + h.slot) * f_pitch, ch_wt, h.xb, h.lane);
-                if ((threadIdx.x & 31) == 0) f_ctrl[1 + (h.slot >> 1)] = (unsigned)it + 1u;      // this warp is done with iteration `it`
-                if (++f_sub == FUSED_IPR) { f_sub = 0; ++f_round; }
-                mrow = h.xb;
-            }
-            uint32_t r[EPT];
-            ntt_fwd_256_fp<FUSED_ALU_ADD>(pre, r, m, scf, twf, h.xb, h.lane);
-            if (i == l) {
-                // acc -= c * vk_left: the challenge row is multiplied by cq2 - vk_left, staged in this lane's own
-                // words of the transposition buffer so that mac_row serves both kinds of row
-                uint32_t vl[EPT];
-                load_u16x16(vl, vk_ntt + item * 2 * D + 16 * h.lane);
-#pragma unroll
-                for (int k = 0; k < EPT; ++k) r[k] -= FP_BIAS;
-#pragma unroll
-                for (int g = 0; g < 4; ++g)
-                    *reinterpret_cast<uint4*>(h.xb + XROW * h.lane + 4 * g) =
-                        make_uint4(m.cq2 - vl[4 * g], m.cq2 - vl[4 * g + 1], m.cq2 - vl[4 * g + 2], m.cq2 - vl[4 * g + 3]);
-                __syncwarp();
-            }
-            mac_row(acc, r, mrow, h.lane);
-        }
-        __syncwarp();                           // the transposition buffer is reused by the next item's first row
-        const bool bad = hi > bd || lo < -bd;
-        uint32_t rhs[EPT];
-        load_u16x16(rhs, vk_ntt + item * 2 * D + D + 16 * h.lane);
-        if (extra_rhs) {
-            uint32_t ex[EPT];
-            load_u16x16(ex, extra_rhs + item * D + 16 * h.lane);
-#pragma unroll
-            for (int k = 0; k < EPT; ++k) rhs[k] += ex[k];
-        }
-        bool eq = true;
-#pragma unroll
-        for (int k = 0; k < EPT; ++k) eq &= divisible_by_q(acc[k] + (uint64_t)(corr[k] - rhs[k]), m);
-        const unsigned votes = __ballot_sync(0xFFFFFFFFu, eq && !bad);
-        if (live && h.lane == 0) verdict[item] = (votes & h.mask) == h.mask ? 1 : 0;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 __global__ void k_vec_addsub(ModQ m, const int16_t* __restrict__ a, const int16_t* __restrict__ b, int64_t nelem,
                              int sub, int16_t* __restrict__ out) {
     // 8 coefficients (16 bytes) per thread per step
@@ -1022,13 +792,6 @@ inline unsigned persistent_grid(int64_t items, int per_block, int num_sms, int r
 
 inline size_t ring_smem(int l) { return (size_t)l * AROW * 4 + (size_t)(RBS / 32) * XWARP * 4; }
 inline size_t verify_smem(int l) { return ring_smem(l) + (size_t)HWB * STAGE_HALF_BYTES + (size_t)TW_BYTES; }
-// fused form: three transform warps, six stage slots, then the sponge warp's scratch (same order as in the kernel)
-inline size_t verify_fused_smem(int l, int ch_wt, int pieces) {
-    const size_t base = (size_t)l * AROW * 4 + (size_t)FTW * XWARP * 4 + (size_t)FHW * STAGE_HALF_BYTES + (size_t)TW_BYTES;
-    const size_t extra = (size_t)(RING_WORDS + 8) * 32 * 4 + 2 * 260 * 4 + 16 + (size_t)2 * 32 * (ch_wt | 1) * 4 +
-                         (size_t)FUSED_MAX_WT * 32 + (size_t)257 * pieces;
-    return (base + extra + 15) / 16 * 16;
-}
 
 template <typename K>
 cudaError_t allow_smem(K kernel, size_t smem) {
@@ -1099,30 +862,6 @@ cudaError_t launch_verify_t(const RingCtx& c, const void* vec, const void* vk, c
     kern<<<grid, RBS, smem, st>>>(c.m, c.sc, c.scf, c.tab, c.a_hat, c.l, static_cast<const int16_t*>(vec),
                                   static_cast<const uint16_t*>(vk), ch_pairs, ch_wt, rhs_only, extra_rhs, n, bd, wt,
                                   sig_bias, verdict);
-    return cudaGetLastError();
-}
-
-// Fused form: the batch has to fill the persistent grid several times over (the sponge warp runs two rounds = ten
-// block iterations ahead) and four blocks have to stay resident.
-bool verify_fused_applies(const RingCtx& c, int ch_bd, int ch_wt, int idx_bits, int mag_bits, int64_t n, int wt) {
-    if (wt < D || ch_bd != 1 || ch_wt < 1 || ch_wt > FUSED_MAX_WT || c.sm_slots == nullptr) return false;
-    if (n < (int64_t)c.num_sms * VERIFY_BLOCKS * FHW * 4 * FUSED_IPR) return false;
-    const size_t smem = verify_fused_smem(c.l, ch_wt, weight_pieces(idx_bits, mag_bits));
-    if (allow_smem(k_verify_fused, smem) != cudaSuccess) return false;
-    return resident_blocks(k_verify_fused, RBS, smem) >= VERIFY_BLOCKS;
-}
-
-cudaError_t launch_verify_fused(const RingCtx& c, const FusedCh& fc, const int16_t* vec_coef, const uint16_t* vk_ntt,
-                                int ch_wt, const uint16_t* extra_rhs, int64_t n, int bd, int wt, uint8_t* verdict,
-                                cudaStream_t st) {
-    if (n <= 0) return cudaSuccess;
-    if (wt < D || fc.bd != 1 || ch_wt > FUSED_MAX_WT || !vk_ntt || !c.sm_slots) return cudaErrorNotSupported;
-    const size_t smem = verify_fused_smem(c.l, ch_wt, weight_pieces(fc.idx_bits, fc.mag_bits));
-    cudaError_t e = allow_smem(k_verify_fused, smem);
-    if (e != cudaSuccess) return e;
-    unsigned grid = persistent_grid(n, FHW, c.num_sms, resident_blocks(k_verify_fused, RBS, smem));
-    k_verify_fused<<<grid, RBS, smem, st>>>(c.m, c.scf, c.tab, c.a_hat, c.l, vec_coef, vk_ntt, ch_wt, extra_rhs, n, bd,
-                                            verdict, fc, c.sm_slots);
     return cudaGetLastError();
 }
 

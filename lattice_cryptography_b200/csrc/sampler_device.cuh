@@ -394,162 +394,6 @@ __device__ __forceinline__ void sample_stream_t(const Geo& geo, const DecodePara
     }
 }
 
-// ---- lean challenge stream (k_verify_fused) ----------------------------------------------------------------------
-// make_signature_challenge for ch_bd == 1, d = 256, one polynomial: the same bits as sample_stream_t<Geo256> with
-// bd = 1 and vec_len = 1, written for CODE SIZE - it runs on one warp per block beside the transform warps of
-// k_verify_fused, and the SM's 32 KB instruction cache has to hold both instruction streams (the first fused kernel
-// embedded sample_stream as it is: 85 % instruction-cache hit rate, 22 % of the warp samples on "no instruction",
-// 8.9 instead of 6.3 ms per 2^20).  Every loop that can be is rolled, the permutation loop is not unrolled, the rate
-// block arrives through 35 four-byte cp.async copies issued by a three-instruction loop (one round trip, like the
-// batched loads of InputView::load_block) and is aligned by a second pass over shared memory; magnitude, pad and
-// vector paths do not exist.  pairs[e] = index | (coefficient as int16) << 16, in draw order.
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
-}
-
-__device__ __forceinline__ void lean_load_block(const InputView& iv, int64_t blk, int64_t tot, int64_t last, uint32_t* col, int P) {
-    const int64_t k0 = blk * RATE_WORDS;
-    const uintptr_t a = reinterpret_cast<uintptr_t>(iv.msg) + (uintptr_t)(4 * k0 - iv.salt_len);   // stream byte 4*k0
-    const uint32_t* aw = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-    const unsigned sh = (unsigned)(a & 3) * 8;
-    // an aligned word may be read iff it overlaps [msg, msg + msg_len): word indices [j_lo, j_hi) of aw[]
-    const int64_t first = (int64_t)((reinterpret_cast<uintptr_t>(iv.msg) & ~(uintptr_t)3) - reinterpret_cast<uintptr_t>(aw)) >> 2;
-    const int64_t end = (int64_t)(reinterpret_cast<uintptr_t>(iv.msg) + (uintptr_t)iv.msg_len + 3 - reinterpret_cast<uintptr_t>(aw)) >> 2;
-    const int j_lo = (int)(first < 0 ? 0 : (first > RATE_WORDS + 1 ? RATE_WORDS + 1 : first));
-    const int j_hi = iv.msg_len > 0 ? (int)(end < 0 ? 0 : (end > RATE_WORDS + 1 ? RATE_WORDS + 1 : end)) : 0;
-#pragma unroll 1
-    for (int w = 0; w <= RATE_WORDS; ++w) {          // 35 aligned words: the window has room (absorbing happens at keep = 0)
-        if (w >= j_lo && w < j_hi) cp_async4(col + w * P, aw + w);
-        else col[w * P] = 0u;
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    uint32_t prev = col[0];
-#pragma unroll 1
-    for (int w = 0; w < RATE_WORDS; ++w) {
-        const uint32_t next = col[(w + 1) * P];
-        col[w * P] = __funnelshift_r(prev, next, sh);
-        prev = next;
-    }
-    const int64_t ks = ((int64_t)iv.salt_len + 3) >> 2;          // stream words [0, ks) touch the salt
-    const int64_t kt = tot >> 2, kl = last >> 2;                  // the words that hold the 0x1F marker / the last pad bit
-#pragma unroll 1
-    for (int w = 0; w < RATE_WORDS; ++w) {
-        const int64_t k = k0 + w;
-        if (k < ks || k == kt) col[w * P] = iv.word_at(k, tot, last);
-        else if (k > kt) col[w * P] = k == kl ? 0x80000000u : 0u;
-    }
-}
-
-__device__ __forceinline__ void challenge_stream_lean(int wt, int idx_bits, int mag_bits, const InputView& iv,
-                                                      const StreamCols& sc, uint32_t* pairs) {
-    const int P = sc.pitch;
-    const int64_t in_total = iv.total();
-    const int64_t in_blocks = (in_total >> 32) == 0 ? (int64_t)((uint32_t)in_total / 136u) + 1 : in_total / 136 + 1;
-    const int64_t in_last = in_blocks * 136 - 1;
-    int64_t in_blk = 0;
-    KeccakState s;
-#pragma unroll
-    for (int i = 0; i < 25; ++i) { s.lo[i] = 0; s.hi[i] = 0; }
-    int rp = 0, nw = 0;          // read cursor (bits) and valid words of the window
-#pragma unroll
-    for (int w = 0; w < 8; ++w) sc.bmap[w * P] = 0xFFFFFFFFu;
-#pragma unroll 1
-    for (int f = 0; f < 2 * wt; ++f) {
-        const bool is_idx = f < wt;
-        const int bits = f == 0 ? LOGD : (is_idx ? idx_bits : 1 + mag_bits);
-        if (rp + bits > 32 * nw) {           // the one call site of the permutation
-            const int drop = rp >> 5, keep = nw - drop;
-#pragma unroll 1
-            for (int i = 0; i < keep; ++i) sc.ring[i * P] = sc.ring[(drop + i) * P];
-            rp -= 32 * drop;
-            do {
-                if (in_blk < in_blocks) {
-                    lean_load_block(iv, in_blk, in_total, in_last, sc.ring + keep * P, P);
-#pragma unroll
-                    for (int i = 0; i < 17; ++i) {
-                        s.lo[i] ^= sc.ring[(keep + 2 * i) * P];
-                        s.hi[i] ^= sc.ring[(keep + 2 * i + 1) * P];
-                    }
-                    ++in_blk;
-                }
-                keccak_f1600_rolled(s, c_keccak_rc);
-            } while (in_blk < in_blocks);
-#pragma unroll
-            for (int i = 0; i < 17; ++i) {
-                sc.ring[(keep + 2 * i) * P] = __byte_perm(s.lo[i], 0, 0x0123);
-                sc.ring[(keep + 2 * i + 1) * P] = __byte_perm(s.hi[i], 0, 0x0123);
-            }
-            nw = keep + RATE_WORDS;
-        }
-        if (is_idx) {
-            uint32_t selw, word, pos;
-            if (f == 0) {
-                const uint32_t r = __funnelshift_l(sc.ring[P], sc.ring[0], 0) >> (32 - LOGD);      // rp == 0 here
-                rp = LOGD;
-                selw = r >> 5;
-                pos = r & 31;
-                word = 0xFFFFFFFFu;
-            } else {
-                const uint32_t m = (uint32_t)(D - f);
-                uint32_t k = 0;
-                if (m == 1) rp += idx_bits;
-                else {
-                    // the field modulo m as a weighted sum of 32-bit pieces aligned to its end (sample_stream_t::field_small)
-                    const uint8_t* wrow = sc.wtab + m * sc.wstride;
-                    const int np = (idx_bits + 31) >> 5;
-                    const int head = idx_bits - 32 * (np - 1);
-                    const uint32_t* rw = sc.ring + (rp >> 5) * P;
-                    uint32_t c = __funnelshift_l(rw[P], rw[0], rp & 31) >> (32 - head);
-                    uint64_t acc = (uint64_t)c * wrow[np - 1];
-                    rp += head;
-                    rw = sc.ring + (rp >> 5) * P;
-                    const int sh = rp & 31;
-                    uint32_t prev = rw[0];
-#pragma unroll 1
-                    for (int kk = np - 2; kk >= 0; --kk) {
-                        rw += P;
-                        const uint32_t nxt = rw[0];
-                        c = __funnelshift_l(nxt, prev, sh);
-                        prev = nxt;
-                        acc += (uint64_t)c * wrow[kk];
-                    }
-                    rp += 32 * (np - 1);
-                    const uint32_t lo = (uint32_t)acc, hi = (uint32_t)(acc >> 32);
-                    k = barrett_small(hi * wrow[1] + (lo >> 16) * sc.r16tab[m] + (lo & 0xFFFFu), sc.mutab[m], m);
-                }
-                bool found = false;
-                selw = 0; word = 0;
-#pragma unroll
-                for (uint32_t w = 0; w < 8; ++w) {
-                    const uint32_t cand = sc.bmap[w * P];
-                    const uint32_t cnt = __popc(cand);
-                    if (!found) {
-                        if (k < cnt) { found = true; selw = w; word = cand; }
-                        else k -= cnt;
-                    }
-                }
-                uint32_t wd = word, cnt;
-                pos = 0;
-                cnt = __popc(wd & 0xFFFFu); if (k >= cnt) { k -= cnt; pos += 16; wd >>= 16; }
-                cnt = __popc(wd & 0xFFu);   if (k >= cnt) { k -= cnt; pos += 8;  wd >>= 8; }
-                cnt = __popc(wd & 0xFu);    if (k >= cnt) { k -= cnt; pos += 4;  wd >>= 4; }
-                cnt = __popc(wd & 0x3u);    if (k >= cnt) { k -= cnt; pos += 2;  wd >>= 2; }
-                cnt = wd & 1u;              if (k >= cnt) { pos += 1; }
-            }
-            sc.bmap[selw * P] = word & ~(1u << pos);
-            sc.idxs[f * sc.idx_stride] = (uint8_t)(selw * 32 + pos);
-        } else {
-            const int e = f - wt;
-            const int wi = rp >> 5;
-            const uint32_t sign = (sc.ring[wi * P] >> (31 - (rp & 31))) & 1u;
-            rp += 1 + mag_bits;
-            pairs[e] = (uint32_t)sc.idxs[e * sc.idx_stride] | (sign ? 0x00010000u : 0xFFFF0000u);
-        }
-    }
-}
-
 template <typename Emit>
 __device__ __forceinline__ void sample_stream(const DecodeParams& dp, const InputView& iv, const StreamCols& sc, Emit&& emit) {
     SpongeFeed feed;
