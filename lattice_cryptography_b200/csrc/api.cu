@@ -575,6 +575,38 @@ int lcb_ctx_create(lcb_ctx** out, int device, int secpar, int q, int d, int l) {
         t.pw[e2] = (uint32_t)powmod(psi, e2, uq);
         t.pws[e2] = shoup(t.pw[e2], uq);
     }
+    {
+        // FP32-assisted inverse (lcb_device.cuh, ntt_inv_256_fp): twiddle psi^-e as {w, w/q, cst, kw}
+        auto fp_entry = [&](uint32_t w) {
+            const float wq = (float)((double)w / (double)uq);
+            const float cst = (float)(12582912.0 - 8388608.0 * (double)wq);
+            const uint32_t kw = (uint32_t)((uint64_t)(0x4B400000u + 2u) * uq - (uint64_t)FP_BIAS * w);
+            uint32_t wq_bits, cst_bits;
+            std::memcpy(&wq_bits, &wq, 4);
+            std::memcpy(&cst_bits, &cst, 4);
+            return make_uint4(w, wq_bits, cst_bits, kw);
+        };
+        auto inv_tw = [&](int half, int j) { return t.pw[(512 - (256 / half) * j % 512) % 512]; };
+        const uint32_t dinv = (uint32_t)powmod((uint32_t)d, uq - 2, uq);
+        for (int half = 2; half <= 8; half *= 2)
+            for (int j = 0; j < half; ++j) {
+                const uint4 e4 = fp_entry(inv_tw(half, j));
+                const int k = half + j;
+                c->ring.iscf.w[k] = e4.x;
+                std::memcpy(&c->ring.iscf.wq[k], &e4.y, 4);
+                std::memcpy(&c->ring.iscf.cst[k], &e4.z, 4);
+                c->ring.iscf.kw[k] = e4.w;
+            }
+        for (int lane = 0; lane < 16; ++lane) {
+            int pos = 0;
+            for (int h16 = 1; h16 <= 8; h16 *= 2)
+                for (int r = 0; r < h16; ++r) t.inv_lane[lane][pos++] = fp_entry(inv_tw(16 * h16, lane + 16 * r));
+            for (int jj = 0; jj < 16; ++jj) {
+                const int i = lane + 16 * jj;
+                t.inv_lane[lane][pos++] = fp_entry((uint32_t)((uint64_t)t.pw[(512 - i) % 512] * dinv % uq));
+            }
+        }
+    }
     ModQ& m = c->ring.m;
     m.zero = 0;
     m.q = uq;

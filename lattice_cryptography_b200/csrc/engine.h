@@ -115,6 +115,7 @@ struct RingCtx {
     ModQ m;
     StageConst sc;
     StageConstF scf;
+    StageConstF iscf;          // warp-uniform twiddles of the FP32-assisted inverse (ntt_inv_256_fp), index half + j
     const NttTables* tab;      // device
     const uint32_t* a_hat;     // device, uint32[l][256]: NTT(key_ch), slot order
     int l;

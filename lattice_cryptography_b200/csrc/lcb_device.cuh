@@ -117,6 +117,10 @@ struct NttTables {
     uint32_t iw[256], iws[256];    // zetas[k]^-1
     uint32_t pw[512], pws[512];    // psi^e, e in [0, 512): NTT image of monomials (BKLM)
     uint16_t oddexp[256];          // 2*bitrev8(p)+1: exponent of the evaluation point of slot p
+    // FP32-assisted INVERSE transform (ntt_inv_256_fp): per lane 31 entries {w, w/q, cst, kw}: [0] half 16,
+    // [1..2] half 32, [3..6] half 64, [7..14] half 128 (twiddle omega^-((256/half) j), j = lane + 16 (jj mod half/16)),
+    // [15..30] the closing twist psi^-i d^-1, i = lane + 16 jj
+    uint4 inv_lane[16][31];
 };
 
 __device__ __forceinline__ uint32_t shoup_mul(uint32_t a, uint32_t w, uint32_t ws, const ModQ& m) {
@@ -373,6 +377,74 @@ __device__ __forceinline__ void ntt_inv_256(uint32_t (&r)[EPT], const ModQ& m, c
         }
         b <<= 1;
     }
+}
+
+// ---- inverse with FP32-assisted butterflies (k_sign) ---------------------------------------------------------
+// The Gentleman-Sande inverse above multiplies AFTER the subtraction: its operands double from stage to stage
+// (2^17 -> 2^25), out of reach of the FP32 quotient estimate (exact below 2^22), so it stays on Shoup multiplications
+// whose IMAD.HI issues at a quarter of the IMAD rate - k_sign was bound by the FMA-heavy pipe (96 IMAD.HI per row).
+// The slot order of this library IS the bit-reversed order of the 256-point cyclic transform of b_i = a_i psi^i
+// (slot p holds a(psi^(2 bitrev(p) + 1)) = DFT_omega(b)[bitrev(p)], omega = psi^2), so the inverse can just as well be
+// the decimation-in-time form: Cooley-Tukey butterflies (u + w v, u - w v) with twiddles omega^-j, half = 1, 2, ..
+// 128, natural order out, followed by the twist a_i = A_i psi^-i d^-1 - which replaces the d^-1 scaling, so it is free.
+// Multiplying BEFORE the add keeps growth additive (+4q per stage): the FP32-assisted multiplication of the forward
+// transform applies (one FFMA + two IMAD, no IMAD.HI).  Butterflies with w = 1 are plain adds in stages 1-3 (doubling
+// three times is affordable: 2^16 + 2q -> < 2^21); from stage 4 on w = 1 is multiplied like any other twiddle.
+// 50 multiplications + 16 for the twist instead of 64 + 16.
+// in : layout B, BIASED lazy values < 2^16 + 2q + FP_BIAS;  out: layout A, unbiased twisted values in (0.87 q, 3.13 q)
+template <typename TW>
+__device__ __forceinline__ void ntt_inv_256_fp(uint32_t (&r)[EPT], const ModQ& m, const StageConstF& isc, const TW& tw,
+                                               uint32_t* xb, int lane) {
+#pragma unroll
+    for (int s = 1; s <= 4; ++s) {
+        const int half = 1 << (s - 1);
+        const uint32_t off = FP_BIAS + (m.q4 << (s - 1));       // 4q, 8q, 16q: at least the bound of the stage's inputs
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            if (j & half) continue;
+            const int e = j & (half - 1);
+            if (e == 0 && s <= 3) {
+                const uint32_t u = r[j], v = r[j + half];
+                r[j] = u + v - FP_BIAS;
+                r[j + half] = u - v + off;
+            } else {
+                const int k = half + e;
+                const uint32_t t = fp_mul(r[j + half], isc.w[k], isc.wq[k], isc.cst[k], isc.kw[k], m);
+                r[j + half] = r[j] + m.q4 - t;
+                r[j] = r[j] + t + m.zero;
+            }
+        }
+    }
+    xpose_b_to_a(r, xb, lane);
+#pragma unroll
+    for (int s = 5; s <= 8; ++s) {
+        const int h16 = 1 << (s - 5);
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            if (j & h16) continue;
+            uint32_t w_, kw_;
+            float wq_, cst_;
+            tw.get((h16 - 1) + (j & (h16 - 1)), w_, wq_, cst_, kw_);
+            const uint32_t t = fp_mul(r[j + h16], w_, wq_, cst_, kw_, m);
+            r[j + h16] = r[j] + m.q4 - t;
+            r[j] = r[j] + t + m.zero;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        uint32_t w_, kw_;
+        float wq_, cst_;
+        tw.get(15 + j, w_, wq_, cst_, kw_);
+        r[j] = fp_mul(r[j], w_, wq_, cst_, kw_, m);
+    }
+}
+
+// value in (0, 4q) congruent to the coefficient -> centred coefficient
+__device__ __forceinline__ int32_t center_lazy4(uint32_t t, const ModQ& m) {
+    const uint32_t q2 = 2 * m.q;
+    t = min(t, t - q2);          // unsigned wrap-around: subtracts only when t >= 2q
+    t = min(t, t - m.q);
+    return center(t, m);
 }
 
 // final scaling of an unscaled inverse transform value -> centred coefficient

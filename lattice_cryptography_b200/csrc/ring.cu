@@ -352,18 +352,28 @@ __device__ __forceinline__ void load_u16x16_smem(uint32_t (&r)[EPT], const unsig
 }
 
 constexpr int SIGN_STAGE_BYTES = 2 * (2 * D * 2) + 32;   // two (sk_left row, sk_right row) pairs per half-warp
+constexpr int ITW_ROW = 31;           // uint4 per lane of NttTables::inv_lane: 124-word pitch, conflict-free LDS.128
+constexpr int ITW_BYTES = LANES * ITW_ROW * 16;
+constexpr int SIGN_BLOCKS = 5;        // resident blocks per SM k_sign is compiled for
 
-// sig = sk_left ** c + sk_right
-__global__ void __launch_bounds__(RBS) k_sign(ModQ m, StageConst sc, const NttTables* __restrict__ tab, int l,
+// sig = sk_left ** c + sk_right.  Both transforms are FP32-assisted (round 2): the challenge goes through
+// ntt_fwd_256_fp, every row through the decimation-in-time inverse ntt_inv_256_fp, whose closing twist absorbs the
+// d^-1 scaling; all per-lane twiddles sit in shared memory.  (Round 1: Shoup butterflies, 96 quarter-rate IMAD.HI per
+// row, 7.3 ms per 2^20 with the FMA-heavy pipe as the limiter.)
+__global__ void __launch_bounds__(RBS, SIGN_BLOCKS) k_sign(ModQ m, StageConstF scf, StageConstF iscf, const NttTables* __restrict__ tab, int l,
                                               const uint16_t* __restrict__ sk_ntt, const int16_t* __restrict__ ch_pairs,
                                               int ch_wt, int64_t n, int16_t* __restrict__ sig) {
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* xbuf = smem;
     unsigned char* stage = reinterpret_cast<unsigned char*>(xbuf + (RBS / 32) * XWARP);
+    uint4* twtab = reinterpret_cast<uint4*>(stage + HWB * SIGN_STAGE_BYTES);
+    uint4* itwtab = twtab + LANES * TW_ROW;
     const HalfWarp h = half_warp(xbuf);
     stage += h.slot * SIGN_STAGE_BYTES;
-    LaneTw itw;
-    load_lane_tw(itw, tab->iw, tab->iws, h.lane);
+    for (int e = threadIdx.x; e < LANES * ITW_ROW; e += blockDim.x) itwtab[e] = __ldg(&tab->inv_lane[0][0] + e);
+    fill_tw_shared(twtab, tab);
+    const LaneTwFShared twf{twtab + h.lane * TW_ROW};
+    const LaneTwFShared itwf{itwtab + h.lane * ITW_ROW};
     const int64_t first = (int64_t)blockIdx.x * HWB, stride = (int64_t)gridDim.x * HWB;
     const int64_t trips = first < n ? (n - first + stride - 1) / stride : 0;   // uniform over the block
     // work list of this half-warp: row pair i (sk_left[i], sk_right[i]) of item(it); the cursor runs 2 ahead
@@ -395,13 +405,12 @@ __global__ void __launch_bounds__(RBS) k_sign(ModQ m, StageConst sc, const NttTa
         const int64_t item = live ? raw : n - 1;
         uint32_t c[EPT];
         {
-            LaneTw tw;
-            load_lane_tw(tw, tab->w, tab->ws, h.lane);
-            load_pairs_a(c, ch_pairs + item * ch_wt * 2, ch_wt, h.xb, h.lane, m.cq);
-            ntt_fwd_256(c, m, sc, tw, h.xb, h.lane);
+            int cx[EPT];
+            load_pairs_raw(cx, ch_pairs + item * ch_wt * 2, ch_wt, h.xb, h.lane);
+            ntt_fwd_256_fp(cx, c, m, scf, twf, h.xb, h.lane);
         }
 #pragma unroll
-        for (int k = 0; k < EPT; ++k) c[k] = barrett_full(c[k], m);
+        for (int k = 0; k < EPT; ++k) c[k] = barrett_full(c[k] - FP_BIAS, m);
         for (int i = 0; i < l; ++i) {
             cp_async_wait<1>();
             __syncwarp();
@@ -413,9 +422,13 @@ __global__ void __launch_bounds__(RBS) k_sign(ModQ m, StageConst sc, const NttTa
             issue();                            // refill the buffer just drained with row pair (+2)
             cur ^= 1u;
 #pragma unroll
-            for (int k = 0; k < EPT; ++k) a[k] = barrett_lazy(c[k] * a[k], m) + b[k];   // < 2q + 2^16 <= cq2
-            ntt_inv_256(a, m, sc, itw, h.xb, h.lane, m.cq2);
-            if (live) store_coef_a(sig + (item * l + i) * D, a, h.lane, m);
+            for (int k = 0; k < EPT; ++k) a[k] = barrett_lazy(c[k] * a[k], m) + b[k] + FP_BIAS;   // < 2q + 2^16, biased
+            ntt_inv_256_fp(a, m, iscf, itwf, h.xb, h.lane);
+            if (live) {
+                int16_t* out = sig + (item * l + i) * D;
+#pragma unroll
+                for (int j = 0; j < EPT; ++j) out[h.lane + 16 * j] = (int16_t)center_lazy4(a[j], m);
+            }
         }
     }
 }
@@ -843,9 +856,11 @@ cudaError_t launch_matvec(const RingCtx& c, const int16_t* vec_coef, int64_t nve
 cudaError_t launch_sign(const RingCtx& c, const uint16_t* sk_ntt, const int16_t* ch_pairs, int ch_wt, int64_t n,
                         int16_t* sig, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
-    const size_t smem = (size_t)(RBS / 32) * XWARP * 4 + (size_t)HWB * SIGN_STAGE_BYTES;
+    const size_t smem = (size_t)(RBS / 32) * XWARP * 4 + (size_t)HWB * SIGN_STAGE_BYTES + (size_t)TW_BYTES + (size_t)ITW_BYTES;
+    cudaError_t e = allow_smem(k_sign, smem);
+    if (e != cudaSuccess) return e;
     unsigned grid = persistent_grid(n, HWB, c.num_sms, resident_blocks(k_sign, RBS, smem));
-    k_sign<<<grid, RBS, smem, st>>>(c.m, c.sc, c.tab, c.l, sk_ntt, ch_pairs, ch_wt, n, sig);
+    k_sign<<<grid, RBS, smem, st>>>(c.m, c.scf, c.iscf, c.tab, c.l, sk_ntt, ch_pairs, ch_wt, n, sig);
     return cudaGetLastError();
 }
 
