@@ -488,6 +488,47 @@ def secondary_bklm(a, rank, local, world, torch, np, dist):
                      'achieved': instr * n_ii / (k['kernel_ms_per_launch'] * 1e-3) / 1e12, 'peak': peaks['int_tinstr_s'],
                      'unit': 'Tinstr/s'}
     k['roofline']['frac'] = k['roofline']['achieved'] / k['roofline']['peak']
+    # ---- row (iii): the linear-time NON-REFERENCE mode (bklm_one_time_agg_sigs 'tree' mode): the message
+    # is bound into a two-level SHAKE256 tree commitment on the GPU, every coefficient then hashes one block
+    from lattice_cryptography_b200.bklm_one_time_agg_sigs import TREE_DOMAIN, TREE_LEAF_BYTES
+    cuts = list(range(0, len(agmsg_b), TREE_LEAF_BYTES)) + [len(agmsg_b)]
+    d_cuts = torch.tensor(cuts, dtype=torch.int64, device=dev)
+    head = torch.from_numpy(np.frombuffer(TREE_DOMAIN + len(agmsg_b).to_bytes(8, 'little'), dtype=np.uint8).copy()).to(dev)
+    d_top_off = torch.tensor([0, head.numel() + 32 * (len(cuts) - 1)], dtype=torch.int64, device=dev)
+
+    def commit():
+        leaves = eng.shake256((d_agmsg, d_cuts), 32, device=True)
+        top = torch.cat([head, leaves.reshape(-1)])
+        return bytes(eng.shake256((top, d_top_off), 32, device=True)[0].cpu().numpy()).hex().encode()
+
+    def agg_tree():
+        ag = eng.agg_coefs(sch, commit(), start, count, device=True)
+        part = reduce_partial(eng.aggregate_partial(sch, sigs, ag, device=True))
+        if rank == 0:
+            res['ag_sig_tree'] = eng.aggregate_finish(part, device=True)
+    agg_tree()
+    ms_agg_t = _timed(torch, dist, world, dev, agg_tree, reps=3)
+    ag_sig_t = res.get('ag_sig_tree')
+    if world > 1:
+        if rank != 0:
+            ag_sig_t = torch.empty((p['l'], D), dtype=torch.int16, device=dev)
+        dist.broadcast(ag_sig_t.view(torch.uint8), src=0)
+
+    def aggv_tree():
+        ag = eng.agg_coefs(sch, commit(), start, count, device=True)
+        part = reduce_partial(eng.aggverify_partial(sch, vk_ntt, d_chm, ag, device=True))
+        if rank == 0:
+            res['ok_tree'] = eng.aggverify_finish(part, ag_sig_t, total, total, avf_bd, 256)
+    aggv_tree()
+    ms_aggv_t = _timed(torch, dist, world, dev, aggv_tree, reps=3)
+    leaves_h = b''.join(hashlib.shake_256(agmsg_b[c0:c1]).digest(32) for c0, c1 in zip(cuts[:-1], cuts[1:]))
+    root_h = hashlib.shake_256(TREE_DOMAIN + len(agmsg_b).to_bytes(8, 'little') + leaves_h).digest(32).hex().encode()
+    tree = {'mode': "pp['ag_mode'] = 'tree': NOT the reference's coefficients (explicit opt-in), same algebra",
+            'aggregate_ms': ms_agg_t, 'aggregate_verify_ms': ms_aggv_t,
+            'aggregate_sigs_per_s': total / (ms_agg_t * 1e-3), 'aggregate_verify_sigs_per_s': total / (ms_aggv_t * 1e-3),
+            'verdict': res.get('ok_tree') if rank == 0 else None, 'commitment_vs_hashlib': commit() == root_h,
+            'reference_mode_rejects_it': (not eng.aggverify_finish(reduce_partial(eng.aggverify_partial(
+                sch, vk_ntt, d_chm, res['ag'], device=True)), ag_sig_t, total, total, avf_bd, 256)) if world == 1 else None}
     eng.close()
     perms = count * ((len(agmsg) + 12) // 136 + 1)
     return {'sigs_per_aggregate': total, 'aggregate_sigs_per_s': total / (ms_agg * 1e-3),
@@ -496,7 +537,8 @@ def secondary_bklm(a, rank, local, world, torch, np, dist):
             'checker': {'coefficients_vs_hashlib': f'{coef_ok}/{len(pick)}', 'aggregate_vs_numpy_sum': sum_ok},
             'agmsg_bytes': int(len(agmsg)), 'agg_coefs_ms_rank0': coef_ms, 'streams_per_gpu': count,
             'agg_coefs_gperm_s_per_gpu': perms / (coef_ms * 1e-3) / 1e9, 'keccak_roofline_gperm_s': 4.28,
-            'row_ii_coefficients_supplied': dict(ii, signatures_per_gpu=n_ii)}
+            'row_ii_coefficients_supplied': dict(ii, signatures_per_gpu=n_ii),
+            'row_iii_tree_mode_nonreference': tree}
 
 
 def secondary_single_ops(a, rank, local, world, torch, np, dist):

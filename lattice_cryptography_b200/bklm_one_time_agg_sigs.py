@@ -51,6 +51,45 @@ def set_aggregation_capacity(pp: PublicParameters, ag_cap: int) -> PublicParamet
     return pp
 
 
+# ------------------------------------------------------------------------------- non-reference: linear-time mode
+# The reference derives coefficient i from ag_salt || str(i) || M with M = str(list(zip(keys, msgs))) - every one of
+# the N coefficients absorbs the whole O(N)-byte message (bklm_one_time_agg_sigs.py:60-81): 3.9e9 Keccak permutations
+# at N = 2^16, which is all of the aggregate's cost.  SURVEY.md 8(f)4 asks for a sub-quadratic VARIANT "offered as an
+# explicitly non-reference mode": with pp['ag_mode'] = 'tree' the message is first bound into a 32-byte commitment
+#     leaf_j = SHAKE256(M[j*8192 : (j+1)*8192])[:32]                   (every 8,192-byte chunk, the last one shorter)
+#     root   = SHAKE256(b'LCB200-AGTREE' || le64(len(M)) || leaf_0 || leaf_1 || ...)[:32]
+# and coefficient i hashes ag_salt || str(i) || root.hex() - one permutation each.  The coefficients still depend on
+# every key and message of the sorted list (through the commitment), so the rogue-key argument is unchanged, but they
+# are NOT the reference's coefficients: aggregates made in one mode do not verify in the other.  Off by default.
+AG_MODES = ('reference', 'tree')
+TREE_LEAF_BYTES = 8192
+TREE_DOMAIN = b'LCB200-AGTREE'
+
+
+def set_aggregation_mode(pp: PublicParameters, mode: str) -> PublicParameters:
+    if mode not in AG_MODES:
+        raise ValueError(f"ag_mode must be one of {AG_MODES}")
+    pp['ag_mode'] = mode
+    return pp
+
+
+def commit_aggregation_message(pp: PublicParameters, agmsg) -> str:
+    """The 64-hex-digit tree commitment of an aggregation message (both levels hashed on the GPU)."""
+    eng, _ = _ctx(pp)
+    raw = agmsg.encode() if isinstance(agmsg, str) else bytes(agmsg)
+    blob = np.frombuffer(raw, dtype=np.uint8) if raw else np.zeros(0, dtype=np.uint8)
+    cuts = np.arange(0, len(raw), TREE_LEAF_BYTES, dtype=np.int64)
+    off = np.concatenate([cuts, np.array([len(raw)], dtype=np.int64)]) if len(raw) else np.zeros(1, dtype=np.int64)
+    leaves = eng.shake256((np.ascontiguousarray(blob), off), 32) if len(raw) else np.zeros((0, 32), dtype=np.uint8)
+    top = TREE_DOMAIN + len(raw).to_bytes(8, 'little') + leaves.tobytes()
+    return bytes(eng.shake256([top], 32)[0]).hex()
+
+
+def _agg_message(pp: PublicParameters, agmsg):
+    """What the aggregation coefficients hash behind ag_salt || str(i): the message itself (reference) or its commitment."""
+    return commit_aggregation_message(pp, agmsg) if pp.get('ag_mode', 'reference') == 'tree' else agmsg
+
+
 # ------------------------------------------------------------------------------- host-side preparation
 def prepare_make_agg_coefs(otvks: List[OneTimeVerificationKey], msgs: List[Message]) -> Tuple[
         List[OneTimeVerificationKey], List[Message]]:
@@ -80,7 +119,7 @@ def _monomials(lp, pairs: np.ndarray) -> List[AggCoef]:
 def make_agg_coefs(pp: PublicParameters, otvks: List[OneTimeVerificationKey], msgs: List[Message]) -> List[AggCoef]:
     h2p = prepare_hash2polyinput(pp=pp, otvks=otvks, msgs=msgs)
     eng, sch = _ctx(pp)
-    return _monomials(h2p['lp'], eng.agg_coefs(sch, h2p['msg'], 0, len(otvks)))
+    return _monomials(h2p['lp'], eng.agg_coefs(sch, _agg_message(pp, h2p['msg']), 0, len(otvks)))
 
 
 def prepare_aggregate(otvks: List[OneTimeVerificationKey], msgs: List[Message], sigs: List[Signature]) -> Tuple[
@@ -124,7 +163,7 @@ def aggregate_shard(pp: PublicParameters, sig_sorted, agmsg, first: int, device:
     position `first` (sig_sorted int16[count,l,d]); aggregation coefficients are derived here."""
     eng, sch = _ctx(pp)
     count = int(sig_sorted.shape[0])
-    ag = _agg_coefs_cached(pp, eng, sch, agmsg, first, count, device)
+    ag = _agg_coefs_cached(pp, eng, sch, _agg_message(pp, agmsg), first, count, device)
     return eng.aggregate_partial(sch, sig_sorted, ag, device=device)
 
 
@@ -137,7 +176,7 @@ def aggregate_verify_shard(pp: PublicParameters, vk_ntt_sorted, chmsgs_sorted, a
     """int32[d] partial sum (NTT form) of (vk_left*c + vk_right) * ag over one shard of the sorted list."""
     eng, sch = _ctx(pp)
     count = int(vk_ntt_sorted.shape[0])
-    ag = _agg_coefs_cached(pp, eng, sch, agmsg, first, count, device)
+    ag = _agg_coefs_cached(pp, eng, sch, _agg_message(pp, agmsg), first, count, device)
     return eng.aggverify_partial(sch, vk_ntt_sorted, chmsgs_sorted, ag, device=device)
 
 

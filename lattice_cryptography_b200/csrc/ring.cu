@@ -632,58 +632,110 @@ __global__ void k_vec_addsub(ModQ m, const int16_t* __restrict__ a, const int16_
 
 // ------------------------------------------------------------------------------------------------
 // BKLM aggregate, monomial coefficients: partial[i][p] += s * sig[t][i][(p - k) mod 256] * (p < k ? -1 : 1)
-// A pure HBM stream (512 bytes per polynomial, one add per 2 bytes).  grid = (chunks, l); a warp takes one
-// signature per step: its 512-byte row arrives as ONE coalesced 16-byte load per lane (two signatures in flight per
-// warp), is parked in the warp's shared-memory row, and each lane then picks its 8 output positions lane + 32 j at
-// the rotated source index - consecutive lanes read consecutive 16-bit words, so the reads are conflict-free - into
-// 8 register accumulators.  (Round 1 read the rotated positions straight from global memory with 2-byte loads:
-// 2.36 TB/s, 0.36 of the HBM roof.)
+// A pure HBM stream (512 bytes per polynomial, one add per 2 bytes) - provided the rotation costs next to nothing.
+// grid = (chunks, l); a warp keeps AGG_DEPTH rows of its polynomial in flight (one coalesced 16-byte load per lane and
+// row).  A row is parked in shared memory TWICE, as E = [~row | row] (512 int16): output position p of a row rotated by
+// k then sits at E[256 + p - k] whatever p and k are - no wrap-around, no comparison, no select: per row and lane 8
+// sign-extending 16-bit shared loads at immediate offsets (consecutive lanes read consecutive halfwords: conflict-free)
+// and 8 multiply-adds.  The wrapped positions read ~v = -v - 1 instead of -v; the missing "+ s" per wrapped read depends
+// only on (k, s) of the row, not on the data: hist[k] += s once per row, and at the end of the block
+// corr[p] = sum over k > p of hist[k] is added to every position.  (Round 1 read the rotated positions from global
+// memory 2 bytes at a time: 2.36 TB/s; the first shared-memory version spent 103 instructions per row on index
+// wrap-around, compare and select and was issue-bound at 3.55 TB/s.)
 constexpr int AGG_WARPS = 8;
-__global__ void __launch_bounds__(32 * AGG_WARPS) k_agg_partial(ModQ m, int l, const int16_t* __restrict__ sigs,
+constexpr int AGG_DEPTH = 4;
+__global__ void __launch_bounds__(32 * AGG_WARPS, 4) k_agg_partial(ModQ m, int l, const int16_t* __restrict__ sigs,
                                                                const int16_t* __restrict__ ag_pairs, int64_t count,
                                                                int32_t* __restrict__ partial) {
     __shared__ int32_t red[D];
-    __shared__ __align__(16) int16_t rows[AGG_WARPS][2][D];
+    __shared__ int32_t hist[D];
+    __shared__ int32_t wsum[AGG_WARPS];
+    __shared__ __align__(16) int16_t rows[AGG_WARPS][AGG_DEPTH][2 * D];
     const int poly = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     red[threadIdx.x] = 0;
+    hist[threadIdx.x] = 0;
     __syncthreads();
     int32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const uint32_t* ap = reinterpret_cast<const uint32_t*>(ag_pairs);
     const int64_t stride = (int64_t)gridDim.x * AGG_WARPS;
-    auto row_of = [&](int64_t t) { return reinterpret_cast<const uint4*>(sigs + (t * l + poly) * D) + lane; };
-    auto fold = [&](const int16_t* row, uint32_t pr) {
-        const int k = (int)(pr & 0xFF);
-        const int sg = (int)(int16_t)(pr >> 16);
+    uint4 v[AGG_DEPTH];
+    uint32_t pr[AGG_DEPTH];
+    // rows of this warp: t0, t0 + stride, ...; `left` of them remain (32-bit: count / stride fits easily)
+    const int64_t t0 = (int64_t)blockIdx.x * AGG_WARPS + warp;
+    int left = t0 < count ? (int)((count - t0 + stride - 1) / stride) : 0;
+    const unsigned char* rowp = reinterpret_cast<const unsigned char*>(sigs + (t0 * l + poly) * D) + 16 * lane;
+    const uint32_t* app = ap + t0;
+    const int64_t rstep = stride * l * (D * 2);
+    auto fetch = [&]() {                         // the next min(left, AGG_DEPTH) rows; missing rows read as (0, sign 0)
+        if (left >= AGG_DEPTH) {
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-            const int p = lane + 32 * jj;
-            const int v = row[(p - k) & 255];
-            acc[jj] += (p < k) ? -sg * v : sg * v;
+            for (int j = 0; j < AGG_DEPTH; ++j) {
+                v[j] = __ldg(reinterpret_cast<const uint4*>(rowp + j * rstep));
+                pr[j] = __ldg(app + j * stride);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < AGG_DEPTH; ++j) {
+                v[j] = make_uint4(0, 0, 0, 0);
+                pr[j] = 0;
+                if (j < left) {
+                    v[j] = __ldg(reinterpret_cast<const uint4*>(rowp + j * rstep));
+                    pr[j] = __ldg(app + j * stride);
+                }
+            }
         }
+        LCB_CHECK(left <= 0 || (t0 + (int64_t)(left - 1) * stride < count && poly < l));
+        rowp += AGG_DEPTH * rstep;
+        app += AGG_DEPTH * stride;
     };
-    int64_t t = (int64_t)blockIdx.x * AGG_WARPS + warp;
-    for (; t + stride < count; t += 2 * stride) {
-        const uint4 v0 = __ldg(row_of(t)), v1 = __ldg(row_of(t + stride));
-        const uint32_t p0 = __ldg(ap + t), p1 = __ldg(ap + t + stride);
-        reinterpret_cast<uint4*>(rows[warp][0])[lane] = v0;
-        reinterpret_cast<uint4*>(rows[warp][1])[lane] = v1;
+    if (left > 0) fetch();
+    const unsigned rows_s = (unsigned)__cvta_generic_to_shared(rows[warp][0]);
+    while (left > 0) {
+        uint32_t cur[AGG_DEPTH];
+#pragma unroll
+        for (int j = 0; j < AGG_DEPTH; ++j) {
+            uint4* e = reinterpret_cast<uint4*>(rows[warp][j]);
+            e[lane] = make_uint4(~v[j].x, ~v[j].y, ~v[j].z, ~v[j].w);
+            e[32 + lane] = v[j];
+            cur[j] = pr[j];
+        }
         __syncwarp();
-        fold(rows[warp][0], p0);
-        fold(rows[warp][1], p1);
+        left -= AGG_DEPTH;
+        if (left > 0) fetch();                   // next rows in flight while this batch is folded
+#pragma unroll
+        for (int j = 0; j < AGG_DEPTH; ++j) {
+            const int k = (int)(cur[j] & 0xFF);
+            const int sg = (int)(int16_t)(cur[j] >> 16);
+            const unsigned a = rows_s + (unsigned)(j * 4 * D) + 2u * (unsigned)(D - k + lane);
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                int x;
+                asm volatile("ld.shared.s16 %0, [%1];" : "=r"(x) : "r"(a + 64u * jj));
+                acc[jj] += sg * x;
+            }
+            if (lane == 0 && sg != 0) atomicAdd(&hist[k], sg);
+        }
         __syncwarp();
-    }
-    if (t < count) {
-        reinterpret_cast<uint4*>(rows[warp][0])[lane] = __ldg(row_of(t));
-        __syncwarp();
-        fold(rows[warp][0], __ldg(ap + t));
     }
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) atomicAdd(&red[lane + 32 * jj], acc[jj]);
     __syncthreads();
     {
+        // corr[p] = sum_{k > p} hist[k]: suffix sums inside the warp, then the totals of the warps above
         const int p = threadIdx.x;
-        int v = red[p] % (int)m.q;       // keep cross-block / cross-rank sums far from int32 overflow
+        const int own = hist[p];
+        int sfx = own;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_down_sync(0xFFFFFFFFu, sfx, o);
+            if (lane + o < 32) sfx += y;
+        }
+        if (lane == 0) wsum[warp] = sfx;
+        __syncthreads();
+        int above = 0;
+        for (int w = warp + 1; w < AGG_WARPS; ++w) above += wsum[w];
+        int v = (red[p] + sfx - own + above) % (int)m.q;   // keep cross-block / cross-rank sums far from int32 overflow
         atomicAdd(&partial[poly * D + p], v);
     }
 }
@@ -696,50 +748,89 @@ __global__ void k_agg_finish(ModQ m, const int32_t* __restrict__ partial, int n,
     out[i] = (int16_t)center((uint32_t)v, m);
 }
 
-// BKLM aggregate_verify right-hand side: partial[p] += (vk_left*c + vk_right)[p] * (s * X^k)^(p), NTT form
-__global__ void __launch_bounds__(RBS) k_aggv_partial(ModQ m, StageConst sc, const NttTables* __restrict__ tab,
-                                                      const uint16_t* __restrict__ vk_ntt,
-                                                      const int16_t* __restrict__ ch_pairs, int ch_wt,
-                                                      const int16_t* __restrict__ ag_pairs, int64_t count,
-                                                      int32_t* __restrict__ partial) {
+// BKLM aggregate_verify right-hand side: partial[p] += (vk_left*c + vk_right)[p] * (s * X^k)^(p), NTT form.
+// Round 2: the challenge goes through the FP32-assisted transform (no quarter-rate IMAD.HI in the butterflies), the
+// monomial's sign is folded into the exponent (psi^256 = -1: -psi^e = psi^(e+256)), products are accumulated lazily in
+// 64 bits (one IMAD.WIDE per slot) and reduced once per block instead of four full Barrett rounds per slot and item.
+__global__ void __launch_bounds__(RBS, 4) k_aggv_partial(ModQ m, StageConstF scf, const NttTables* __restrict__ tab,
+                                                         const uint16_t* __restrict__ vk_ntt,
+                                                         const int16_t* __restrict__ ch_pairs, int ch_wt,
+                                                         const int16_t* __restrict__ ag_pairs, int64_t count,
+                                                         int32_t* __restrict__ partial) {
     __shared__ __align__(16) uint32_t xbuf[(RBS / 32) * XWARP];
+    __shared__ __align__(16) uint4 twtab[LANES * TW_ROW];
     __shared__ uint32_t pw[512];
     __shared__ uint32_t red[D];
     for (int i = threadIdx.x; i < 512; i += blockDim.x) pw[i] = tab->pw[i];
     for (int i = threadIdx.x; i < D; i += blockDim.x) red[i] = 0;
-    __syncthreads();
+    fill_tw_shared(twtab, tab);
     const HalfWarp h = half_warp(xbuf);
-    LaneTw tw;
-    load_lane_tw(tw, tab->w, tab->ws, h.lane);
+    const LaneTwFShared twf{twtab + h.lane * TW_ROW};
     uint32_t odd[EPT];
 #pragma unroll
     for (int k = 0; k < EPT; ++k) odd[k] = 2 * (__brev((uint32_t)(16 * h.lane + k)) >> 24) + 1;
-    uint32_t lacc[EPT];
+    uint64_t acc[EPT];
 #pragma unroll
-    for (int k = 0; k < EPT; ++k) lacc[k] = 0;
+    for (int k = 0; k < EPT; ++k) acc[k] = 0;
     const uint32_t* ap = reinterpret_cast<const uint32_t*>(ag_pairs);
-    for (int64_t base = (int64_t)blockIdx.x * HWB; base < count; base += (int64_t)gridDim.x * HWB) {
-        const int64_t raw = base + h.slot;
-        const bool live = raw < count;
-        const int64_t item = live ? raw : count - 1;
-        uint32_t c[EPT], vl[EPT], vr[EPT];
-        load_pairs_a(c, ch_pairs + item * ch_wt * 2, ch_wt, h.xb, h.lane, m.cq);
-        ntt_fwd_256(c, m, sc, tw, h.xb, h.lane);
-        load_u16x16(vl, vk_ntt + item * 2 * D + 16 * h.lane);
-        load_u16x16(vr, vk_ntt + item * 2 * D + D + 16 * h.lane);
-        const uint32_t pr = __ldg(ap + item);
+    const uint32_t* cp = reinterpret_cast<const uint32_t*>(ch_pairs);
+    // The first two challenge words of a lane (all of them for ch_wt <= 32) and the aggregation coefficient of the NEXT
+    // item are requested one iteration ahead, the key rows at the top of the iteration: no global round trip is left
+    // on the critical path of an item.
+    const int64_t step = (int64_t)gridDim.x * HWB;
+    auto item_of = [&](int64_t base) { const int64_t raw = base + h.slot; return raw < count ? raw : count - 1; };
+    uint32_t n_c0 = 0, n_c1 = 0, n_pr = 0;
+    auto prefetch = [&](int64_t base) {
+        const int64_t it = item_of(base);
+        const uint32_t* q = cp + it * ch_wt;
+        n_c0 = h.lane < ch_wt ? __ldg(q + h.lane) : 0xFFFF0000u;            // index 0, coefficient -1: never written
+        n_c1 = h.lane + LANES < ch_wt ? __ldg(q + h.lane + LANES) : 0xFFFF0000u;
+        n_pr = __ldg(ap + it);
+    };
+    int64_t base = (int64_t)blockIdx.x * HWB;
+    if (base < count) prefetch(base);
+    for (; base < count; base += step) {
+        const bool live = base + h.slot < count;
+        const int64_t item = item_of(base);
+        const uint32_t c0 = n_c0, c1 = n_c1, pr = n_pr;
+        const uint4* vkp = reinterpret_cast<const uint4*>(vk_ntt + item * 2 * D + 16 * h.lane);
+        const uint4 va = __ldg(vkp), vb = __ldg(vkp + 1), vc = __ldg(vkp + D / 8), vd = __ldg(vkp + D / 8 + 1);
+        if (base + step < count) prefetch(base + step);
+        uint32_t c[EPT];
+        {
+            int cx[EPT];
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) h.xb[XROW * j + h.lane] = 0;
+            __syncwarp();
+            if (h.lane < ch_wt) h.xb[XROW * ((c0 & 0xFFu) >> 4) + (c0 & 15u)] = (uint32_t)(int)(int16_t)(c0 >> 16);
+            if (h.lane + LANES < ch_wt) h.xb[XROW * ((c1 & 0xFFu) >> 4) + (c1 & 15u)] = (uint32_t)(int)(int16_t)(c1 >> 16);
+            for (int e = h.lane + 2 * LANES; e < ch_wt; e += LANES) {
+                const uint32_t w = __ldg(cp + item * ch_wt + e);
+                h.xb[XROW * ((w & 0xFFu) >> 4) + (w & 15u)] = (uint32_t)(int)(int16_t)(w >> 16);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) cx[j] = (int)h.xb[XROW * j + h.lane];
+            __syncwarp();
+            ntt_fwd_256_fp(cx, c, m, scf, twf, h.xb, h.lane);
+        }
+        const uint32_t wl[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+        const uint32_t wr[8] = {vc.x, vc.y, vc.z, vc.w, vd.x, vd.y, vd.z, vd.w};
         const uint32_t kk = pr & 0xFF;
-        const bool neg = (int16_t)(pr >> 16) < 0;
+        const uint32_t negoff = (int16_t)(pr >> 16) < 0 ? 256u : 0u;
 #pragma unroll
         for (int k = 0; k < EPT; ++k) {
-            uint32_t t = barrett_full(barrett_lazy(barrett_full(c[k], m) * vl[k], m) + vr[k], m);
-            uint32_t u = mulmod_full(t, pw[(odd[k] * kk) & 511], m);
-            u = neg ? csub(m.q - u, m.q) : u;
-            if (live) lacc[k] = csub(lacc[k] + u, m.q);
+            const uint32_t vl = (k & 1) ? wl[k >> 1] >> 16 : wl[k >> 1] & 0xFFFFu;
+            const uint32_t vr = (k & 1) ? wr[k >> 1] >> 16 : wr[k >> 1] & 0xFFFFu;
+            uint32_t ck = barrett_lazy(c[k] - FP_BIAS, m);                 // < 2q
+            ck = min(ck, ck - m.q);                                       // < q: the product below stays under 2^32
+            const uint32_t t = barrett_lazy(ck * vl, m) + vr;             // < 2q + 2^16
+            const uint32_t w = live ? pw[(odd[k] * kk + negoff) & 511] : 0u;
+            acc[k] += (uint64_t)t * w;
         }
     }
 #pragma unroll
-    for (int k = 0; k < EPT; ++k) atomicAdd(&red[16 * h.lane + k], lacc[k]);
+    for (int k = 0; k < EPT; ++k) atomicAdd(&red[16 * h.lane + k], reduce64(acc[k], m));
     __syncthreads();
     for (int i = threadIdx.x; i < D; i += blockDim.x) atomicAdd(&partial[i], (int32_t)(red[i] % m.q));
 }
@@ -910,8 +1001,11 @@ cudaError_t launch_vec_addsub(const RingCtx& c, const int16_t* a, const int16_t*
 cudaError_t launch_agg_partial(const RingCtx& c, const int16_t* sigs, const int16_t* ag_pairs, int64_t count,
                                int32_t* partial, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
-    int64_t need = (count + 8 * AGG_WARPS - 1) / (8 * AGG_WARPS);      // >= 8 signatures per warp
-    int64_t cap = (int64_t)c.num_sms * 8 / c.l + 1;                    // 8 resident blocks of 256 threads per SM
+    const int64_t per_block = (int64_t)AGG_WARPS * AGG_DEPTH;          // one batch of rows per warp
+    int64_t need = (count + per_block - 1) / per_block;
+    // exactly one resident wave: chunks * l blocks <= SMs * resident blocks
+    int64_t cap = (int64_t)c.num_sms * resident_blocks(k_agg_partial, 32 * AGG_WARPS, 0) / c.l;
+    if (cap < 1) cap = 1;
     dim3 grid((unsigned)(need < cap ? need : cap), (unsigned)c.l);
     k_agg_partial<<<grid, 32 * AGG_WARPS, 0, st>>>(c.m, c.l, sigs, ag_pairs, count, partial);
     return cudaGetLastError();
@@ -927,7 +1021,7 @@ cudaError_t launch_aggv_partial(const RingCtx& c, const uint16_t* vk_ntt, const 
                                 const int16_t* ag_pairs, int64_t count, int32_t* partial, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
     unsigned grid = persistent_grid(count, HWB, c.num_sms, resident_blocks(k_aggv_partial, RBS, 0));
-    k_aggv_partial<<<grid, RBS, 0, st>>>(c.m, c.sc, c.tab, vk_ntt, ch_pairs, ch_wt, ag_pairs, count, partial);
+    k_aggv_partial<<<grid, RBS, 0, st>>>(c.m, c.scf, c.tab, vk_ntt, ch_pairs, ch_wt, ag_pairs, count, partial);
     return cudaGetLastError();
 }
 
