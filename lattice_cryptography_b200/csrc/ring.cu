@@ -277,19 +277,25 @@ __global__ void __launch_bounds__(RBS, 4) k_matvec(ModQ m, StageConst sc, StageC
     const LaneTwFShared twf{twtab + h.lane * TW_ROW};
     const int64_t first = (int64_t)blockIdx.x * HWB, stride = (int64_t)gridDim.x * HWB;
     const int64_t trips = first < nvec ? (nvec - first + stride - 1) / stride : 0;   // uniform over the block
-    int64_t pf_it = 0;
+    int pf_left = (int)trips;                   // running-pointer prefetch cursor, see k_verify
     int pf_i = 0;
-    unsigned pf_buf = 0;
+    int64_t pf_item = first + h.slot;
+    const unsigned char* const rows_base = reinterpret_cast<const unsigned char*>(vec_coef) + 16 * h.lane;
+    const unsigned char* src = rows_base + (pf_item < nvec ? pf_item : nvec - 1) * l * (D * 2);
+    const unsigned dst0 = (unsigned)__cvta_generic_to_shared(stage) + 16u * (unsigned)h.lane;
+    unsigned pf_off = 0;
     auto issue = [&]() {
-        if (pf_it < trips) {
-            int64_t it_item = first + pf_it * stride + h.slot;
-            it_item = it_item < nvec ? it_item : nvec - 1;
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(vec_coef + (it_item * l + pf_i) * D);
-            unsigned char* dst = stage + pf_buf * (D * 2);
-            cp_async16(dst + 16 * h.lane, src + 16 * h.lane);
-            cp_async16(dst + 256 + 16 * h.lane, src + 256 + 16 * h.lane);
-            if (++pf_i == l) { pf_i = 0; ++pf_it; }
-            pf_buf ^= 1u;
+        if (pf_left > 0) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + pf_off), "l"(src) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + pf_off + 256), "l"(src + 256) : "memory");
+            src += D * 2;
+            pf_off ^= (unsigned)(D * 2);
+            if (++pf_i == l) {
+                pf_i = 0;
+                --pf_left;
+                pf_item += stride;
+                src = pf_item < nvec ? src + (stride - 1) * l * (D * 2) : rows_base + (nvec - 1) * l * (D * 2);
+            }
         }
         cp_async_commit();
     };
@@ -376,23 +382,31 @@ __global__ void __launch_bounds__(RBS, SIGN_BLOCKS) k_sign(ModQ m, StageConstF s
     const LaneTwFShared itwf{itwtab + h.lane * ITW_ROW};
     const int64_t first = (int64_t)blockIdx.x * HWB, stride = (int64_t)gridDim.x * HWB;
     const int64_t trips = first < n ? (n - first + stride - 1) / stride : 0;   // uniform over the block
-    // work list of this half-warp: row pair i (sk_left[i], sk_right[i]) of item(it); the cursor runs 2 ahead
-    int64_t pf_it = 0;
+    // work list of this half-warp: row pair i (sk_left[i], sk_right[i]) of item(it); the cursor runs 2 ahead as a
+    // running source pointer (see k_verify)
+    int pf_left = (int)trips;
     int pf_i = 0;
-    unsigned pf_buf = 0;
+    int64_t pf_item = first + h.slot;
+    const int64_t item_bytes = (int64_t)2 * l * D * 2, right_off = (int64_t)l * D * 2;
+    const unsigned char* const rows_base = reinterpret_cast<const unsigned char*>(sk_ntt) + 32 * h.lane;
+    const unsigned char* src = rows_base + (pf_item < n ? pf_item : n - 1) * item_bytes;
+    const unsigned dst0 = (unsigned)__cvta_generic_to_shared(stage) + 16u * (unsigned)h.lane;   // split layout, see load_u16x16_smem
+    unsigned pf_off = 0;
     auto issue = [&]() {
-        if (pf_it < trips) {
-            int64_t it_item = first + pf_it * stride + h.slot;
-            it_item = it_item < n ? it_item : n - 1;
-            const unsigned char* left = reinterpret_cast<const unsigned char*>(sk_ntt + (it_item * 2 * l + pf_i) * D) + 32 * h.lane;
-            const unsigned char* right = left + (int64_t)l * D * 2;
-            unsigned char* dst = stage + pf_buf * (2 * D * 2) + 16 * h.lane;      // split layout, see load_u16x16_smem
-            cp_async16(dst, left);
-            cp_async16(dst + D, left + 16);
-            cp_async16(dst + D * 2, right);
-            cp_async16(dst + D * 2 + D, right + 16);
-            if (++pf_i == l) { pf_i = 0; ++pf_it; }
-            pf_buf ^= 1u;
+        if (pf_left > 0) {
+            const unsigned d = dst0 + pf_off;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + D), "l"(src + 16) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 2 * D), "l"(src + right_off) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 3 * D), "l"(src + right_off + 16) : "memory");
+            src += D * 2;
+            pf_off ^= (unsigned)(2 * D * 2);
+            if (++pf_i == l) {
+                pf_i = 0;
+                --pf_left;
+                pf_item += stride;
+                src = pf_item < n ? src + stride * item_bytes - right_off : rows_base + (n - 1) * item_bytes;
+            }
         }
         cp_async_commit();
     };
@@ -492,22 +506,32 @@ __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageCons
 
     const int64_t first = (int64_t)blockIdx.x * HWB, stride = (int64_t)gridDim.x * HWB;
     const int64_t trips = first < n ? (n - first + stride - 1) / stride : 0;   // uniform over the block
-    // work list of this half-warp: polynomial i of item(it), it = 0..trips-1; the prefetch cursor runs 2 ahead
-    int64_t pf_it = 0;
+    // work list of this half-warp: polynomial i of item(it), it = 0..trips-1; the prefetch cursor runs 2 ahead.
+    // The cursor is a running source pointer and a running shared-memory address: rows of an item are contiguous, so
+    // a row costs one 64-bit add; the item arithmetic (and the clamp of the last, partial trip) runs once per item.
+    // (The first version recomputed item, clamp and address for every row: 31 instructions per row, 6.5 % of the kernel.)
+    int pf_left = (int)trips;                   // items the cursor has not finished
     int pf_i = 0;
-    unsigned pf_buf = 0;
+    int64_t pf_item = first + h.slot;
+    const unsigned char* const rows_base = reinterpret_cast<const unsigned char*>(vec_coef) + 16 * h.lane;
+    const unsigned char* src = rows_base + (pf_item < n ? pf_item : n - 1) * l * ROW_BYTES;
+    const unsigned dst0 = (unsigned)__cvta_generic_to_shared(stage) + 16u * (unsigned)h.lane;
+    unsigned pf_off = 0;
     auto issue = [&]() {
-        if (pf_it < trips) {
-            int64_t it_item = first + pf_it * stride + h.slot;
-            it_item = it_item < n ? it_item : n - 1;
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(vec_coef) + (it_item * l + pf_i) * ROW_BYTES;
-            LCB_CHECK(it_item >= 0 && it_item < n && pf_i < l);          // the staged row is a row of the batch
-            unsigned char* dst = stage + pf_buf * (D * 2);
+        if (pf_left > 0) {
+            LCB_CHECK(src >= rows_base && (src - rows_base) + ROW_BYTES <= n * l * ROW_BYTES);   // a row of the batch
 #pragma unroll
             for (int o = 0; o < ROW_BYTES; o += 16 * LANES)
-                if (o + 16 * h.lane < ROW_BYTES) cp_async16(dst + o + 16 * h.lane, src + o + 16 * h.lane);
-            if (++pf_i == l) { pf_i = 0; ++pf_it; }
-            pf_buf ^= 1u;
+                if (o + 16 * h.lane < ROW_BYTES)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + pf_off + o), "l"(src + o) : "memory");
+            src += ROW_BYTES;
+            pf_off ^= (unsigned)(D * 2);
+            if (++pf_i == l) {
+                pf_i = 0;
+                --pf_left;
+                pf_item += stride;
+                src = pf_item < n ? src + (stride - 1) * l * ROW_BYTES : rows_base + (n - 1) * l * ROW_BYTES;
+            }
         }
         cp_async_commit();
     };

@@ -1,5 +1,5 @@
-"""Warm lm_verify time for 2^k device-resident triples: the fused form (challenges hashed inside k_verify) against the
-sampler + k_verify pair, verdicts compared with each other and with the construction rule (every 64th triple tampered).
+"""Warm lm_verify time for 2^k device-resident triples (challenge sampler + k_verify), verdicts compared with the
+construction rule (every 64th triple tampered).
 usage: verify_timing.py <secpar> <log2 n> [reps]"""
 import os, sys
 sys.path.insert(0, '/root/repo')
@@ -22,8 +22,7 @@ bad = torch.arange(0, n, 64, device='cuda')
 sig.view(n, -1)[bad, 7] += 1
 expect = torch.ones(n, dtype=torch.uint8, device='cuda'); expect[bad] = 0
 out = {}
-for mode in ('0', '1', '0', '1'):
-    os.environ['LCB_VERIFY_FUSED'] = mode
+for rnd in range(2):
     verdict = torch.zeros(n, dtype=torch.uint8, device='cuda')
     eng.lm_verify(sch, vk_ntt, (msgs.view(-1), off), sig, P['vf_bd'], 256, out=verdict)
     torch.cuda.synchronize()
@@ -34,7 +33,7 @@ for mode in ('0', '1', '0', '1'):
     for _ in range(reps):
         eng.lm_verify(sch, vk_ntt, (msgs.view(-1), off), sig, P['vf_bd'], 256, out=verdict)
     ev1.record(); torch.cuda.synchronize()
-    prof = {k: eng.profile_read(k) for k in ('verify', 'sampler', 'verify_fused')}
+    prof = {k: eng.profile_read(k) for k in ('verify', 'sampler')}
     eng.profile(False)
-    print(f'fused={mode} secpar={secpar} n=2^{sys.argv[2]}: {ev0.elapsed_time(ev1) / reps:.3f} ms per step, verdicts as constructed: {ok}, '
+    print(f'secpar={secpar} n=2^{sys.argv[2]}: {ev0.elapsed_time(ev1) / reps:.3f} ms per step, verdicts as constructed: {ok}, '
           f'{ {k: (round(v[0] / max(v[1], 1), 3), v[1]) for k, v in prof.items()} }', flush=True)
