@@ -618,7 +618,7 @@ int lcb_ctx_create(lcb_ctx** out, int device, int secpar, int q, int d, int l) {
     m.dinv = (uint32_t)powmod((uint32_t)d, uq - 2, uq);
     m.dinv_s = shoup(m.dinv, uq);
     m.q4 = 4 * uq;
-    m.in_off = m.cq + FP_BIAS;
+    m.in_off = m.cq + 26 * uq + FP_BIAS;
     m.in_off_q4 = m.in_off + m.q4;
     m.bias_mod_q = FP_BIAS % uq;
     m.z1c = (int32_t)t.w[1] > (int32_t)m.half ? (int32_t)t.w[1] - (int32_t)uq : (int32_t)t.w[1];

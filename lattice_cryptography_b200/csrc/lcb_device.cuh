@@ -51,8 +51,9 @@ struct ModQ {
     uint32_t half;        // (q-1)/2
     uint32_t dinv, dinv_s;  // d^-1 mod q and its Shoup companion
     uint32_t q4;          // 4q: positivity offset of the FP32-assisted butterflies
-    uint32_t in_off;      // cq + FP_BIAS: raw int16 coefficient -> biased non-negative lazy value
-    uint32_t in_off_q4;   // in_off + 4q
+    uint32_t in_off;      // cq + 26 q + FP_BIAS: raw int16 coefficient -> biased lazy value that stays non-negative
+                          // through eight offset-free butterfly stages (ntt_fwd_256_fp)
+    uint32_t in_off_q4;   // (unused since the two-stage butterflies; kept so that the parameter layout is stable)
     uint32_t bias_mod_q;  // FP_BIAS mod q
     int32_t z1c;          // zetas[1] (the stage-1 twiddle) as a centred residue, |z1c| < 2^15
     uint32_t k1;          // least multiple of q >= 2^30 + 2^15: offset of the reduction-free first stage
@@ -298,49 +299,86 @@ __device__ __forceinline__ uint32_t fp_mul(uint32_t yb, uint32_t w, float wq, fl
     return __float_as_uint(qf) * m.negq + t;
 }
 
-// Forward transform of RAW centred int16 coefficients with FP32-assisted butterflies.  Values stay biased
-// throughout (inputs x + cq < 2^17, +4q per stage: < 2^17 + 32 q < 2^21 < 2^23); outputs are UNBIASED lazy
-// values < 2^21 PLUS FP_BIAS in layout B (what ntt_fwd_256 would deliver, up to multiples of q, plus the bias).
+// Forward transform of RAW centred int16 coefficients with FP32-assisted butterflies, two stages at a time.
+// A pair of Cooley-Tukey stages acts on quadruples (a, b, c, d) = r[i], r[i+h], r[i+2h], r[i+3h]:
+//     first stage   a' = a + Tc, c' = a - Tc, b' = b + Td, d' = b - Td            (Tc = c*w, Td = d*w)
+//     second stage  a'' = a' + T1, b'' = a' - T1, c'' = c' + T2, d'' = c' - T2    (T1 = b'*w0, T2 = d'*w1)
+// Only b' and d' are multiplied again, so a' and c' are never formed: a'' = a + Tc + T1, b'' = a + Tc - T1,
+// c'' = a - Tc + T2, d'' = a - Tc - T2 are four 3-input adds - 6 adds per quadruple instead of 8, 18 instructions instead
+// of 20 (round 2; k_verify 4.25 -> see DESIGN.md).  A 3-input add has no slot for the "+4q" that kept differences
+// positive, so positivity comes from the INPUT offset instead: products are T in (0.87 q, 3.13 q), every stage moves a
+// value by at most 3.13 q either way, and inputs enter as x + cq + 26 q (in_off): after eight stages values lie in
+// (0.9 q, cq + 2^15 + 52 q) - non-negative, and below 2^22 for every q < 2^16, where the FP32 quotient estimate is exact
+// to +-1.  Values stay biased throughout; outputs are UNBIASED lazy values < 2^22 PLUS FP_BIAS in layout B.
+// x + y + z and friends as ONE IADD3 each: two dependent PTX adds in an asm block (ptxas fuses them; written in C++ the
+// compiler regroups the four sums of a quadruple around their common a + tc / a - tc and is back at eight adds)
+__device__ __forceinline__ uint32_t add3_pp(uint32_t x, uint32_t y, uint32_t z) {
+    uint32_t o;
+    asm("{ .reg .u32 t; add.u32 t, %1, %2; add.u32 %0, t, %3; }" : "=r"(o) : "r"(x), "r"(y), "r"(z));
+    return o;
+}
+__device__ __forceinline__ uint32_t add3_pm(uint32_t x, uint32_t y, uint32_t z) {   // x + y - z
+    uint32_t o;
+    asm("{ .reg .u32 t; add.u32 t, %1, %2; sub.u32 %0, t, %3; }" : "=r"(o) : "r"(x), "r"(y), "r"(z));
+    return o;
+}
+__device__ __forceinline__ uint32_t add3_mm(uint32_t x, uint32_t y, uint32_t z) {   // x - y - z
+    uint32_t o;
+    asm("{ .reg .u32 t; sub.u32 t, %1, %2; sub.u32 %0, t, %3; }" : "=r"(o) : "r"(x), "r"(y), "r"(z));
+    return o;
+}
+
+// RAW = true: a and b arrive without the input offset `off` (it joins a's explicit add and b's 3-input adds)
+template <bool RAW, typename GET>
+__device__ __forceinline__ void fp_quad(uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d, int kA, int kB0, int kB1,
+                                        const ModQ& m, GET&& get, uint32_t off = 0) {
+    uint32_t w_, kw_;
+    float wq_, cst_;
+    get(kA, w_, wq_, cst_, kw_);
+    const uint32_t tc = fp_mul(c, w_, wq_, cst_, kw_, m), td = fp_mul(d, w_, wq_, cst_, kw_, m);
+    uint32_t b1, d1;
+    if (RAW) {
+        b1 = add3_pp(b, off, td);
+        d1 = add3_pm(b, off, td);
+        a = a + off + m.zero;
+    } else {
+        b1 = b + td + m.zero;
+        d1 = b - td + m.zero;
+    }
+    get(kB0, w_, wq_, cst_, kw_);
+    const uint32_t t1 = fp_mul(b1, w_, wq_, cst_, kw_, m);
+    get(kB1, w_, wq_, cst_, kw_);
+    const uint32_t t2 = fp_mul(d1, w_, wq_, cst_, kw_, m);
+    // grouped so that no two results share a subexpression
+    const uint32_t na = add3_pp(a, t1, tc), nb = add3_pm(a, tc, t1), nc = add3_pm(a, t2, tc), nd = add3_mm(a, t2, tc);
+    a = na; b = nb; c = nc; d = nd;
+}
+
 template <typename TW>
 __device__ __forceinline__ void ntt_fwd_256_fp(const int (&x)[EPT], uint32_t (&r)[EPT], const ModQ& m,
                                                const StageConstF& sc, const TW& tw, uint32_t* xb, int lane) {
-    // stage 1: only the multiplied operands are biased explicitly; the others take the input offset
-    // inside the butterfly's 3-input adds
+    auto uni = [&](int k, uint32_t& w_, float& wq_, float& cst_, uint32_t& kw_) {
+        w_ = sc.w[k]; wq_ = sc.wq[k]; cst_ = sc.cst[k]; kw_ = sc.kw[k];
+    };
+    auto per_lane = [&](int k, uint32_t& w_, float& wq_, float& cst_, uint32_t& kw_) { tw.get(k, w_, wq_, cst_, kw_); };
+    // stages 1 + 2 (distances 8, 4): the inputs take their offset on the way in
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const uint32_t t = fp_mul((uint32_t)x[j + 8] + m.in_off, sc.w[1], sc.wq[1], sc.cst[1], sc.kw[1], m);
-        r[j + 8] = (uint32_t)x[j] + m.in_off_q4 - t;
-        r[j] = (uint32_t)x[j] + m.in_off + t;
+    for (int j = 0; j < 4; ++j) {
+        r[j] = (uint32_t)x[j];
+        r[j + 4] = (uint32_t)x[j + 4];
+        r[j + 8] = (uint32_t)x[j + 8] + m.in_off + m.zero;
+        r[j + 12] = (uint32_t)x[j + 12] + m.in_off + m.zero;
+        fp_quad<true>(r[j], r[j + 4], r[j + 8], r[j + 12], 1, 2, 3, m, uni, m.in_off);
     }
+    // stages 3 + 4 (distances 2, 1)
 #pragma unroll
-    for (int s = 2; s <= 4; ++s) {
-        const int len = 8 >> (s - 1);
-#pragma unroll
-        for (int j = 0; j < EPT; ++j) {
-            if (j & len) continue;
-            const int k = (1 << (s - 1)) + (j >> (5 - s));
-            const uint32_t t = fp_mul(r[j + len], sc.w[k], sc.wq[k], sc.cst[k], sc.kw[k], m);
-            r[j + len] = r[j] + m.q4 - t;
-            r[j] = r[j] + t + m.zero;
-        }
-    }
+    for (int g = 0; g < 4; ++g) fp_quad<false>(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3], 4 + g, 8 + 2 * g, 9 + 2 * g, m, uni);
     xpose_a_to_b(r, xb, lane);
+    // stages 5 + 6, 7 + 8: the same index pattern on the per-lane twiddles (LaneTwF indexing = stage index - 1)
 #pragma unroll
-    for (int s = 5; s <= 8; ++s) {
-        const int len = 256 >> s;
-        const int base = (1 << (s - 5)) - 1;
+    for (int j = 0; j < 4; ++j) fp_quad<false>(r[j], r[j + 4], r[j + 8], r[j + 12], 0, 1, 2, m, per_lane);
 #pragma unroll
-        for (int j = 0; j < EPT; ++j) {
-            if (j & len) continue;
-            const int k = base + (j >> (9 - s));
-            uint32_t w_, kw_;
-            float wq_, cst_;
-            tw.get(k, w_, wq_, cst_, kw_);
-            const uint32_t t = fp_mul(r[j + len], w_, wq_, cst_, kw_, m);
-            r[j + len] = r[j] + m.q4 - t;
-            r[j] = r[j] + t + m.zero;
-        }
-    }
+    for (int g = 0; g < 4; ++g) fp_quad<false>(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3], 3 + g, 7 + 2 * g, 8 + 2 * g, m, per_lane);
     // outputs stay BIASED (r + FP_BIAS): the caller's multiply-accumulate removes the bias once per slot
 }
 

@@ -56,30 +56,12 @@ __device__ __forceinline__ void store_coef_a(int16_t* __restrict__ p, const uint
     for (int j = 0; j < EPT; ++j) p[lane + 16 * j] = (int16_t)finish_coef(r[j], m);
 }
 
-// sparse (index, coefficient) pairs -> dense polynomial in layout A (via the transposition buffer)
-__device__ __forceinline__ void load_pairs_a(uint32_t (&r)[EPT], const int16_t* __restrict__ pairs, int wt,
-                                             uint32_t* xb, int lane, uint32_t cq) {
-#pragma unroll
-    for (int j = 0; j < EPT; ++j) xb[XROW * j + lane] = 0;
-    __syncwarp();
-    const uint32_t* pp = reinterpret_cast<const uint32_t*>(pairs);
-    for (int e = lane; e < wt; e += LANES) {
-        uint32_t pr = __ldg(pp + e);
-        int idx = (int)(pr & 0xFFu);                 // d = 256
-        int coef = (int)(int16_t)(pr >> 16);
-        xb[XROW * (idx >> 4) + (idx & 15)] = (uint32_t)coef;
-    }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < EPT; ++j) r[j] = xb[XROW * j + lane] + cq;
-    __syncwarp();
-}
-
 // key_ch rows in shared memory: the 16 slots of lane t start at word XROW*t (pitch 20, like the
 // transposition buffer) so that the 128-bit reads of a quarter-warp fall in 8 distinct bank groups.
 constexpr int AROW = LANES * XROW;   // 320 words per row
 
-// same, but as raw signed coefficients (input of the FP32-assisted transform)
+// sparse (index, coefficient) pairs -> dense polynomial in layout A (via the transposition buffer), as raw signed
+// coefficients (input of the FP32-assisted transform)
 __device__ __forceinline__ void load_pairs_raw(int (&x)[EPT], const int16_t* __restrict__ pairs, int wt, uint32_t* xb,
                                                int lane) {
 #pragma unroll
@@ -247,10 +229,6 @@ __global__ void __launch_bounds__(RBS, 4) k_matvec(ModQ m, StageConst sc, StageC
 // Asynchronous global->shared staging (LDGSTS, L2-only) used by k_sign and k_verify: each half-warp owns two
 // stage buffers and keeps the next two rows of its work list in flight while it works on the current one, so
 // HBM latency never reaches the scoreboard.
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
