@@ -25,6 +25,13 @@ cap verify k_verify 2
 cap sampler_challenge k_sampler 5
 cap sign k_sign 0
 cap agg_coefs_il k_agg_coefs_il 0
-cap agg_partial k_agg_partial 1
 cap matvec k_matvec 0
+# the BKLM algebra kernels at the configured aggregate size (2^16 signatures per launch)
+CAP="python bench.py --steps 1 --warmup 3 $SMALL --log2n 16 --bklm-log2n 16"
+cap agg_partial k_agg_partial 1
+cap aggv_partial k_aggv_partial 1
 ls -la $O | grep prof_${R}
+python tools/sign_timing.py 128 20 2>&1 | tail -1
+python tools/sign_timing.py 256 18 2>&1 | tail -1
+python tools/verify_timing.py 128 20 10 2>&1 | tail -1
+python tools/verify_timing.py 256 18 10 2>&1 | tail -1
