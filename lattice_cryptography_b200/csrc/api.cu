@@ -632,6 +632,7 @@ int lcb_ctx_create(lcb_ctx** out, int device, int secpar, int q, int d, int l) {
         m.dlim_lo = (uint32_t)lim;
         m.dlim_hi = (uint32_t)(lim >> 32);
         m.kq18 = (((1u << 18) + uq - 1) / uq) * uq;
+        m.kw0 = (uint32_t)((uint64_t)(0x4B400000u + 2u) * uq);
     }
     for (int k = 0; k < 16; ++k) {
         c->ring.sc.w[k] = t.w[k];

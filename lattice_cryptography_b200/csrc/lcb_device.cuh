@@ -63,6 +63,7 @@ struct ModQ {
     uint32_t qinv_lo, qinv_hi;    // q^-1 mod 2^64
     uint32_t dlim_lo, dlim_hi;    // floor((2^64 - 1) / q)
     uint32_t kq18;                // least multiple of q >= 2^18: keeps acc - (rhs + corr) non-negative
+    uint32_t kw0;                 // (0x4B400000 + 2) * q mod 2^32: constant part of the FP32-assisted twiddle offset kw
 };
 
 // Warp-uniform twiddles of stages 1..4 (zeta index k = 1..15), forward and inverse.
@@ -100,13 +101,30 @@ struct LaneTwF {                // per-lane stages 5..8, same indexing as LaneTw
         w_ = w[k]; wq_ = wq[k]; cst_ = cst[k]; kw_ = kw[k];
     }
 };
-// The same 15 twiddles read from a shared-memory row {w, wq, cst, kw}[15] at every use (one LDS.128 each):
-// frees 60 registers per thread at the price of 15 shared loads per transform.
+// The same per-lane twiddles read from a shared-memory row at every use (frees 60 registers per thread), in two forms:
+//   LaneTwFShared   {w, wq, cst, kw}: one LDS.128 per twiddle - four shared-memory wavefronts per warp, no arithmetic;
+//   LaneTwFShared2  {w, wq}: one LDS.64 (two wavefronts); cst = 1.5*2^23 - 2^23*(w/q) and kw = (0x4B400000 + 2) q -
+//                   0x4B000000 w are re-derived with one FFMA and one IMAD - bit-identical to the table values (the FFMA
+//                   rounds the same real number once; the IMAD is exact mod 2^32).
+// Which one wins depends on what binds the kernel (measured, round 2): k_sign sat at 86 % of the L1/shared-memory
+// pipeline with 31 twiddle rows per polynomial as 63 % of its wavefronts (mio-throttle + short-scoreboard = 33 % of the
+// warp samples) and gains 4.6 % from the short rows (6.36 -> 6.07 ms per 2^20); k_verify (15 rows per polynomial, 80 % of
+// the pipeline but 71 % issue-active) loses 5 % to the 30 extra instructions per row (4.20 -> 4.42 ms) and keeps the long rows.
 struct LaneTwFShared {
     const uint4* row;
     __device__ __forceinline__ void get(int k, uint32_t& w_, float& wq_, float& cst_, uint32_t& kw_) const {
         const uint4 v = row[k];
         w_ = v.x; wq_ = __uint_as_float(v.y); cst_ = __uint_as_float(v.z); kw_ = v.w;
+    }
+};
+struct LaneTwFShared2 {
+    const uint2* row;
+    uint32_t kw0;            // (0x4B400000 + 2) * q mod 2^32
+    __device__ __forceinline__ void get(int k, uint32_t& w_, float& wq_, float& cst_, uint32_t& kw_) const {
+        const uint2 v = row[k];
+        w_ = v.x; wq_ = __uint_as_float(v.y);
+        cst_ = __fmaf_rn(wq_, -8388608.0f, 12582912.0f);
+        kw_ = w_ * (0u - FP_BIAS) + kw0;
     }
 };
 

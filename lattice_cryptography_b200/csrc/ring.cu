@@ -336,8 +336,8 @@ __device__ __forceinline__ void load_u16x16_smem(uint32_t (&r)[EPT], const unsig
 }
 
 constexpr int SIGN_STAGE_BYTES = 2 * (2 * D * 2) + 32;   // two (sk_left row, sk_right row) pairs per half-warp
-constexpr int ITW_ROW = 31;           // uint4 per lane of NttTables::inv_lane: 124-word pitch, conflict-free LDS.128
-constexpr int ITW_BYTES = LANES * ITW_ROW * 16;
+constexpr int ITW_ROW = 31;           // uint2 {w, w/q} per lane from NttTables::inv_lane: 62-word pitch, conflict-free LDS.64
+constexpr int ITW_BYTES = LANES * ITW_ROW * 8;
 constexpr int SIGN_BLOCKS = 5;        // resident blocks per SM k_sign is compiled for
 
 // sig = sk_left ** c + sk_right.  Both transforms are FP32-assisted (round 2): the challenge goes through
@@ -351,13 +351,16 @@ __global__ void __launch_bounds__(RBS, SIGN_BLOCKS) k_sign(ModQ m, StageConstF s
     uint32_t* xbuf = smem;
     unsigned char* stage = reinterpret_cast<unsigned char*>(xbuf + (RBS / 32) * XWARP);
     uint4* twtab = reinterpret_cast<uint4*>(stage + HWB * SIGN_STAGE_BYTES);
-    uint4* itwtab = twtab + LANES * TW_ROW;
+    uint2* itwtab = reinterpret_cast<uint2*>(twtab + LANES * TW_ROW);      // short rows: k_sign is bound by the shared-memory pipeline
     const HalfWarp h = half_warp(xbuf);
     stage += h.slot * SIGN_STAGE_BYTES;
-    for (int e = threadIdx.x; e < LANES * ITW_ROW; e += blockDim.x) itwtab[e] = __ldg(&tab->inv_lane[0][0] + e);
+    for (int e = threadIdx.x; e < LANES * ITW_ROW; e += blockDim.x) {
+        const uint4 v = __ldg(&tab->inv_lane[0][0] + e);
+        itwtab[e] = make_uint2(v.x, v.y);
+    }
     fill_tw_shared(twtab, tab);
     const LaneTwFShared twf{twtab + h.lane * TW_ROW};
-    const LaneTwFShared itwf{itwtab + h.lane * ITW_ROW};
+    const LaneTwFShared2 itwf{itwtab + h.lane * ITW_ROW, m.kw0};
     const int64_t first = (int64_t)blockIdx.x * HWB, stride = (int64_t)gridDim.x * HWB;
     const int64_t trips = first < n ? (n - first + stride - 1) / stride : 0;   // uniform over the block
     // work list of this half-warp: row pair i (sk_left[i], sk_right[i]) of item(it); the cursor runs 2 ahead as a

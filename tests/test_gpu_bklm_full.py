@@ -142,3 +142,44 @@ def test_aggregate_verify_verdict_over_eight_shards(world):
     wrong = vpart.copy()
     wrong[5] += 1
     assert eng.aggverify_finish(wrong.astype(np.int32), ag, total, total, avf_bd, D) is False
+
+
+@pytest.mark.parametrize('secpar,q,l', [(128, 11777, 13), (256, 39937, 23)])
+def test_aggregate_partial_shapes_and_extremes(secpar, q, l):
+    """k_agg_partial on synthetic rows: every count around its batching (4 rows per warp, 8 warps per block), rotations 0
+    and 255, both signs, coefficients at the int16 extremes the verifier admits (|x| <= q // 2) - against numpy.  The kernel
+    reads wrapped positions from a complemented copy of the row and repairs the sum with a per-rotation histogram: the
+    cases here are the ones that repair has to get right (all rows wrapped / none wrapped / one row only)."""
+    from lattice_cryptography_b200 import Engine, make_scheme
+    eng = Engine(secpar, q, D, l)
+    sch = make_scheme(sk_bd=1, sk_wt=D, ch_bd=1, ch_wt=20)
+    rng = np.random.default_rng(secpar)
+    for count in (1, 2, 3, 4, 5, 31, 32, 33, 127, 128, 129, 1000, 4099):
+        sigs = rng.integers(-(q // 2), q // 2 + 1, (count, l, D), dtype=np.int16)
+        ks = rng.integers(0, D, count).astype(np.int16)
+        ss = rng.choice(np.array([-1, 1], dtype=np.int16), count)
+        if count >= 3:
+            ks[0], ks[1], ks[2] = 0, 255, 1
+            sigs[1] = q // 2
+            sigs[2] = -(q // 2)
+        for variant in ('mixed', 'all_k255', 'all_k0', 'all_negative'):
+            k2, s2 = ks.copy(), ss.copy()
+            if variant == 'all_k255':
+                k2[:] = 255
+            elif variant == 'all_k0':
+                k2[:] = 0
+            elif variant == 'all_negative':
+                s2[:] = -1
+            pairs = np.ascontiguousarray(np.stack([k2, s2], axis=1)[:, None, :])
+            got = eng.aggregate_partial(sch, sigs, pairs).astype(np.int64)
+            p = np.arange(D)
+            src = (p[None, :] - k2[:, None].astype(np.int64)) & (D - 1)
+            sign = np.where(p[None, :] < k2[:, None], -1, 1) * s2[:, None].astype(np.int64)
+            rot = np.take_along_axis(sigs.astype(np.int64), np.broadcast_to(src[:, None, :], (count, l, D)), axis=2)
+            want = (rot * sign[:, None, :]).sum(axis=0)
+            assert np.array_equal((got - want) % q, np.zeros_like(want)), (count, variant)
+            fin = eng.aggregate_finish(got.astype(np.int32)).astype(np.int64)
+            cen = want % q
+            cen = np.where(cen > q // 2, cen - q, cen)
+            assert np.array_equal(fin, cen), (count, variant)
+    eng.close()

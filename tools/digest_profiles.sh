@@ -10,6 +10,7 @@ for rep in gpurun_out/prof_${R}_*.ncu-rep; do
   # what the captured launch processed (tools/refresh_profiles.sh captures `bench.py --log2n 18`) and the commit the
   # binary was built from: bench.py only quotes digests that carry this line
   case "$k" in
+    *aggv_partial*|*agg_partial*) units=65536 ;;
     *verify*|*sign*) units=262144 ;;
     *) units= ;;
   esac
