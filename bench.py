@@ -843,7 +843,13 @@ def engine_arm(a):
                                  'frac': hbm_achieved / peaks['hbm_gbs'], 'algorithmic_bytes_per_unit': unit_bytes,
                                  'algorithmic_bytes_per_launch': unit_bytes * n, 'peak_source': peaks['source'] + ' hbm_gbs',
                                  'note': 'secondary figure: the kernel needs 7.8 KB per ~140 k instructions, HBM does not bind'},
-                         'ncu': ncu},
+                         'ncu': ncu,
+                         # what the kernel really issues (committed ncu digest of this kernel x this launch's live time):
+                         # the model above counts 8 instructions per butterfly, the kernel needs 4.5, so `frac` (work
+                         # done per peak issue rate) sits above the share of issue slots actually used
+                         'executed': ({'thread_instr_per_unit': ncu['warp_instr_per_unit'] * 32,
+                                       'issue_slot_frac': ncu['warp_instr_per_unit'] * n / (k_ms * 1e-3) /
+                                                          (148 * 4 * peaks['sm_max_mhz'] * 1e6)} if ncu else None)},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'steps': a.e2e_steps, 'host_cpus_bound_per_rank': numa_cpus,
                     'h2d_gbs_per_rank': h2d * a.e2e_steps / float(e2e_s.item()) / 1e9,
