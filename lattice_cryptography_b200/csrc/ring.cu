@@ -13,7 +13,6 @@
 // for the life of the kernel; accumulation of the row-vector product is 64-bit (IMAD.WIDE) with a
 // single reduction per output coefficient.  Grids are persistent: (#SM x resident blocks) blocks
 // striding over the batch.
-#include <cstdlib>
 #include "engine.h"
 
 namespace lcb {
@@ -450,35 +449,7 @@ __device__ __forceinline__ void load_u14x16(uint32_t (&r)[EPT], const uint32_t* 
 // SIG_BITS / VK_BITS: 0 = int16 coefficients / uint16 slots; otherwise the inputs are rows of the packed wire
 // format (wire.cu): signatures SIG_BITS bits per coefficient with bias sig_bias, keys VK_BITS (14) bits per slot.
 // The packed rows ride through the same cp.async stage buffers and are expanded on the way into registers.
-// BULK: rows staged by one cp.async.bulk (1-D TMA) per row and half-warp, completion on an mbarrier, instead of one 16-byte
-// cp.async per lane and 16 bytes (measured).  Selected at run time by
-// LCB_VERIFY_BULK=1; off by default.
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-
-template <bool CHECK_WT, int SIG_BITS, int VK_BITS, bool BULK>
+template <bool CHECK_WT, int SIG_BITS, int VK_BITS>
 __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageConst sc, StageConstF scf, const NttTables* __restrict__ tab,
                                                 const uint32_t* __restrict__ a_hat_g, int l,
                                                 const int16_t* __restrict__ vec_coef,
@@ -496,16 +467,6 @@ __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageCons
     const HalfWarp h = half_warp(xbuf);
     unsigned char* stage = stage_base + h.slot * STAGE_HALF_BYTES;
     uint4* twtab = reinterpret_cast<uint4*>(stage_base + HWB * STAGE_HALF_BYTES);
-    // two mbarriers per half-warp (one per stage buffer), behind the twiddle table
-    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(reinterpret_cast<unsigned char*>(twtab) + TW_BYTES) + 16u * (unsigned)h.slot;
-    if (BULK) {
-        if (h.lane == 0) {
-            mbar_init(bar0, 1);
-            mbar_init(bar0 + 8, 1);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
     fill_tw_shared(twtab, tab);
     const LaneTwFShared twf{twtab + h.lane * TW_ROW};
     // The FP32-assisted transform returns biased values (r + FP_BIAS); the row-vector product then carries
@@ -540,18 +501,10 @@ __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageCons
     auto issue = [&]() {
         if (pf_left > 0) {
             LCB_CHECK(src >= rows_base && (src - rows_base) + ROW_BYTES <= n * l * ROW_BYTES);   // a row of the batch
-            if (BULK) {
-                if (h.lane == 0) {                  // src and dst0 of lane 0 are the row's first byte
-                    const unsigned bar = bar0 + (pf_off ? 8u : 0u);
-                    mbar_expect_tx(bar, ROW_BYTES);
-                    bulk_g2s(dst0 + pf_off, src, ROW_BYTES, bar);
-                }
-            } else {
 #pragma unroll
-                for (int o = 0; o < ROW_BYTES; o += 16 * LANES)
-                    if (o + 16 * h.lane < ROW_BYTES)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + pf_off + o), "l"(src + o) : "memory");
-            }
+            for (int o = 0; o < ROW_BYTES; o += 16 * LANES)
+                if (o + 16 * h.lane < ROW_BYTES)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + pf_off + o), "l"(src + o) : "memory");
             src += ROW_BYTES;
             pf_off ^= (unsigned)(D * 2);
             if (++pf_i == l) {
@@ -561,12 +514,11 @@ __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageCons
                 src = pf_item < n ? src + (stride - 1) * l * ROW_BYTES : rows_base + (n - 1) * l * ROW_BYTES;
             }
         }
-        if (!BULK) cp_async_commit();
+        cp_async_commit();
     };
     issue();
     issue();
     unsigned cur = 0;
-    unsigned seq = 0;                           // BULK: rows consumed so far; buffer seq & 1 is in phase (seq >> 1) & 1
     for (int64_t it = 0; it < trips; ++it) {
         const int64_t raw = first + it * stride + h.slot;
         const bool live = raw < n;
@@ -577,13 +529,8 @@ __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageCons
         bool bad = false;
         int hi = 0, lo = 0;                     // running max / min coefficient of the whole vector
         for (int i = 0; i < l; ++i) {
-            if (BULK) {
-                mbar_wait(bar0 + 8u * cur, (seq >> 1) & 1u);
-                ++seq;
-            } else {
-                cp_async_wait<1>();
-                __syncwarp();
-            }
+            cp_async_wait<1>();
+            __syncwarp();
             int pre[EPT];
             if (SIG_BITS == 0) {
                 const unsigned sp = (unsigned)__cvta_generic_to_shared(stage + cur * (D * 2) + 2 * h.lane);
@@ -953,7 +900,7 @@ inline unsigned persistent_grid(int64_t items, int per_block, int num_sms, int r
 }
 
 inline size_t ring_smem(int l) { return (size_t)l * AROW * 4 + (size_t)(RBS / 32) * XWARP * 4; }
-inline size_t verify_smem(int l) { return ring_smem(l) + (size_t)HWB * STAGE_HALF_BYTES + (size_t)TW_BYTES + (size_t)HWB * 16; }   // + mbarriers (BULK)
+inline size_t verify_smem(int l) { return ring_smem(l) + (size_t)HWB * STAGE_HALF_BYTES + (size_t)TW_BYTES; }
 
 template <typename K>
 cudaError_t allow_smem(K kernel, size_t smem) {
@@ -1019,9 +966,7 @@ cudaError_t launch_verify_t(const RingCtx& c, const void* vec, const void* vk, c
                             uint8_t* verdict, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     size_t smem = verify_smem(c.l);
-    static const bool bulk = [] { const char* e = std::getenv("LCB_VERIFY_BULK"); return e && e[0] == '1'; }();
-    auto kern = bulk ? (wt < D ? k_verify<true, SIG_BITS, VK_BITS, true> : k_verify<false, SIG_BITS, VK_BITS, true>)
-                     : (wt < D ? k_verify<true, SIG_BITS, VK_BITS, false> : k_verify<false, SIG_BITS, VK_BITS, false>);
+    auto kern = wt < D ? k_verify<true, SIG_BITS, VK_BITS> : k_verify<false, SIG_BITS, VK_BITS>;
     cudaError_t e = allow_smem(kern, smem);
     if (e != cudaSuccess) return e;
     unsigned grid = persistent_grid(n, HWB, c.num_sms, resident_blocks(kern, RBS, smem));
