@@ -383,8 +383,12 @@ int run_agg_coefs(lcb_ctx* c, const lcb_scheme* sch, const uint8_t* d_agmsg, int
         uint8_t* salts = nullptr;
         int32_t* lens = nullptr;
         CK(c, cudaMallocAsync((void**)&salts, (size_t)count * SALT_BYTES, c->stream));
-        CK(c, cudaMallocAsync((void**)&lens, (size_t)count * sizeof(int32_t), c->stream));
-        cudaError_t e = launch_index_salts(a, salts, lens, c->stream);
+        cudaError_t e = cudaMallocAsync((void**)&lens, (size_t)count * sizeof(int32_t), c->stream);
+        if (e != cudaSuccess) {
+            cudaFreeAsync(salts, c->stream);
+            return fail_cuda(c, e, "general aggregation coefficients");
+        }
+        e = launch_index_salts(a, salts, lens, c->stream);
         a.stream_salts = salts;
         a.stream_salt_len = lens;
         if (e == cudaSuccess) e = sampler_scratch(c, a);
