@@ -321,7 +321,12 @@ __global__ void __launch_bounds__(RBS, 4) k_matvec(ModQ m, StageConst sc, StageC
     }
 }
 
-constexpr int VERIFY_BLOCKS = 4;     // resident blocks per SM k_verify is compiled for
+#ifdef LCB_EXP_VERIFY_BLOCKS
+constexpr int VERIFY_BLOCKS = LCB_EXP_VERIFY_BLOCKS;
+#else
+constexpr int VERIFY_BLOCKS = 4;     // resident blocks per SM k_verify is compiled for (3 at 155 registers: +1.2 %,
+                                     // 5 at 96 registers: +1.7 %; profiles/exp_r2_verify_regs.txt)
+#endif
 
 // 16 slots of one lane from a staged 512-byte row.  The row is staged SPLIT: the first 16 bytes of every lane's 32
 // (256 bytes), then the second 16 bytes of every lane - so that the eight lanes of a quarter-warp read 128
@@ -338,7 +343,12 @@ __device__ __forceinline__ void load_u16x16_smem(uint32_t (&r)[EPT], const unsig
 constexpr int SIGN_STAGE_BYTES = 2 * (2 * D * 2) + 32;   // two (sk_left row, sk_right row) pairs per half-warp
 constexpr int ITW_ROW = 31;           // uint2 {w, w/q} per lane from NttTables::inv_lane: 62-word pitch, conflict-free LDS.64
 constexpr int ITW_BYTES = LANES * ITW_ROW * 8;
-constexpr int SIGN_BLOCKS = 5;        // resident blocks per SM k_sign is compiled for
+#ifdef LCB_EXP_SIGN_BLOCKS
+constexpr int SIGN_BLOCKS = LCB_EXP_SIGN_BLOCKS;
+#else
+constexpr int SIGN_BLOCKS = 4;        // resident blocks per SM k_sign is compiled for (121 registers; 5 blocks at 95
+                                      // registers: 6.10 instead of 6.03 ms per 2^20, 6 at 80: 6.13 ms)
+#endif
 
 // sig = sk_left ** c + sk_right.  Both transforms are FP32-assisted (round 2): the challenge goes through
 // ntt_fwd_256_fp, every row through the decimation-in-time inverse ntt_inv_256_fp, whose closing twist absorbs the
@@ -471,7 +481,11 @@ __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageCons
     const LaneTwFShared twf{twtab + h.lane * TW_ROW};
     // The FP32-assisted transform returns biased values (r + FP_BIAS); the row-vector product then carries
     // FP_BIAS * sum_i a_hat[i][slot], removed once per slot before the comparison.
-    uint32_t corr[EPT];
+    // The correction depends on (lane, slot index) only and is used once per item: a 16 x 16 table per block in shared
+    // memory (every half-warp writes the same values) instead of 16 registers held across the row loop - the kernel
+    // wants 155 registers and is compiled for 128: 4.135 -> 4.06 ms per 2^20 (profiles/exp_r2_verify_regs.txt).
+    uint32_t* corr = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(twtab) + TW_BYTES) + h.lane;
+#define CORR(k) corr[(k) * LANES]
     {
         uint32_t colsum[EPT];
 #pragma unroll
@@ -481,21 +495,25 @@ __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageCons
             for (int k = 0; k < EPT; ++k) colsum[k] += a_hat[i * AROW + XROW * h.lane + k];
         }
 #pragma unroll
-        for (int k = 0; k < EPT; ++k) corr[k] = m.kq18 - mulmod_full(barrett_full(colsum[k], m), m.bias_mod_q, m);
+        for (int k = 0; k < EPT; ++k) CORR(k) = m.kq18 - mulmod_full(barrett_full(colsum[k], m), m.bias_mod_q, m);
     }
+    __syncthreads();            // make the table visible before the first read
     constexpr bool check_wt = CHECK_WT;
 
-    const int64_t first = (int64_t)blockIdx.x * HWB, stride = (int64_t)gridDim.x * HWB;
-    const int64_t trips = first < n ? (n - first + stride - 1) / stride : 0;   // uniform over the block
+    // item indices are 32-bit (the launcher refuses n > 2^30: that many signatures would be terabytes); 64-bit
+    // arithmetic only where an address is formed
+    const unsigned first = blockIdx.x * HWB, stride = gridDim.x * HWB;
+    const unsigned n32 = (unsigned)n;
+    const int trips = first < n32 ? (int)((n32 - first + stride - 1) / stride) : 0;   // uniform over the block
     // work list of this half-warp: polynomial i of item(it), it = 0..trips-1; the prefetch cursor runs 2 ahead.
     // The cursor is a running source pointer and a running shared-memory address: rows of an item are contiguous, so
     // a row costs one 64-bit add; the item arithmetic (and the clamp of the last, partial trip) runs once per item.
     // (The first version recomputed item, clamp and address for every row: 31 instructions per row, 6.5 % of the kernel.)
-    int pf_left = (int)trips;                   // items the cursor has not finished
+    int pf_left = trips;                        // items the cursor has not finished
     int pf_i = 0;
-    int64_t pf_item = first + h.slot;
+    unsigned pf_item = first + h.slot;
     const unsigned char* const rows_base = reinterpret_cast<const unsigned char*>(vec_coef) + 16 * h.lane;
-    const unsigned char* src = rows_base + (pf_item < n ? pf_item : n - 1) * l * ROW_BYTES;
+    const unsigned char* src = rows_base + (int64_t)(pf_item < n32 ? pf_item : n32 - 1) * l * ROW_BYTES;
     const unsigned dst0 = (unsigned)__cvta_generic_to_shared(stage) + 16u * (unsigned)h.lane;
     unsigned pf_off = 0;
     auto issue = [&]() {
@@ -511,7 +529,7 @@ __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageCons
                 pf_i = 0;
                 --pf_left;
                 pf_item += stride;
-                src = pf_item < n ? src + (stride - 1) * l * ROW_BYTES : rows_base + (n - 1) * l * ROW_BYTES;
+                src = pf_item < n32 ? src + (int64_t)(stride - 1) * l * ROW_BYTES : rows_base + (int64_t)(n32 - 1) * l * ROW_BYTES;
             }
         }
         cp_async_commit();
@@ -519,10 +537,10 @@ __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageCons
     issue();
     issue();
     unsigned cur = 0;
-    for (int64_t it = 0; it < trips; ++it) {
-        const int64_t raw = first + it * stride + h.slot;
-        const bool live = raw < n;
-        const int64_t item = live ? raw : n - 1;
+    unsigned raw = first + h.slot;
+    for (int it = 0; it < trips; ++it, raw += stride) {
+        const bool live = raw < n32;
+        const int64_t item = live ? raw : n32 - 1;
         uint64_t acc[EPT];
 #pragma unroll
         for (int i = 0; i < EPT; ++i) acc[i] = 0;
@@ -603,7 +621,7 @@ __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageCons
         }
         bool eq = true;
 #pragma unroll
-        for (int k = 0; k < EPT; ++k) eq &= divisible_by_q(acc[k] + (uint64_t)(corr[k] - rhs[k]), m);   // corr = kq18 - bias term
+        for (int k = 0; k < EPT; ++k) eq &= divisible_by_q(acc[k] + (uint64_t)(CORR(k) - rhs[k]), m);   // corr = kq18 - bias term
         const unsigned votes = __ballot_sync(0xFFFFFFFFu, eq && !bad);
         if (live && h.lane == 0) verdict[item] = (votes & h.mask) == h.mask ? 1 : 0;
     }
@@ -900,7 +918,8 @@ inline unsigned persistent_grid(int64_t items, int per_block, int num_sms, int r
 }
 
 inline size_t ring_smem(int l) { return (size_t)l * AROW * 4 + (size_t)(RBS / 32) * XWARP * 4; }
-inline size_t verify_smem(int l) { return ring_smem(l) + (size_t)HWB * STAGE_HALF_BYTES + (size_t)TW_BYTES; }
+// a_hat + transposition buffers + stage buffers + twiddle table + k_verify's 16 x 16 correction table
+inline size_t verify_smem(int l) { return ring_smem(l) + (size_t)HWB * STAGE_HALF_BYTES + (size_t)TW_BYTES + (size_t)LANES * EPT * 4; }
 
 template <typename K>
 cudaError_t allow_smem(K kernel, size_t smem) {
@@ -965,6 +984,7 @@ cudaError_t launch_verify_t(const RingCtx& c, const void* vec, const void* vk, c
                             const uint16_t* rhs_only, const uint16_t* extra_rhs, int64_t n, int bd, int wt, int sig_bias,
                             uint8_t* verdict, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
+    if (n > ((int64_t)1 << 30)) return cudaErrorInvalidValue;      // 32-bit item indices inside the kernel
     size_t smem = verify_smem(c.l);
     auto kern = wt < D ? k_verify<true, SIG_BITS, VK_BITS> : k_verify<false, SIG_BITS, VK_BITS>;
     cudaError_t e = allow_smem(kern, smem);

@@ -114,8 +114,12 @@ __global__ void __launch_bounds__(128) k_seed_expand(const uint8_t* __restrict__
 // ------------------------------------------------------------------------------------------------
 // Fused SHAKE256 squeeze + decode2polycoefs (sampler_device.cuh), one stream per thread.
 // Shared memory per block: ring [54][P] u32, bmap [8][P] u32, two modulus tables, the piece-weight table.
-template <int P>   // streams (threads) per block; compile-time so that column addressing is shifts, not multiplies
-__global__ void __launch_bounds__(P, 640 / P) k_sampler(SamplerArgs a) {   // 5 x 128 streams resident per SM
+// P = streams (threads) per block; compile-time so that column addressing is shifts, not multiplies
+#ifndef LCB_EXP_SAMPLER_STREAMS
+#define LCB_EXP_SAMPLER_STREAMS 640          // streams resident per SM the sampler is compiled for
+#endif
+template <int P>
+__global__ void __launch_bounds__(P, LCB_EXP_SAMPLER_STREAMS / P) k_sampler(SamplerArgs a) {   // 5 x 128 streams resident per SM
     extern __shared__ uint32_t smem[];
     uint32_t* ring = smem;                       // [RING_WORDS][P]
     uint32_t* bmap = ring + RING_WORDS * P;      // [8][P]   (directly after the ring, see StreamCols)
