@@ -686,8 +686,16 @@ struct KeccakHalfRhoPi<25> {
 // and forming its theta-applied word locally (one dependent exchange per round instead of two, 5 more SHF) changes
 // nothing at one warp per scheduler (173 vs 174 ms) - a lone warp issues one instruction every two cycles whatever
 // the pipe, so the 17 SHFL count as much as the 90 ALU instructions and only the instruction total matters.
+// Rounds per loop body.  A lone warp per scheduler (the regime this form exists for) pays every instruction that is not
+// on the ALU pipe - loop control, the round-constant load - with issue cycles nothing else fills: 8,192 streams of 7,472
+// permutations take 21.6 / 20.5 / 20.3 / 19.8 / 19.3 ms with 1 / 2 / 4 / 8 / 12 rounds per body; all 24 (2,660
+// instructions, 43 KB) overflow the instruction cache: 33 ms (profiles/exp_r2_keccak_half_unroll.txt).
+#ifndef LCB_EXP_HALF_UNROLL
+#define LCB_EXP_HALF_UNROLL 12
+#endif
+constexpr int KECCAK_HALF_UNROLL = LCB_EXP_HALF_UNROLL;
 __device__ __forceinline__ void keccak_f1600_half(KeccakHalf& s, const uint32_t* __restrict__ rc, const KeccakHalfRot& rot) {
-#pragma unroll 2
+#pragma unroll KECCAK_HALF_UNROLL
     for (int round = 0; round < 24; ++round) {
         uint32_t c[5], r1[5];
 #pragma unroll

@@ -636,13 +636,14 @@ unsigned agg_delta_mask(int salt_len, int64_t first, int64_t count) {
 
 bool agg_coefs_two_lane(int64_t n, int num_sms) {
     if (const char* env = getenv("LCB_AGG_LANES")) return atoi(env) == 2;       // tuning knob
-    // Measured on B200 (tools/agg_coefs_timing.py, 59,754 permutations per stream): 8,192 streams 297 -> 164 ms,
-    // 16,384 streams 297 vs 302 ms, 65,536 streams 1,104 -> 1,000 ms.  Two lanes win while the lane pairs still fit
-    // one warp per scheduler (the one-thread form then leaves half the schedulers empty) and again once there are
-    // enough warps for the finer grain to balance (7 instead of 3.5 warps per scheduler); in between both forms put
-    // two warps on the busiest scheduler and tie.
-    const int64_t schedulers = (int64_t)num_sms * 4;
-    return n <= schedulers * 16 || n >= schedulers * 64;
+    // Measured on B200 (tools/agg_coefs_timing.py; profiles/exp_r2_keccak_half_unroll.txt), one thread per sponge
+    // against two lanes per sponge with 12 rounds per loop body and the next block requested a block ahead:
+    // 8,192 streams 2.0 x, 16,384 streams 36.7 vs 36.3 ms, 24,576 streams 70.1 vs 53.6 ms, 32,768 streams 70.1 vs
+    // 70.9 ms, 65,536 streams 3.55 vs 3.98 Gperm/s.  The finer grain never loses more than 1 %, so it is the default
+    // at every size; the one-thread kernel stays for the comparison tests.
+    (void)n;
+    (void)num_sms;
+    return true;
 }
 
 cudaError_t launch_agg_coefs(const SamplerArgs& a, int num_sms, cudaStream_t st) {
@@ -658,9 +659,10 @@ cudaError_t launch_agg_coefs(const SamplerArgs& a, int num_sms, cudaStream_t st)
             if (e != cudaSuccess) return e;
         }
         int64_t blocks = (2 * a.n + ABS2 - 1) / ABS2;
-        // few warps (at most about one per scheduler): nothing hides a load, so request a block ahead (80 registers);
-        // many warps: stay at 64 registers so that 2^16 streams (4,096 warps) are resident at once
-        bool prefetch = 2 * a.n <= (int64_t)num_sms * 4 * 32 * 2;
+        // the next block is requested a block ahead (96 instead of 64 registers): with about one warp per scheduler
+        // nothing else hides the load, and with many warps it still measured 1 - 2 % faster although only 2,960 of the
+        // 4,096 warps of a 2^16-stream launch are then resident at once
+        bool prefetch = true;
         if (const char* env = getenv("LCB_AGG_PREFETCH")) prefetch = atoi(env) != 0;
         auto kern = prefetch ? k_agg_coefs_il<true> : k_agg_coefs_il<false>;
         kern<<<(unsigned)blocks, ABS2, 0, st>>>(a);
