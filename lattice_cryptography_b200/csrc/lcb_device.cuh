@@ -684,8 +684,11 @@ struct KeccakHalfRhoPi<25> {
 // All 32 lanes of the warp must be active and converged.
 // Measured dead end (tools/agg_coefs_timing.py, round 2): fetching the partner's raw odd-rho words and parities up front
 // and forming its theta-applied word locally (one dependent exchange per round instead of two, 5 more SHF) changes
-// nothing at one warp per scheduler (173 vs 174 ms) - a lone warp issues one instruction every two cycles whatever
-// the pipe, so the 17 SHFL count as much as the 90 ALU instructions and only the instruction total matters.
+// nothing at one warp per scheduler (173 vs 174 ms).  What a lone warp pays (tools/halfwarp_bench.cu): two cycles per
+// ALU-pipe instruction, about half a cycle to one cycle per instruction of another pipe (LOP3 + IMAD 1:1 issue at 0.79
+// per cycle; 90 LOP3 + 17 independent SHFL take 190 cycles), so the 90 LOP3/SHF of a round are a floor of 180 cycles
+// and the SHFL, the round-constant load and loop control come on top - hence 12 rounds per loop body below.  Rotations
+// moved to the FMA pipe (IMAD.HI + IMAD by 2^a, no ALU instruction) were measured too: 30.3 instead of 19.3 ms.
 // Rounds per loop body.  A lone warp per scheduler (the regime this form exists for) pays every instruction that is not
 // on the ALU pipe - loop control, the round-constant load - with issue cycles nothing else fills: 8,192 streams of 7,472
 // permutations take 21.6 / 20.5 / 20.3 / 19.8 / 19.3 ms with 1 / 2 / 4 / 8 / 12 rounds per body; all 24 (2,660
