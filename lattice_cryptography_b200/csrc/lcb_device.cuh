@@ -693,12 +693,12 @@ struct KeccakHalfRhoPi<25> {
 // on the ALU pipe - loop control, the round-constant load - with issue cycles nothing else fills: 8,192 streams of 7,472
 // permutations take 21.6 / 20.5 / 20.3 / 19.8 / 19.3 ms with 1 / 2 / 4 / 8 / 12 rounds per body; all 24 (2,660
 // instructions, 43 KB) overflow the instruction cache: 33 ms (profiles/exp_r2_keccak_half_unroll.txt).
-#ifndef LCB_EXP_HALF_UNROLL
-#define LCB_EXP_HALF_UNROLL 12
-#endif
-constexpr int KECCAK_HALF_UNROLL = LCB_EXP_HALF_UNROLL;
+// The cooperative sampler shares its SM's instruction cache between this loop and the decoder warps: there 12 rounds
+// per body cost 3.46 ms per single key generation against 2.81 / 2.74 / 2.75 ms with 2 / 4 / 6 - hence a template
+// parameter: 12 in k_agg_coefs_il, 4 in k_sampler_coop.
+template <int UNROLL>
 __device__ __forceinline__ void keccak_f1600_half(KeccakHalf& s, const uint32_t* __restrict__ rc, const KeccakHalfRot& rot) {
-#pragma unroll KECCAK_HALF_UNROLL
+#pragma unroll UNROLL
     for (int round = 0; round < 24; ++round) {
         uint32_t c[5], r1[5];
 #pragma unroll

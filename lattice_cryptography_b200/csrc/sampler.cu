@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(32 * coop_warps(COOP_MAX_POLYS)) k_sampler_coo
                 for (int j = 0; j < 17; ++j)
                     if (j == i) s.a[j] ^= hv;
             }
-            keccak_f1600_half(s, rc, rot);
+            keccak_f1600_half<4>(s, rc, rot);
         }
         const unsigned total_words = (unsigned)(nd * words_per_poly) + RATE_WORDS + RING_EXTRA;
         unsigned blocks_out = 0;
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(32 * coop_warps(COOP_MAX_POLYS)) k_sampler_coo
                 __syncwarp();
                 if (lane == 0) produced = done + RATE_WORDS;
             }
-            keccak_f1600_half(s, rc, rot);
+            keccak_f1600_half<4>(s, rc, rot);
         }
     } else if ((warp & 3) != 0 && lane == 0 && warp - 1 - warp / 4 < nd) {
         // ---- decoder of polynomial p
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(ABS2) k_agg_coefs_il(SamplerArgs a) {
         }
         have = PREFETCH && interior(g + 17);
         if (have) request(g + 17);
-        keccak_f1600_half(s, rc, rot);
+        keccak_f1600_half<12>(s, rc, rot);
         if (blk + 1 == nb) result = s.a[0];
     }
     // digest bits 0..7 (position) and 15 (sign) of word 0: even lane has bits 0,2,..,14, odd lane 1,3,..,15
