@@ -35,6 +35,7 @@ struct lcb_ctx {
     size_t idx_scratch_bytes = 0;
     uint2* il_scratch = nullptr;         // bit-split copies of the BKLM aggregation message (grow-only)
     size_t il_scratch_bytes = 0;
+    uint32_t* d_mod_tab = nullptr;       // decoder modulus tables for m <= 256 (engine.h), made once
     uint32_t* coop_scratch = nullptr;    // digest scratch of the cooperative low-latency sampler (grow-only)
     size_t coop_scratch_bytes = 0;
     // optional per-kernel CUDA-event timing (lcb_profile_*)
@@ -328,6 +329,7 @@ int fill_sampler(lcb_ctx* c, SamplerArgs& a, const char* salt, const char* suffi
     a.stream_salts = nullptr;
     a.stream_salt_len = nullptr;
     a.coop_digest = nullptr;
+    a.mod_tab = c->d_mod_tab;
     a.idx_bits = logd + c->secpar;
     const int btd = ceil_log2(bd) + 1 + c->secpar;
     a.mag_bits = btd - 1;
@@ -656,6 +658,14 @@ int lcb_ctx_create(lcb_ctx** out, int device, int secpar, int q, int d, int l) {
     c->gen.a_hat = c->d_a_hat;
     c->ring.l = l;
     c->ring.num_sms = prop.multiProcessorCount;
+    {
+        // the sampler's modulus tables (every m <= 256), so that no block computes them (sampler_device.cuh)
+        std::vector<uint32_t> mt(SAMPLER_MOD_TABLE_WORDS);
+        fill_sampler_mod_table(mt.data());
+        if ((e = cudaMalloc(&c->d_mod_tab, mt.size() * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc sampler tables");
+        if ((e = cudaMemcpy(c->d_mod_tab, mt.data(), mt.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess)
+            return bail(e, "cudaMemcpy sampler tables");
+    }
     *out = c;
     return LCB_OK;
 }
@@ -668,6 +678,7 @@ int lcb_ctx_destroy(lcb_ctx* c) {
     if (c->d_gen_tab) cudaFree(c->d_gen_tab);
     if (c->d_a_hat) cudaFree(c->d_a_hat);
     if (c->idx_scratch) cudaFree(c->idx_scratch);
+    if (c->d_mod_tab) cudaFree(c->d_mod_tab);
     if (c->il_scratch) cudaFree(c->il_scratch);
     if (c->coop_scratch) cudaFree(c->coop_scratch);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);

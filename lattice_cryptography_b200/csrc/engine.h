@@ -45,7 +45,12 @@ struct SamplerArgs {
     // cooperative low-latency kernel (few streams): digest scratch, sampler_coop_digest_words() words per stream;
     // nullptr = the ordinary one-thread-per-stream kernel
     uint32_t* coop_digest;
+    // the decoder's modulus tables for every m <= 256 (sampler_mod_table_words() words, made once per context by
+    // fill_sampler_mod_table): floor((2^32-1)/m) [260] | 2^16 mod m [260] | bytes 2^(32k) mod m [257][20]
+    const uint32_t* mod_tab;
 };
+constexpr int SAMPLER_MOD_TABLE_WORDS = 260 + 260 + (257 * 20 + 3) / 4;
+void fill_sampler_mod_table(uint32_t* host_words);      // SAMPLER_MOD_TABLE_WORDS words
 
 cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st);
 cudaError_t launch_seed_expand(const uint8_t* secret, int64_t first, int64_t n, int secpar, uint8_t* out, cudaStream_t st);

@@ -136,8 +136,7 @@ __global__ void __launch_bounds__(P, LCB_EXP_SAMPLER_STREAMS / P) k_sampler(Samp
     const int64_t item = a.paired ? inst >> 1 : inst;
     const bool second = a.paired && (inst & 1);
     const int64_t msg_begin = __ldg(a.off + item), msg_end = __ldg(a.off + item + 1);
-    fill_mod_tables(mutab, r16tab, a.wt);
-    fill_weight_table(wtab, a.wt, a.bd, pieces);
+    load_mod_tables(a.mod_tab, mutab, r16tab, wtab, a.wt, a.bd, pieces);
     __syncthreads();
 
     const InputView iv{reinterpret_cast<const uint32_t*>(second ? a.salt2 : a.salt), second ? a.salt2_len : a.salt_len,
@@ -226,8 +225,7 @@ __global__ void __launch_bounds__(32 * coop_warps(COOP_MAX_POLYS)) k_sampler_coo
     const int pieces = weight_pieces(a.idx_bits, a.mag_bits);
     if (threadIdx.x < 48) rc_sh[threadIdx.x / 24][threadIdx.x % 24] = c_keccak_rc2.v[threadIdx.x / 24][threadIdx.x % 24];
     if (threadIdx.x == 0) produced = 0;
-    fill_mod_tables(mutab, r16tab, a.wt);
-    fill_weight_table(wtab, a.wt, a.bd, pieces);
+    load_mod_tables(a.mod_tab, mutab, r16tab, wtab, a.wt, a.bd, pieces);
     __syncthreads();
     const int64_t inst = blockIdx.x;                         // one block per stream
     const int64_t item = a.paired ? inst >> 1 : inst;
@@ -542,6 +540,21 @@ __global__ void __launch_bounds__(ABS2) k_agg_coefs_il(SamplerArgs a) {
 }
 
 }  // namespace
+
+// The decoder tables for every modulus the fast decoder can meet (m <= 256): floor((2^32-1)/m), 2^16 mod m and the
+// weights 2^(32k) mod m of the 32-bit pieces of a field (sampler_device.cuh: field_small).
+void fill_sampler_mod_table(uint32_t* w) {
+    for (int i = 0; i < SAMPLER_MOD_TABLE_WORDS; ++i) w[i] = 0;
+    uint8_t* wt = reinterpret_cast<uint8_t*>(w + 520);
+    for (uint32_t m = 1; m <= 256; ++m) {
+        w[m] = 0xFFFFFFFFu / m;
+        w[260 + m] = 65536u % m;
+        if (m < 2) continue;
+        const uint32_t r16 = 65536u % m, r32 = (r16 * r16) % m;
+        uint32_t x = 1;
+        for (int k = 0; k < WT_K; ++k) { wt[m * WT_K + k] = (uint8_t)x; x = (x * r32) % m; }
+    }
+}
 
 cudaError_t launch_shake256(const uint8_t* in, const int64_t* off, int64_t n, uint8_t* out, int64_t out_len,
                             cudaStream_t st) {

@@ -124,7 +124,7 @@ struct StreamColsT {
     int pitch;
     const uint32_t* mutab;     // [257] floor((2^32-1)/m)   (block-shared)
     const uint32_t* r16tab;    // [257] 2^16 mod m
-    const uint8_t* wtab;       // [257][wstride] 2^(32k) mod m, rows filled by fill_weight_table
+    const uint8_t* wtab;       // [257][wstride] 2^(32k) mod m, rows copied by load_mod_tables
     int wstride;               // pieces per row
     IdxT* idxs;                // global scratch, index e of this stream at idxs[e * idx_stride]
     int64_t idx_stride;
@@ -140,22 +140,33 @@ __device__ __forceinline__ void fill_mod_tables(uint32_t* mutab, uint32_t* r16ta
 }
 
 // Weights of the 32-bit pieces of a big-endian field modulo m <= 256: wtab[m][k] = 2^(32k) mod m.
-// Only the rows a sampler call can touch are filled: the index moduli D-wt+1 .. D-1 and bd.  A row holds
-// `pieces` = max(2, ceil(widest field / 32)) <= WT_K bytes.
+// Only the rows a sampler call can touch are copied into shared memory: the index moduli D-wt+1 .. D-1 and bd.  A row
+// holds `pieces` = max(2, ceil(widest field / 32)) <= WT_K bytes there (WT_K in the per-context global table).
 constexpr int WT_K = 20;          // MAX_FIELD_BITS / 32 + 1
 __host__ __device__ __forceinline__ int weight_pieces(int idx_bits, int mag_bits) {
     const int w = idx_bits > mag_bits ? idx_bits : mag_bits;
     const int p = (w + 31) >> 5;
     return p < 2 ? 2 : p;
 }
-__device__ __forceinline__ void fill_weight_table(uint8_t* wtab, int wt, int bd, int pieces) {
+// The three tables of the fast decoder, copied from the per-context global table (engine.h: mod_tab; made on the host
+// by fill_sampler_mod_table, sampler.cu): no division or modulo in the kernel.  (Computed in the kernel, the dependent
+// modulo chains of the 21 rows kept warp 0 of every block busy for ~20 us behind 19 ALU-bound warps while its three
+// sibling warps sat at the barrier: 12.8 % of the challenge sampler's warp samples for 0.3 % of its instructions.
+// Removing them changed the kernel's time by nothing - 1.741 vs 1.743 ms per 2^20 challenges, the other warps kept the
+// ALU pipe fed - but a prologue without division routines is the simpler one.)
+__device__ __forceinline__ void load_mod_tables(const uint32_t* __restrict__ tab, uint32_t* mutab, uint32_t* r16tab,
+                                                uint8_t* wtab, int wt, int bd, int pieces) {
+    const int m_first = max(1, D - wt + 1);
+    for (int m = m_first + (int)threadIdx.x; m <= D; m += blockDim.x) {
+        mutab[m] = __ldg(tab + m);
+        r16tab[m] = __ldg(tab + 260 + m);
+    }
+    const uint8_t* gw = reinterpret_cast<const uint8_t*>(tab + 520);
     const int m_lo = max(2, D - wt + 1), m_hi = D - 1;
     for (int i = m_lo + (int)threadIdx.x; i <= m_hi + 1; i += blockDim.x) {
-        const uint32_t m = i <= m_hi ? (uint32_t)i : (uint32_t)bd;
+        const int m = i <= m_hi ? i : bd;
         if (m < 2 || m > 256) continue;
-        const uint32_t r16 = 65536u % m, r32 = (r16 * r16) % m;
-        uint32_t w = 1;
-        for (int k = 0; k < pieces; ++k) { wtab[m * pieces + k] = (uint8_t)w; w = (w * r32) % m; }
+        for (int k = 0; k < pieces; ++k) wtab[m * pieces + k] = __ldg(gw + m * WT_K + k);
     }
 }
 
