@@ -321,12 +321,23 @@ __global__ void __launch_bounds__(RBS, 4) k_matvec(ModQ m, StageConst sc, StageC
     }
 }
 
+// k_verify runs 16 warps per SM at 128 registers however they are grouped; grouped as ONE block of 512 threads they share
+// one key_ch / twiddle / correction copy (62 instead of 164 KB of shared memory per SM at l = 13; the rest serves the L1
+// for the per-item key and challenge loads): 4 x 128 threads 4.075 ms, 2 x 256 3.97 ms, 1 x 512 3.84 ms per 2^20
+// (secpar 256, 2^18: 1.73 / 1.68 / 1.64 ms).  Fewer warps lose in proportion - 5 x 96 threads (15 warps) 4.33 ms,
+// 7 x 64 (14 warps) 4.65 ms - and more registers or more warps do not pay: 3 x 128 at 155 registers +1.2 %, 5 x 128 at
+// 96 registers +1.7 % (profiles/exp_r2_verify_regs.txt).
+#ifdef LCB_EXP_VBS
+constexpr int VBS = LCB_EXP_VBS;
+#else
+constexpr int VBS = 512;                 // threads per block of k_verify
+#endif
 #ifdef LCB_EXP_VERIFY_BLOCKS
 constexpr int VERIFY_BLOCKS = LCB_EXP_VERIFY_BLOCKS;
 #else
-constexpr int VERIFY_BLOCKS = 4;     // resident blocks per SM k_verify is compiled for (3 at 155 registers: +1.2 %,
-                                     // 5 at 96 registers: +1.7 %; profiles/exp_r2_verify_regs.txt)
+constexpr int VERIFY_BLOCKS = 512 / VBS; // resident blocks per SM k_verify is compiled for (16 warps)
 #endif
+constexpr int VHWB = VBS / LANES;        // half-warps (items in flight) per block of k_verify
 
 // 16 slots of one lane from a staged 512-byte row.  The row is staged SPLIT: the first 16 bytes of every lane's 32
 // (256 bytes), then the second 16 bytes of every lane - so that the eight lanes of a quarter-warp read 128
@@ -460,7 +471,7 @@ __device__ __forceinline__ void load_u14x16(uint32_t (&r)[EPT], const uint32_t* 
 // format (wire.cu): signatures SIG_BITS bits per coefficient with bias sig_bias, keys VK_BITS (14) bits per slot.
 // The packed rows ride through the same cp.async stage buffers and are expanded on the way into registers.
 template <bool CHECK_WT, int SIG_BITS, int VK_BITS>
-__global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageConst sc, StageConstF scf, const NttTables* __restrict__ tab,
+__global__ void __launch_bounds__(VBS, VERIFY_BLOCKS) k_verify(ModQ m, StageConst sc, StageConstF scf, const NttTables* __restrict__ tab,
                                                 const uint32_t* __restrict__ a_hat_g, int l,
                                                 const int16_t* __restrict__ vec_coef,
                                                 const uint16_t* __restrict__ vk_ntt,
@@ -472,11 +483,11 @@ __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageCons
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t* a_hat = smem;
     uint32_t* xbuf = smem + l * AROW;
-    unsigned char* stage_base = reinterpret_cast<unsigned char*>(xbuf + (RBS / 32) * XWARP);
+    unsigned char* stage_base = reinterpret_cast<unsigned char*>(xbuf + (VBS / 32) * XWARP);
     copy_a_hat(a_hat, a_hat_g, l);
     const HalfWarp h = half_warp(xbuf);
     unsigned char* stage = stage_base + h.slot * STAGE_HALF_BYTES;
-    uint4* twtab = reinterpret_cast<uint4*>(stage_base + HWB * STAGE_HALF_BYTES);
+    uint4* twtab = reinterpret_cast<uint4*>(stage_base + VHWB * STAGE_HALF_BYTES);
     fill_tw_shared(twtab, tab);
     const LaneTwFShared twf{twtab + h.lane * TW_ROW};
     // The FP32-assisted transform returns biased values (r + FP_BIAS); the row-vector product then carries
@@ -502,7 +513,7 @@ __global__ void __launch_bounds__(RBS, VERIFY_BLOCKS) k_verify(ModQ m, StageCons
 
     // item indices are 32-bit (the launcher refuses n > 2^30: that many signatures would be terabytes); 64-bit
     // arithmetic only where an address is formed
-    const unsigned first = blockIdx.x * HWB, stride = gridDim.x * HWB;
+    const unsigned first = blockIdx.x * VHWB, stride = gridDim.x * VHWB;
     const unsigned n32 = (unsigned)n;
     const int trips = first < n32 ? (int)((n32 - first + stride - 1) / stride) : 0;   // uniform over the block
     // work list of this half-warp: polynomial i of item(it), it = 0..trips-1; the prefetch cursor runs 2 ahead.
@@ -917,9 +928,12 @@ inline unsigned persistent_grid(int64_t items, int per_block, int num_sms, int r
     return (unsigned)(need < cap ? need : cap);
 }
 
-inline size_t ring_smem(int l) { return (size_t)l * AROW * 4 + (size_t)(RBS / 32) * XWARP * 4; }
-// a_hat + transposition buffers + stage buffers + twiddle table + k_verify's 16 x 16 correction table
-inline size_t verify_smem(int l) { return ring_smem(l) + (size_t)HWB * STAGE_HALF_BYTES + (size_t)TW_BYTES + (size_t)LANES * EPT * 4; }
+inline size_t ring_smem(int l, int threads = RBS) { return (size_t)l * AROW * 4 + (size_t)(threads / 32) * XWARP * 4; }
+// a_hat + transposition buffers + stage buffers + twiddle table (k_matvec; k_verify adds its 16 x 16 correction table)
+inline size_t matvec_smem(int l) { return ring_smem(l) + (size_t)HWB * STAGE_HALF_BYTES + (size_t)TW_BYTES; }
+inline size_t verify_smem(int l) {
+    return ring_smem(l, VBS) + (size_t)VHWB * STAGE_HALF_BYTES + (size_t)TW_BYTES + (size_t)LANES * EPT * 4;
+}
 
 template <typename K>
 cudaError_t allow_smem(K kernel, size_t smem) {
@@ -960,7 +974,7 @@ cudaError_t launch_poly_mul(const RingCtx& c, const int16_t* a, const int16_t* b
 cudaError_t launch_matvec(const RingCtx& c, const int16_t* vec_coef, int64_t nvec, uint16_t* vec_ntt,
                           uint16_t* y_ntt, int16_t* y_coef, cudaStream_t st) {
     if (nvec <= 0) return cudaSuccess;
-    size_t smem = verify_smem(c.l);
+    size_t smem = matvec_smem(c.l);
     cudaError_t e = allow_smem(k_matvec, smem);
     if (e != cudaSuccess) return e;
     unsigned grid = persistent_grid(nvec, HWB, c.num_sms, resident_blocks(k_matvec, RBS, smem));
@@ -989,8 +1003,8 @@ cudaError_t launch_verify_t(const RingCtx& c, const void* vec, const void* vk, c
     auto kern = wt < D ? k_verify<true, SIG_BITS, VK_BITS> : k_verify<false, SIG_BITS, VK_BITS>;
     cudaError_t e = allow_smem(kern, smem);
     if (e != cudaSuccess) return e;
-    unsigned grid = persistent_grid(n, HWB, c.num_sms, resident_blocks(kern, RBS, smem));
-    kern<<<grid, RBS, smem, st>>>(c.m, c.sc, c.scf, c.tab, c.a_hat, c.l, static_cast<const int16_t*>(vec),
+    unsigned grid = persistent_grid(n, VHWB, c.num_sms, resident_blocks(kern, VBS, smem));
+    kern<<<grid, VBS, smem, st>>>(c.m, c.sc, c.scf, c.tab, c.a_hat, c.l, static_cast<const int16_t*>(vec),
                                   static_cast<const uint16_t*>(vk), ch_pairs, ch_wt, rhs_only, extra_rhs, n, bd, wt,
                                   sig_bias, verdict);
     return cudaGetLastError();
