@@ -835,6 +835,10 @@ def engine_arm(a):
                                        f'{p["l"]} x 256 x 2 (bounds) + 512 (compare) int32 instructions per verify '
                                        f'(SURVEY.md 8d); peak = 148 SMs x 128 lanes x {peaks["sm_max_mhz"]:.0f} MHz',
                          'peak_source': peaks['source'] + ' sm_max_mhz',
+                         'note': 'frac = algorithmic work by the SURVEY 8(d) model / peak issue rate; it can exceed 1 because '
+                                 'the kernel needs fewer instructions than the model counts (4.5 instead of 8 per butterfly, '
+                                 'FP32-assisted multiplication and two-stage quadruples): the share of issue slots actually '
+                                 'used is executed.issue_slot_frac, the ncu counters are under ncu',
                          'kernel_ms_per_launch': k_ms, 'kernel_share_of_step': v_ms / total_ms,
                          'sampler_ms_per_launch': s_ms / max(s_n, 1),
                          'whole_step': {'algorithmic_instr_per_unit': step_instr,
