@@ -21,6 +21,13 @@ namespace {
 
 constexpr int RBS = 128;                 // threads per block
 constexpr int HWB = RBS / LANES;         // half-warps (work items) per block iteration
+#ifdef LCB_EXP_MBS
+constexpr int MBS = LCB_EXP_MBS;
+#else
+constexpr int MBS = 512;                 // threads per block of k_matvec: one key_ch copy per SM, as in k_verify (1.89 ->
+                                         // 1.78 ms for 2^17 keygen + witgen products)
+#endif
+constexpr int MHWB = MBS / LANES;
 
 struct HalfWarp {
     int lane;        // 0..15
@@ -219,7 +226,7 @@ __device__ __forceinline__ void fill_tw_shared(uint4* twtab, const NttTables* __
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(RBS, 4) k_matvec(ModQ m, StageConst sc, StageConstF scf, const NttTables* __restrict__ tab,
+__global__ void __launch_bounds__(MBS, 512 / MBS) k_matvec(ModQ m, StageConst sc, StageConstF scf, const NttTables* __restrict__ tab,
                                                 const uint32_t* __restrict__ a_hat_g, int l,
                                                 const int16_t* __restrict__ vec_coef, int64_t nvec,
                                                 uint16_t* __restrict__ vec_ntt, uint16_t* __restrict__ y_ntt,
@@ -238,7 +245,7 @@ constexpr int STAGE_HALF_BYTES = 2 * D * 2 + 32;   // two polynomials + 32 B so 
 // Coefficient-form rows reach k_matvec the way they reach k_verify: through a 2-deep cp.async pipeline per half-warp
 // and conflict-free 16-bit shared loads.  (Round 1 read them with 16 strided 2-byte global loads per lane: 35 % of
 // the warp samples sat on the long scoreboard.)
-__global__ void __launch_bounds__(RBS, 4) k_matvec(ModQ m, StageConst sc, StageConstF scf, const NttTables* __restrict__ tab,
+__global__ void __launch_bounds__(MBS, 512 / MBS) k_matvec(ModQ m, StageConst sc, StageConstF scf, const NttTables* __restrict__ tab,
                                                 const uint32_t* __restrict__ a_hat_g, int l,
                                                 const int16_t* __restrict__ vec_coef, int64_t nvec,
                                                 uint16_t* __restrict__ vec_ntt, uint16_t* __restrict__ y_ntt,
@@ -248,12 +255,12 @@ __global__ void __launch_bounds__(RBS, 4) k_matvec(ModQ m, StageConst sc, StageC
     uint32_t* xbuf = smem + l * AROW;
     copy_a_hat(a_hat, a_hat_g, l);
     const HalfWarp h = half_warp(xbuf);
-    unsigned char* stage_base = reinterpret_cast<unsigned char*>(xbuf + (RBS / 32) * XWARP);
+    unsigned char* stage_base = reinterpret_cast<unsigned char*>(xbuf + (MBS / 32) * XWARP);
     unsigned char* stage = stage_base + h.slot * STAGE_HALF_BYTES;
-    uint4* twtab = reinterpret_cast<uint4*>(stage_base + HWB * STAGE_HALF_BYTES);
+    uint4* twtab = reinterpret_cast<uint4*>(stage_base + MHWB * STAGE_HALF_BYTES);
     fill_tw_shared(twtab, tab);
     const LaneTwFShared twf{twtab + h.lane * TW_ROW};
-    const int64_t first = (int64_t)blockIdx.x * HWB, stride = (int64_t)gridDim.x * HWB;
+    const int64_t first = (int64_t)blockIdx.x * MHWB, stride = (int64_t)gridDim.x * MHWB;
     const int64_t trips = first < nvec ? (nvec - first + stride - 1) / stride : 0;   // uniform over the block
     int pf_left = (int)trips;                   // running-pointer prefetch cursor, see k_verify
     int pf_i = 0;
@@ -930,7 +937,7 @@ inline unsigned persistent_grid(int64_t items, int per_block, int num_sms, int r
 
 inline size_t ring_smem(int l, int threads = RBS) { return (size_t)l * AROW * 4 + (size_t)(threads / 32) * XWARP * 4; }
 // a_hat + transposition buffers + stage buffers + twiddle table (k_matvec; k_verify adds its 16 x 16 correction table)
-inline size_t matvec_smem(int l) { return ring_smem(l) + (size_t)HWB * STAGE_HALF_BYTES + (size_t)TW_BYTES; }
+inline size_t matvec_smem(int l) { return ring_smem(l, MBS) + (size_t)MHWB * STAGE_HALF_BYTES + (size_t)TW_BYTES; }
 inline size_t verify_smem(int l) {
     return ring_smem(l, VBS) + (size_t)VHWB * STAGE_HALF_BYTES + (size_t)TW_BYTES + (size_t)LANES * EPT * 4;
 }
@@ -977,8 +984,8 @@ cudaError_t launch_matvec(const RingCtx& c, const int16_t* vec_coef, int64_t nve
     size_t smem = matvec_smem(c.l);
     cudaError_t e = allow_smem(k_matvec, smem);
     if (e != cudaSuccess) return e;
-    unsigned grid = persistent_grid(nvec, HWB, c.num_sms, resident_blocks(k_matvec, RBS, smem));
-    k_matvec<<<grid, RBS, smem, st>>>(c.m, c.sc, c.scf, c.tab, c.a_hat, c.l, vec_coef, nvec, vec_ntt, y_ntt, y_coef);
+    unsigned grid = persistent_grid(nvec, MHWB, c.num_sms, resident_blocks(k_matvec, MBS, smem));
+    k_matvec<<<grid, MBS, smem, st>>>(c.m, c.sc, c.scf, c.tab, c.a_hat, c.l, vec_coef, nvec, vec_ntt, y_ntt, y_coef);
     return cudaGetLastError();
 }
 
