@@ -109,7 +109,8 @@ struct LaneTwF {                // per-lane stages 5..8, same indexing as LaneTw
 // Which one wins depends on what binds the kernel (measured, round 2): k_sign sat at 86 % of the L1/shared-memory
 // pipeline with 31 twiddle rows per polynomial as 63 % of its wavefronts (mio-throttle + short-scoreboard = 33 % of the
 // warp samples) and gains 4.6 % from the short rows (6.36 -> 6.07 ms per 2^20); k_verify (15 rows per polynomial, 80 % of
-// the pipeline but 71 % issue-active) loses 5 % to the 30 extra instructions per row (4.20 -> 4.42 ms) and keeps the long rows.
+// the pipeline but 71 % issue-active) loses 5 % to the 30 extra instructions per row (4.20 -> 4.42 ms) and keeps the long rows
+// (re-tried on the 512-thread form, 89 % of the pipeline and 77 % issue-active: 3.87 -> 4.13 ms, still a loss).
 struct LaneTwFShared {
     const uint4* row;
     __device__ __forceinline__ void get(int k, uint32_t& w_, float& wq_, float& cst_, uint32_t& kw_) const {
