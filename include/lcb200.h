@@ -133,7 +133,8 @@ int lcb_lm_sign_batch(lcb_ctx* ctx, const lcb_scheme* sch, const uint16_t* sk_nt
  * st_ntt may be NULL (LM verify, preverify) or uint16[n][d] (adaptor verify).
  * The bound is tested on the int16 values AS GIVEN: coefficient-form inputs MUST be centred residues (what every
  * engine entry point emits and what the reference's get_coef_rep() returns).  A non-canonical representative
- * such as x + q is not re-centred first; it fails the bound (verdict 0) whenever |x + q| > bd. */
+ * such as x + q is not re-centred first; it fails the bound (verdict 0) whenever |x + q| > bd.
+ * At most 2^30 items per call (LCB_ERR_INVALID beyond; the same for the packed and the witness-verify entry points). */
 int lcb_lm_verify_batch(lcb_ctx* ctx, const lcb_scheme* sch, const uint16_t* vk_ntt, const uint8_t* chmsg,
                         const int64_t* chmsg_off, const int16_t* sig, const uint16_t* st_ntt, int64_t n,
                         int bd, int wt, uint8_t* verdict);

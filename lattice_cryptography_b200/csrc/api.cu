@@ -1039,6 +1039,7 @@ int lcb_lm_verify_batch(lcb_ctx* c, const lcb_scheme* sch, const uint16_t* vk_nt
     LCB_RANGE();
     if (!c || !sch || !vk_ntt || !chmsg_off || !sig || !verdict || n < 0 || bd < 0 || wt < 0) return LCB_ERR_INVALID;
     if (!c->has_key_ch) return fail(c, LCB_ERR_NO_KEY_CH, "lcb_lm_verify_batch before lcb_set_key_ch");
+    if (n > ((int64_t)1 << 30)) return fail(c, LCB_ERR_INVALID, "more than 2^30 items in one verify call");
     if (n == 0) return LCB_OK;
     CK(c, cudaSetDevice(c->device));
     const int l = c->l;
@@ -1143,6 +1144,7 @@ int lcb_lm_verify_packed_batch(lcb_ctx* c, const lcb_scheme* sch, const uint8_t*
         return LCB_ERR_INVALID;
     if (c->generic) return fail(c, LCB_ERR_INVALID, "the packed wire format is defined for d == 256, q < 2^16 contexts only");
     if (!c->has_key_ch) return fail(c, LCB_ERR_NO_KEY_CH, "lcb_lm_verify_packed_batch before lcb_set_key_ch");
+    if (n > ((int64_t)1 << 30)) return fail(c, LCB_ERR_INVALID, "more than 2^30 items in one verify call");
     if (n == 0) return LCB_OK;
     CK(c, cudaSetDevice(c->device));
     const int l = c->l;
@@ -1430,6 +1432,7 @@ int lcb_adaptor_witness_verify_batch(lcb_ctx* c, const int16_t* wit_coef, const 
     LCB_RANGE();
     if (!c || !wit_coef || !st_ntt || !verdict || n < 0 || bd < 0 || wt < 0) return LCB_ERR_INVALID;
     if (!c->has_key_ch) return fail(c, LCB_ERR_NO_KEY_CH, "lcb_adaptor_witness_verify_batch before lcb_set_key_ch");
+    if (n > ((int64_t)1 << 30)) return fail(c, LCB_ERR_INVALID, "more than 2^30 items in one verify call");
     if (n == 0) return LCB_OK;
     CK(c, cudaSetDevice(c->device));
     Staging sg(c);
