@@ -397,17 +397,21 @@ __global__ void __launch_bounds__(RBS, SIGN_BLOCKS) k_sign(ModQ m, StageConstF s
     int pf_i = 0;
     int64_t pf_item = first + h.slot;
     const int64_t item_bytes = (int64_t)2 * l * D * 2, right_off = (int64_t)l * D * 2;
-    const unsigned char* const rows_base = reinterpret_cast<const unsigned char*>(sk_ntt) + 32 * h.lane;
+    // The split layout (load_u16x16_smem) puts 16-byte chunk j of a row at (j & 1) * 256 + (j >> 1) * 16.  A lane copies
+    // chunks `lane` and `16 + lane`, so that one cp.async instruction reads 256 CONTIGUOUS bytes of the row (the first
+    // version had lane t copy its own chunks 2t and 2t + 1: every instruction touched 16 bytes of 16 different sectors and
+    // ncu counted 32 shared-memory wavefronts per instruction instead of 7 - half of the kernel's shared traffic).
+    const unsigned char* const rows_base = reinterpret_cast<const unsigned char*>(sk_ntt) + 16 * h.lane;
     const unsigned char* src = rows_base + (pf_item < n ? pf_item : n - 1) * item_bytes;
-    const unsigned dst0 = (unsigned)__cvta_generic_to_shared(stage) + 16u * (unsigned)h.lane;   // split layout, see load_u16x16_smem
+    const unsigned dst0 = (unsigned)__cvta_generic_to_shared(stage) + (unsigned)((h.lane & 1) * D + (h.lane >> 1) * 16);
     unsigned pf_off = 0;
     auto issue = [&]() {
         if (pf_left > 0) {
             const unsigned d = dst0 + pf_off;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + D), "l"(src + 16) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 128), "l"(src + D) : "memory");
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 2 * D), "l"(src + right_off) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 3 * D), "l"(src + right_off + 16) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 2 * D + 128), "l"(src + right_off + D) : "memory");
             src += D * 2;
             pf_off ^= (unsigned)(2 * D * 2);
             if (++pf_i == l) {
